@@ -1,0 +1,282 @@
+"""CPU oracle for the HPCS hot path (kNN graph, Poincare triplet objective, linkage decode).
+
+TEST INFRASTRUCTURE ONLY -- never imported by the product package ``hpcs_b200``.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline / ``--impl reference`` legs may use it.
+
+Each function restates, in plain PyTorch / numpy / scipy, what the reference computes; the
+docstring names the reference file:line it follows (paths relative to ``/root/reference``).  All
+functions are dtype-generic: feed ``float64`` tensors to get the fp64 evaluation that SURVEY.md
+(Finding 4) defines as the parity target for distances, losses and gradients.
+
+PARITY PIN: the reference ships no golden vectors.  The oracle is pinned
+instead against outputs of the reference itself, executed unmodified in the build container by
+``oracle/make_golden.py`` and committed under ``tests/golden/`` (checked by
+``tests/test_oracle_golden.py``).  scipy (``scipy.cluster.hierarchy.linkage``) is the reference's
+own third-party decoder (``hpcs-env.yaml:302`` pins 1.9.1; 1.18.1 in this image) and is called
+directly.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+MIN_NORM = 1e-15                       # hpcs/distances/poincare.py:9
+BALL_EPS = {torch.float32: 4e-3, torch.float64: 1e-5}   # hpcs/distances/poincare.py:10
+ARTANH_CLAMP = 1e-5                    # hpcs/utils/math.py:64
+SCALE_MIN, SCALE_MAX = 1e-4, 1.0       # hpcs/loss/ultrametric_loss.py:141-143
+
+
+# --------------------------------------------------------------------------------------------
+# part 1: kNN graph + edge features
+# --------------------------------------------------------------------------------------------
+def knn_reference(x: torch.Tensor, k: int) -> torch.Tensor:
+    """``knn`` as the reference evaluates it (hpcs/nn/dgcnn/utils/vn_dgcnn_util.py:4-10).
+
+    x[B,D,N] -> idx[B,N,k] int64: top-k of ``-|xi|^2 + 2 xi.xj - |xj|^2`` per row (self included),
+    using torch's matmul/topk, i.e. with whatever accumulation order and tie order they pick.
+    """
+    gram = torch.matmul(x.transpose(2, 1), x)
+    sq = (x * x).sum(dim=1, keepdim=True)
+    neg_d2 = -sq - (-2 * gram) - sq.transpose(2, 1)
+    return neg_d2.topk(k=k, dim=-1)[1]
+
+
+def neg_sqdist_fp64(x: torch.Tensor) -> torch.Tensor:
+    """Exact-ish ``-|xi-xj|^2`` in fp64 from fp32 inputs; used to grade near-ties (Finding 5)."""
+    xd = x.double()
+    diff = xd.unsqueeze(3) - xd.unsqueeze(2)          # [B,D,N,N]
+    return -(diff * diff).sum(dim=1)
+
+
+_KNN_LIB = None
+
+
+def _knn_lib():
+    global _KNN_LIB
+    if _KNN_LIB is None:
+        here = os.path.dirname(os.path.abspath(__file__))
+        path = os.path.join(here, "_build", "libknn_canonical.so")
+        if not os.path.exists(path):
+            from . import build_oracle
+            build_oracle.build()
+        lib = ctypes.CDLL(path)
+        lib.knn_canonical_f32.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                          ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        lib.knn_canonical_f32.restype = ctypes.c_int
+        _KNN_LIB = lib
+    return _KNN_LIB
+
+
+def knn_canonical(x: torch.Tensor, k: int, return_values: bool = False):
+    """Canonical-order kNN (C restatement in ``oracle/knn_canonical.c``).
+
+    Same quantity as vn_dgcnn_util.py:5-9, evaluated in fp32 with ONE fixed operation order
+    (fma chain over d ascending) and the stated tie-break (larger value first, then lower index).
+    This is the bit-exact target of the CUDA kernel.
+    """
+    assert x.dtype == torch.float32 and x.dim() == 3
+    xc = x.detach().cpu().contiguous()
+    B, D, N = xc.shape
+    idx = torch.empty(B, N, k, dtype=torch.int64)
+    val = torch.empty(B, N, k, dtype=torch.float32)
+    rc = _knn_lib().knn_canonical_f32(xc.data_ptr(), B, D, N, k, idx.data_ptr(), val.data_ptr())
+    if rc != 0:
+        raise RuntimeError(f"knn_canonical_f32 failed: {rc}")
+    return (idx, val) if return_values else idx
+
+
+def graph_feature(x: torch.Tensor, k: int = 20, idx: Optional[torch.Tensor] = None,
+                  x_coord: Optional[torch.Tensor] = None, cross: bool = False,
+                  knn_fn=knn_reference) -> torch.Tensor:
+    """Edge features (vn_dgcnn_util.py:13-41; cross variant :44-69).
+
+    x[B,C,3,N] -> [B,2C,3,N,k] = cat(x_j - x_i, x_i) over vector channels (+ cross(x_j, x_i) ->
+    3C channels when ``cross``).  Written with plain gathers; differentiable wrt x.
+    """
+    B, C, _, N = x.shape
+    flat = x.reshape(B, C * 3, N)
+    if idx is None:
+        idx = knn_fn(flat if x_coord is None else x_coord, k)
+    rows = flat.transpose(1, 2)                                         # [B,N,3C]
+    nbr = torch.gather(rows.unsqueeze(1).expand(B, N, N, 3 * C), 2,
+                       idx.unsqueeze(-1).expand(B, N, k, 3 * C))        # [B,N,k,3C]
+    nbr = nbr.reshape(B, N, k, C, 3)
+    ctr = rows.reshape(B, N, 1, C, 3).expand(B, N, k, C, 3)
+    parts = [nbr - ctr, ctr]
+    if cross:
+        parts.append(torch.cross(nbr, ctr, dim=-1))
+    return torch.cat(parts, dim=3).permute(0, 3, 4, 1, 2).contiguous()
+
+
+# --------------------------------------------------------------------------------------------
+# part 2: Poincare math, hyperbolic LCA, triplet objective
+# --------------------------------------------------------------------------------------------
+class _Artanh(torch.autograd.Function):
+    """hpcs/utils/math.py:61-74: clamp to +-(1-1e-5), forward in double, backward g/(1-x_c^2)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        xc = x.clamp(-1 + ARTANH_CLAMP, 1 - ARTANH_CLAMP)
+        ctx.save_for_backward(xc)
+        z = xc.double()
+        return (0.5 * (torch.log1p(z) - torch.log1p(-z))).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        (xc,) = ctx.saved_tensors
+        return g / (1 - xc * xc)
+
+
+def artanh(x):
+    return _Artanh.apply(x)
+
+
+def tanh_clamped(x):
+    """hpcs/utils/math.py:81-82."""
+    return x.clamp(-15, 15).tanh()
+
+
+def expmap0(u: torch.Tensor) -> torch.Tensor:
+    """``ExpMap.forward`` = ``expmap_1(u, 0)`` (hpcs/nn/hyperbolic/hyp_embed.py:6-10,
+    hpcs/utils/poincare.py:50-54,79-86).  With p = 0 the conformal factor is 2 and the Moebius
+    addition ``0 (+) y`` is ``y / max(1, MIN_NORM)``."""
+    nrm = u.norm(dim=-1, p=2, keepdim=True).clamp_min(MIN_NORM)
+    y = tanh_clamped(2.0 * nrm / 2) * u / nrm
+    p = torch.zeros_like(u)
+    return mobius_add(p, y)
+
+
+def mobius_add(x, y):
+    """hpcs/utils/poincare.py:79-86 (same body: hpcs/distances/poincare.py:71-78)."""
+    x2 = (x * x).sum(-1, keepdim=True)
+    y2 = (y * y).sum(-1, keepdim=True)
+    xy = (x * y).sum(-1, keepdim=True)
+    top = (1 + 2 * xy + y2) * x + (1 - x2) * y
+    return top / (1 + 2 * xy + x2 * y2).clamp_min(MIN_NORM)
+
+
+def project(x):
+    """hpcs/distances/poincare.py:61-68."""
+    nrm = x.norm(dim=-1, p=2, keepdim=True).clamp_min(MIN_NORM)
+    lim = 1 - BALL_EPS[x.dtype]
+    return torch.where(nrm > lim, x / nrm * lim, x)
+
+
+def hyp_dist_o(x):
+    """hpcs/distances/poincare.py:131-136."""
+    return 2 * artanh(x.norm(dim=-1, p=2, keepdim=True))
+
+
+def _invert(center, x):
+    """Circle inversion through the circle centred at ``center`` orthogonal to the unit sphere
+    (hpcs/distances/lca.py:8-12)."""
+    rad2 = (center * center).sum(-1, keepdim=True) - 1.0
+    u = x - center
+    return rad2 / (u * u).sum(-1, keepdim=True) * u + center
+
+
+def hyp_lca(a, b, return_coord: bool = True):
+    """Projection of the origin on the geodesic through a and b (hpcs/distances/lca.py:37-52,
+    helpers :15-34)."""
+    r = a / (a * a).sum(-1, keepdim=True)                              # :15-17
+    b_inv = _invert(r, b)                                              # :44
+    # reflect a across the line through the origin and b_inv (:20-29)
+    dot = (a * b_inv).sum(-1, keepdim=True)
+    nb = (b_inv * b_inv).sum(-1, keepdim=True).clamp_min(MIN_NORM)
+    a_ref = 2 * (dot * b_inv / nb) - a
+    o_ref = _invert(r, a_ref)                                          # :47
+    proj = o_ref / (1.0 + torch.sqrt(1 - (o_ref * o_ref).sum(-1, keepdim=True)))   # :32-34
+    return proj if return_coord else hyp_dist_o(proj)
+
+
+def cosine_similarity_matrix(q, r=None):
+    """``CosineSimilarity()(q, r)`` (hpcs/distances/cosine.py:4-16 on PML ``BaseDistance``:
+    rows are L2-normalised with ``F.normalize`` eps 1e-12 first)."""
+    qn = F.normalize(q, p=2, dim=1)
+    rn = qn if r is None else F.normalize(r, p=2, dim=1)
+    return 0.5 * (1 + qn @ rn.t())
+
+
+def normalize_embeddings(e, scale):
+    """hpcs/loss/ultrametric_loss.py:139-143."""
+    return F.normalize(e, p=2, dim=1) * torch.clamp(scale, SCALE_MIN, SCALE_MAX)
+
+
+def sample_triplets(labels: torch.Tensor, t_per_anchor: int, fraction: float
+                    ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Class-balanced random triplets (hpcs/miner/loss_and_miner_utils.py:7-75, ``ref_labels is
+    labels`` and ``weights is None`` branch).  Consumes the global torch CPU RNG in the same
+    order as the reference (one ``randint`` for positives, one for negatives, per label in
+    ascending label order), so a common seed yields identical triplets."""
+    lab = labels.cpu()
+    counts = torch.bincount(lab)
+    biggest = counts.max()
+    out_a, out_p, out_n = [], [], []
+    for value in torch.unique(lab):
+        members = torch.nonzero(lab == value, as_tuple=True)[0]
+        others = torch.nonzero(lab != value, as_tuple=True)[0]
+        m = members.numel()
+        if m < 2 or others.numel() < 1:
+            continue
+        per_anchor = int(t_per_anchor * torch.pow(biggest / m, fraction))     # :30
+        total = m * per_anchor
+        draw_p = torch.randint(0, m - 1, (total,))                            # :38
+        anchor_pos = torch.arange(m).repeat_interleave(per_anchor)            # :40
+        # the reference removes the diagonal of an m x m table; skipping slot ``anchor_pos``:
+        pos_pos = draw_p + (draw_p >= anchor_pos).long()
+        draw_n = torch.randint(0, others.numel(), (total,))                   # :61
+        out_a.append(members[anchor_pos])
+        out_p.append(members[pos_pos])
+        out_n.append(others[draw_n])
+    if not out_a:
+        e = torch.empty(0, dtype=torch.long, device=labels.device)
+        return e, e.clone(), e.clone()
+    dev = labels.device
+    return torch.cat(out_a).to(dev), torch.cat(out_p).to(dev), torch.cat(out_n).to(dev)
+
+
+def filter_triplets(x, a, p, n, margin: float = 0.0, kind: str = "easy"):
+    """``RandomTripletMarginMiner.mine`` after sampling (hpcs/miner/triplet_margin_miner.py:16-38);
+    the similarity is inverted, so the margin is ``sim(a,p) - sim(a,n)``."""
+    with torch.no_grad():
+        mat = cosine_similarity_matrix(x)
+        gap = mat[a, p] - mat[a, n]
+        if kind == "easy":
+            keep = gap > margin
+        else:
+            keep = gap <= margin
+            if kind == "hard":
+                keep &= gap <= 0
+            elif kind == "semihard":
+                keep &= gap > 0
+    return a[keep], p[keep], n[keep]
+
+
+def compute_hyp(x, a, p, n, scale, temperature: float):
+    """``MetricHyperbolicLoss.compute_hyp`` after mining (hpcs/loss/ultrametric_loss.py:64-93):
+    dense similarity matrix, three LCA distances per triplet, softmax-weighted HypHC loss plus
+    the mean of the similarity matrix."""
+    sim = cosine_similarity_matrix(x)                                   # :65
+    w = torch.stack([sim[a, p], sim[a, n], sim[p, n]], dim=-1)          # :67-69,:84
+    ea, ep, en = (normalize_embeddings(x[i], scale) for i in (a, p, n))  # :71-77
+    d = torch.cat([hyp_lca(ea, ep, False), hyp_lca(ea, en, False), hyp_lca(ep, en, False)], dim=-1)
+    soft = torch.softmax(d / temperature, dim=-1)                       # :86
+    per_triplet = w.sum(-1) - (w * soft).sum(-1)                        # :88-89
+    return per_triplet.mean() + sim.mean()                              # :91
+
+
+# --------------------------------------------------------------------------------------------
+# part 3: linkage decode
+# --------------------------------------------------------------------------------------------
+def decode_linkage(x: torch.Tensor, scale: torch.Tensor, method: str = "complete") -> np.ndarray:
+    """``BaseSimilarityHypHC._decode_linkage`` (hpcs/models/base_hyp_hc.py:81-86): rescale to the
+    common radius, project, go to CPU, scipy ``linkage(metric='cosine')``.  ``method='complete'``
+    is what the reference ships; ``'single'`` is the HypHC-paper decoder named by north_star."""
+    from scipy.cluster.hierarchy import linkage
+    e = project(normalize_embeddings(x, scale)).detach().cpu()
+    return linkage(e.numpy(), method=method, metric="cosine")
