@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""bench.py -- point clouds/s through the HPCS hot path (fwd+bwd), one process per GPU.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload train|decode]
+
+Workload (BASELINE.json configs[1]): ShapeNet-shaped training step, batch 32 clouds x 1024 points per
+GPU, k=20, 32-d embeddings, 50 mined triplets per anchor.  One "step" is one pass of the hot path over
+one batch of synthetic input:
+    kNN(D=3)  -> edge features C=1  fwd+bwd      (vn_dgcnn_partseg.py:65)
+    kNN(D=63) -> edge features C=21 fwd+bwd  x2  (vn_dgcnn_partseg.py:70,75)
+    fused Poincare triplet loss fwd+bwd over 1.64 M mined triplets ('easy' filter in-kernel)
+The dense VN/conv layers between these ops are outside the path, so the inputs of
+the 63-d layers, the upstream gradients of the edge features and the embeddings are synthetic tensors.
+Clouds are independent: ranks own disjoint batches (weak scaling); the only collective is the
+all-reduce of the `scale` gradient, the one trainable parameter on this path.
+
+`value`   : clouds/s with every input resident in HBM (CUDA events, max over ranks).
+`e2e`     : same step through the public API from pinned HOST buffers: H2D of the step's inputs and D2H
+            of its results (loss, kept, d scale, input gradients) inside the timed region.
+`roofline`: the kernel with the largest share of the step; per-op figures under "ops".
+`--impl reference`: the oracle's restatement of the reference's PyTorch CPU path, on host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+B_PER_GPU, N_PTS, K_NN, C_FEAT, D_EMB, T_PER_ANCHOR = 32, 1024, 20, 21, 32, 50
+SCALE, TEMPERATURE = 1e-3, 0.05
+METRIC = "point clouds/sec (1024 pts, k=20) fwd+bwd"
+UNIT = "clouds/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p.get("bf16_tflops"), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback"}
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic ShapeNet-shaped inputs
+# ------------------------------------------------------------------------------------------------
+def synth_inputs(B, seed):
+    gen = torch.Generator().manual_seed(seed)
+    pts = torch.randn(B, N_PTS, 3, generator=gen)
+    pts = pts - pts.mean(1, keepdim=True)
+    pts = (pts / pts.norm(dim=-1).amax(1).view(B, 1, 1)).transpose(1, 2).contiguous().view(B, 1, 3, N_PTS)
+    f1 = torch.randn(B, C_FEAT, 3, N_PTS, generator=gen)
+    f2 = torch.randn(B, C_FEAT, 3, N_PTS, generator=gen)
+    u = torch.randn(B * N_PTS, D_EMB, generator=gen)
+    nrm = u.norm(dim=-1, keepdim=True)
+    emb = torch.tanh(nrm.clamp(max=15)) * u / nrm                    # ExpMap(N(0,1))
+    # labels: one of 16 categories per cloud, 2-6 parts each, Dirichlet(1) proportions, global ids 0..49
+    labels = []
+    for b in range(B):
+        cat = int(torch.randint(0, 16, (1,), generator=gen))
+        parts = 2 + int(torch.randint(0, 5, (1,), generator=gen))
+        probs = torch._sample_dirichlet(torch.ones(parts), generator=gen)
+        labels.append(torch.multinomial(probs, N_PTS, replacement=True, generator=gen) + (cat * 3) % 45)
+    labels = torch.cat(labels)
+    return {"pts": pts, "f1": f1, "f2": f2, "emb": emb, "labels": labels}
+
+
+def algorithmic_work(B):
+    """Per-op algorithmic bytes / flops (DESIGN.md 'Kernels and rooflines')."""
+    n = B * N_PTS
+    E = N_PTS * K_NN
+    T0 = T_PER_ANCHOR * n
+
+    def edge(C):
+        out = B * 2 * C * 3 * E * 4
+        return out + B * 3 * C * N_PTS * 4 + B * E * 8, out + B * E * 8 + B * 3 * C * N_PTS * 4
+
+    e1f, e1b = edge(1)
+    e21f, e21b = edge(C_FEAT)
+    return {
+        "knn_d3": {"flop": B * N_PTS * N_PTS * 9.0, "bytes": B * (12 * N_PTS + 8 * E)},
+        "knn_d63": {"flop": B * N_PTS * N_PTS * (2 * 63 + 3.0), "bytes": B * (252 * N_PTS + 8 * E)},
+        "edge_fwd_c1": {"bytes": e1f}, "edge_bwd_c1": {"bytes": e1b},
+        "edge_fwd_c21": {"bytes": e21f}, "edge_bwd_c21": {"bytes": e21b},
+        "hyp_loss_fwd_bwd": {"flop": T0 * 2100.0, "bytes": T0 * 24.0 + 3 * n * D_EMB * 4},
+    }
+
+
+class ClockSampler(threading.Thread):
+    """SM clock / throttle reasons during the timed region (nvml; one sample every 50 ms)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+            }
+            while not self._stop_evt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                self._stop_evt.wait(0.05)
+        except Exception as exc:                                # nvml missing: report, do not fail the bench
+            self.reasons.add(f"nvml_unavailable:{type(exc).__name__}")
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+# native arm
+# ------------------------------------------------------------------------------------------------
+def run_native(args):
+    import hpcs_b200 as hb
+    from hpcs_b200 import _lib, dist as hdist
+    import torch.distributed as dist
+
+    rank, world, local = hdist.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (native arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B = B_PER_GPU
+    host = synth_inputs(B, seed=rank)
+    torch.manual_seed(1000 + rank)
+    trip_host = hb.get_balanced_random_triplet_indices(host["labels"], t_per_anchor=T_PER_ANCHOR, fraction=0.0)
+    T0 = trip_host[0].numel()
+
+    d = {k: v.to(dev) for k, v in host.items()}
+    trip = tuple(t.to(dev) for t in trip_host)
+    scale = torch.tensor([SCALE], device=dev, requires_grad=True)
+    gen = torch.Generator(device=dev).manual_seed(rank)
+    E = N_PTS * K_NN
+    g1 = torch.randn(B, 2, 3, N_PTS, K_NN, device=dev, generator=gen)
+    g2 = torch.randn(B, 2 * C_FEAT, 3, N_PTS, K_NN, device=dev, generator=gen)
+    g3 = torch.randn(B, 2 * C_FEAT, 3, N_PTS, K_NN, device=dev, generator=gen)
+
+    op_names = ["knn_d3", "edge_fwd_c1", "edge_bwd_c1", "knn_d63", "edge_fwd_c21", "edge_bwd_c21", "hyp_loss_fwd_bwd"]
+    op_events = {n: [] for n in op_names}
+
+    def timed(name, fn, record):
+        if not record:
+            return fn()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        out = fn()
+        e.record()
+        op_events[name].append((s, e))
+        return out
+
+    def layer(x, g, tag_knn, tag_f, tag_b, record):
+        xr = x.detach().requires_grad_(True)
+        Bc, C, _, Np = xr.shape
+        idx = timed(tag_knn, lambda: hb.knn(xr.detach().view(Bc, 3 * C, Np), K_NN), record)
+        y = timed(tag_f, lambda: hb.get_graph_feature(xr, K_NN, idx=idx), record)
+        (gx,) = timed(tag_b, lambda: torch.autograd.grad(y, xr, g), record)
+        return gx
+
+    def step(inp, tr, record=False):
+        gx1 = layer(inp["pts"], g1, "knn_d3", "edge_fwd_c1", "edge_bwd_c1", record)
+        gx2 = layer(inp["f1"], g2, "knn_d63", "edge_fwd_c21", "edge_bwd_c21", record)
+        gx3 = layer(inp["f2"], g3, "knn_d63", "edge_fwd_c21", "edge_bwd_c21", record)
+        emb = inp["emb"].detach().requires_grad_(True)
+
+        def loss_fb():
+            loss, kept = hb.hyp_triplet_loss(emb, tr, scale, TEMPERATURE, "easy", 0.0, return_kept=True)
+            ge, gs = torch.autograd.grad(loss, (emb, scale))
+            return loss, kept, ge, gs
+        loss, kept, ge, gs = timed("hyp_loss_fwd_bwd", loss_fb, record)
+        if world > 1:
+            dist.all_reduce(gs, op=dist.ReduceOp.SUM)           # d loss / d scale: the path's only parameter
+            gs = gs / world
+        return loss, kept, gs, (gx1, gx2, gx3, ge)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident-input timing ------------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        out = step(d, trip)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = _lib.launch_count()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        out = step(d, trip, record=True)
+    t1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    clocks = sampler.stop()
+    ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = ms.item() / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+    loss_val, kept_val = float(out[0]), int(out[1])
+
+    # ---- end-to-end from pinned host buffers ----------------------------------------------------
+    pin = {k: host[k].pin_memory() for k in ("pts", "f1", "f2", "emb")}
+    trip_pin = tuple(t.pin_memory() for t in trip_host)
+    h2d_bytes = sum(v.numel() * v.element_size() for v in pin.values()) + sum(t.numel() * 8 for t in trip_pin)
+    res_host = None
+
+    def e2e_step():
+        inp = {k: v.to(dev, non_blocking=True) for k, v in pin.items()}
+        tr = tuple(t.to(dev, non_blocking=True) for t in trip_pin)
+        loss, kept, gs, grads = step(inp, tr)
+        outs = [loss.reshape(1), kept.reshape(1).float(), gs.reshape(1)] + [g.reshape(-1) for g in grads]
+        return [o.to("cpu", non_blocking=True) for o in outs]
+
+    for _ in range(3):
+        res_host = e2e_step()
+    barrier()
+    d2h_bytes = sum(o.numel() * o.element_size() for o in res_host)
+    t0.record()
+    for _ in range(args.steps):
+        res_host = e2e_step()
+    t1.record()
+    barrier()
+    ms_e = torch.tensor([t0.elapsed_time(t1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
+    e2e_value = world * B / (ms_e.item() / args.steps * 1e-3)
+
+    if rank != 0:
+        return
+    pk = peaks()
+    work = algorithmic_work(B)
+    ops = {}
+    for name in op_names:
+        evs = op_events[name]
+        if not evs:
+            continue
+        avg_ms = sum(s.elapsed_time(e) for s, e in evs) / len(evs)
+        calls_per_step = len(evs) / args.steps
+        w = work[name]
+        ent = {"ms": round(avg_ms, 4), "calls_per_step": calls_per_step,
+               "share": round(avg_ms * calls_per_step / ms_per_step, 4)}
+        if name.startswith("edge"):
+            ent.update(bound="hbm", achieved=round(w["bytes"] / (avg_ms * 1e-3) / 1e9, 1), peak=pk["hbm_gbs"], unit="GB/s")
+        else:
+            ent.update(bound="fp32-alu", achieved=round(w["flop"] / (avg_ms * 1e-3) / 1e12, 3), peak=None, unit="TFLOP/s")
+        if ent["peak"]:
+            ent["frac"] = round(ent["achieved"] / ent["peak"], 4)
+        ops[name] = ent
+    top = max((n for n in ops if ops[n].get("peak")), key=lambda n: ops[n]["share"])
+    roofline = {"kernel": top, "bound": ops[top]["bound"], "achieved": ops[top]["achieved"], "peak": ops[top]["peak"],
+                "unit": ops[top]["unit"], "frac": ops[top]["frac"], "traffic": None, "peak_source": pk["source"]}
+    line = {
+        "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "shapenet_train_step_b32_n1024_k20_d32_t50 (BASELINE.json configs[1])",
+                   "clouds_per_gpu": B, "points": N_PTS, "k": K_NN, "feat_channels": [1, C_FEAT, C_FEAT],
+                   "emb_dim": D_EMB, "triplets_mined": T0, "triplets_kept": kept_val, "filter": "easy",
+                   "scale": SCALE, "temperature": TEMPERATURE, "parallelism": f"dp{world}",
+                   "l2": "per-step working set ~1.4 GB (edge-feature tensors) exceeds the 126 MB L2; no explicit flush"},
+        "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
+                "d2h_bytes_per_step": int(d2h_bytes)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": roofline,
+        "ops": ops,
+        "loss": loss_val,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_reference_pass(steps=2, warmup=1)
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle's restatement of the reference's PyTorch path on host cores
+# ------------------------------------------------------------------------------------------------
+CPU_SAMPLE_B = 8
+
+
+def cpu_reference_pass(steps, warmup):
+    from oracle import hpcs_oracle as O
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B = CPU_SAMPLE_B
+    host = synth_inputs(B, seed=0)
+    torch.manual_seed(1000)
+    trip = O.sample_triplets(host["labels"], T_PER_ANCHOR, 0.0)
+    gen = torch.Generator().manual_seed(0)
+    gs = [torch.randn(B, 2 * c, 3, N_PTS, K_NN, generator=gen) for c in (1, C_FEAT, C_FEAT)]
+    scale = torch.tensor([SCALE], requires_grad=True)
+
+    def one():
+        for x, g in zip((host["pts"], host["f1"], host["f2"]), gs):
+            xr = x.clone().requires_grad_(True)
+            y = O.graph_feature(xr, K_NN)                           # reference knn + gather/cat/permute
+            torch.autograd.grad(y, xr, g)
+        emb = host["emb"].clone().requires_grad_(True)
+        a, p, n = O.filter_triplets(emb.detach(), *trip)             # dense [n,n] similarity, like the miner
+        loss = O.compute_hyp(emb, a, p, n, scale, TEMPERATURE)       # dense [n,n] again + 3 hyp_lca
+        torch.autograd.grad(loss, (emb, scale))
+        return float(loss.detach())
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": round(B / dt, 3), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{B} clouds x {N_PTS} pts ({B * N_PTS * T_PER_ANCHOR} mined triplets) per step, "
+                      f"oracle restatement of the reference PyTorch path, torch CPU threads={cores}",
+            "s_per_step": round(dt, 3)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+    cb = cpu_reference_pass(steps, warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world, "steps": steps,
+        "warmup": warmup, "ms_per_step": round(cb["s_per_step"] * 1e3, 2), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "shapenet_train_step_b32_n1024_k20_d32_t50 (BASELINE.json configs[1])",
+                   "note": "reference is pure Python/PyTorch; this arm times the oracle restatement of its CPU path "
+                           f"on a bounded sample of {CPU_SAMPLE_B} clouds per step (the dense similarity matrix of "
+                           "the full batch, 2 x 4.3 GB forward, does not fit a bounded CPU run)"},
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["native", "reference"], default="native")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+    import torch.distributed as dist
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,223 @@
+// Batched per-cloud kNN graph construction (exact fp32, canonical order).
+//
+// Replaces knn() of hpcs/nn/dgcnn/utils/vn_dgcnn_util.py:4-10, which materialises three [B,N,N]
+// temporaries plus a batched SGEMM with K = 3 / 63 and a topk.  Here nothing of size N x N ever
+// exists: one warp owns QW query rows; the 32 lanes of the warp each take one candidate column of
+// the current 32-wide chunk, keep its D features in registers, and evaluate the canonical
+// distance against the warp's queries (query features broadcast from shared memory).  The running
+// top-k of a query is a sorted list spread over the lanes of the warp (rank r lives in lane r%32,
+// slot r/32); a candidate that beats the current k-th value is inserted with two warp shuffles.
+//
+// Canonical arithmetic (bit-exact with oracle/knn_canonical.c):
+//   sq_i  = fma chain over d ascending;  dot_ij = fma chain over d ascending;
+//   pd_ij = fmaf(2, dot_ij, -sq_i) - sq_j;   order: larger pd first, ties -> lower j.
+// Zero padding of d up to a multiple of 4 does not change any bit of pd (fma(0,0,acc) == acc).
+#include <float.h>
+
+#include "common.cuh"
+
+namespace hpcs {
+
+constexpr int kKnnWarps = 8;
+
+__global__ void knn_sqnorm_kernel(const float* __restrict__ x, int D, int N, float* __restrict__ sq) {
+    const int b = blockIdx.y;
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    const float* xb = x + (size_t)b * D * N;
+    float s = 0.f;
+    for (int d = 0; d < D; ++d) {
+        const float v = __ldg(xb + (size_t)d * N + j);
+        s = __fmaf_rn(v, v, s);
+    }
+    sq[(size_t)b * N + j] = s;
+}
+
+// DREG: candidate features held in registers per d-block (multiple of 4).
+// QW:   query rows per warp.   SLOTS: ceil(k/32).   STAGED: whole cloud copied to shared memory.
+template <int DREG, int QW, int SLOTS, bool STAGED>
+__global__ void __launch_bounds__(kKnnWarps * 32)
+knn_kernel(const float* __restrict__ x, const float* __restrict__ sq, int D, int Dp, int N, int k,
+           int64_t* __restrict__ idx, float* __restrict__ val) {
+    extern __shared__ __align__(16) float smem[];
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    constexpr int QB = kKnnWarps * QW;            // queries per CTA
+    const int q0 = blockIdx.x * QB;
+    const float* xb = x + (size_t)b * D * N;
+    const float* sqb = sq + (size_t)b * N;
+
+    float* qs = smem;                             // [QB][Dp], zero padded
+    float* xs = smem + QB * Dp;                   // STAGED: [Dp][N] candidates, then [N] norms
+    float* sqs = xs + (size_t)Dp * N;
+
+    for (int e = threadIdx.x; e < QB * Dp; e += blockDim.x) {
+        const int d = e / QB, qi = e % QB;        // consecutive threads -> consecutive points
+        const int i = q0 + qi;
+        qs[qi * Dp + d] = (d < D && i < N) ? __ldg(xb + (size_t)d * N + i) : 0.f;
+    }
+    if (STAGED) {
+        for (int e = threadIdx.x; e < Dp * N; e += blockDim.x) {
+            const int d = e / N;
+            xs[e] = d < D ? __ldg(xb + e) : 0.f;
+        }
+        for (int e = threadIdx.x; e < N; e += blockDim.x) sqs[e] = __ldg(sqb + e);
+    }
+    __syncthreads();
+
+    // lane-distributed sorted lists, one per query of this warp
+    float lv[QW][SLOTS];
+    int li[QW][SLOTS];
+    float tau[QW], sqq[QW];
+#pragma unroll
+    for (int q = 0; q < QW; ++q) {
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) { lv[q][s] = -INFINITY; li[q][s] = 0x7fffffff; }
+        tau[q] = -INFINITY;
+        const int i = q0 + warp * QW + q;
+        sqq[q] = i < N ? (STAGED ? sqs[i] : __ldg(sqb + i)) : 0.f;
+    }
+    const int tau_slot = (k - 1) >> 5, tau_lane = (k - 1) & 31;
+
+    for (int j0 = 0; j0 < N; j0 += 32) {
+        const int j = j0 + lane;
+        const bool valid = j < N;
+        float acc[QW];
+#pragma unroll
+        for (int q = 0; q < QW; ++q) acc[q] = 0.f;
+        for (int db = 0; db < Dp; db += DREG) {
+            float c[DREG];
+#pragma unroll
+            for (int t = 0; t < DREG; ++t) {
+                const int d = db + t;
+                float v = 0.f;
+                if (valid && d < Dp) v = STAGED ? xs[(size_t)d * N + j] : (d < D ? __ldg(xb + (size_t)d * N + j) : 0.f);
+                c[t] = v;
+            }
+#pragma unroll
+            for (int t = 0; t < DREG; t += 4) {
+                if (db + t < Dp) {                 // warp-uniform
+#pragma unroll
+                    for (int q = 0; q < QW; ++q) {
+                        const float4 qv = *reinterpret_cast<const float4*>(qs + (warp * QW + q) * Dp + db + t);
+                        float a = acc[q];
+                        a = __fmaf_rn(qv.x, c[t], a);
+                        a = __fmaf_rn(qv.y, c[t + 1], a);
+                        a = __fmaf_rn(qv.z, c[t + 2], a);
+                        a = __fmaf_rn(qv.w, c[t + 3], a);
+                        acc[q] = a;
+                    }
+                }
+            }
+        }
+        const float sqc = valid ? (STAGED ? sqs[j] : __ldg(sqb + j)) : 0.f;
+#pragma unroll
+        for (int q = 0; q < QW; ++q) {
+            const float t = __fmaf_rn(2.f, acc[q], -sqq[q]);
+            const float pd = valid ? __fsub_rn(t, sqc) : -INFINITY;
+            unsigned bm = __ballot_sync(kFull, pd > tau[q]);
+            while (bm) {
+                const int src = __ffs(bm) - 1;
+                bm &= bm - 1;
+                const float v = __shfl_sync(kFull, pd, src);
+                if (v > tau[q]) {                  // tau may have risen since the ballot
+                    const int jj = j0 + src;
+                    int pos = 0;
+#pragma unroll
+                    for (int s = 0; s < SLOTS; ++s) pos += __popc(__ballot_sync(kFull, lv[q][s] >= v));
+#pragma unroll
+                    for (int s = SLOTS - 1; s >= 0; --s) {
+                        float pv = __shfl_up_sync(kFull, lv[q][s], 1);
+                        int pi = __shfl_up_sync(kFull, li[q][s], 1);
+                        if (s > 0) {
+                            const float cv = __shfl_sync(kFull, lv[q][s - 1], 31);
+                            const int ci = __shfl_sync(kFull, li[q][s - 1], 31);
+                            if (lane == 0) { pv = cv; pi = ci; }
+                        }
+                        const int r = s * 32 + lane;
+                        if (r > pos) { lv[q][s] = pv; li[q][s] = pi; }
+                        else if (r == pos) { lv[q][s] = v; li[q][s] = jj; }
+                    }
+                    float tv = lv[q][0];
+#pragma unroll
+                    for (int s = 1; s < SLOTS; ++s) if (s == tau_slot) tv = lv[q][s];
+                    tau[q] = __shfl_sync(kFull, tv, tau_lane);
+                }
+            }
+        }
+    }
+
+#pragma unroll
+    for (int q = 0; q < QW; ++q) {
+        const int i = q0 + warp * QW + q;
+        if (i >= N) continue;
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            const int r = s * 32 + lane;
+            if (r < k) {
+                const int jj = li[q][s];
+                const size_t o = ((size_t)b * N + i) * k + r;
+                idx[o] = jj < N ? jj : i;
+                if (val) val[o] = lv[q][s];
+            }
+        }
+    }
+}
+
+template <int DREG, int QW, int SLOTS>
+static int launch_knn(const float* x, const float* sq, int B, int D, int N, int k, int64_t* idx, float* val,
+                      cudaStream_t st) {
+    const int Dp = (D + 3) / 4 * 4;
+    constexpr int QB = kKnnWarps * QW;
+    dim3 grid((N + QB - 1) / QB, B), block(kKnnWarps * 32);
+    const size_t smem_q = (size_t)QB * Dp * sizeof(float);
+    const size_t smem_staged = smem_q + ((size_t)Dp * N + N) * sizeof(float);
+    if (smem_staged <= 64 * 1024) {
+        auto kern = knn_kernel<DREG, QW, SLOTS, true>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        kern<<<grid, block, smem_staged, st>>>(x, sq, D, Dp, N, k, idx, val);
+    } else {
+        if (smem_q > 200 * 1024) return fail(HPCS_ERR_ARG, "knn: D=%d too large", D);
+        auto kern = knn_kernel<DREG, QW, SLOTS, false>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q);
+        kern<<<grid, block, smem_q, st>>>(x, sq, D, Dp, N, k, idx, val);
+    }
+    return check_launch("knn_kernel");
+}
+
+template <int DREG, int QW>
+static int dispatch_slots(const float* x, const float* sq, int B, int D, int N, int k, int64_t* idx, float* val,
+                          cudaStream_t st) {
+    if (k <= 32) return launch_knn<DREG, QW, 1>(x, sq, B, D, N, k, idx, val, st);
+    if (k <= 64) return launch_knn<DREG, QW, 2>(x, sq, B, D, N, k, idx, val, st);
+    if (k <= 128) return launch_knn<DREG, QW, 4>(x, sq, B, D, N, k, idx, val, st);
+    return fail(HPCS_ERR_ARG, "knn: k=%d > 128 not supported", k);
+}
+
+}  // namespace hpcs
+
+extern "C" {
+
+size_t hpcs_knn_workspace_bytes(int B, int D, int N, int k) {
+    (void)D; (void)k;
+    return hpcs::align_up((size_t)B * N * sizeof(float), 256);
+}
+
+int hpcs_knn_f32(const float* x, int B, int D, int N, int k, int64_t* idx, float* val, void* ws,
+                 size_t ws_bytes, void* stream) {
+    using namespace hpcs;
+    if (!x || !idx || !ws) return fail(HPCS_ERR_ARG, "knn: null pointer");
+    if (B <= 0 || D <= 0 || N <= 0 || k <= 0 || k > N) return fail(HPCS_ERR_ARG, "knn: bad shape B=%d D=%d N=%d k=%d", B, D, N, k);
+    if (ws_bytes < hpcs_knn_workspace_bytes(B, D, N, k)) return fail(HPCS_ERR_WORKSPACE, "knn: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    float* sq = static_cast<float*>(ws);
+    knn_sqnorm_kernel<<<dim3((N + 255) / 256, B), 256, 0, st>>>(x, D, N, sq);
+    int rc = check_launch("knn_sqnorm_kernel");
+    if (rc) return rc;
+    if (D <= 4) return dispatch_slots<4, 4>(x, sq, B, D, N, k, idx, val, st);
+    if (D <= 32) return dispatch_slots<32, 4>(x, sq, B, D, N, k, idx, val, st);
+    return dispatch_slots<64, 4>(x, sq, B, D, N, k, idx, val, st);
+}
+
+}  // extern "C"

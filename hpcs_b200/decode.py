@@ -1,0 +1,61 @@
+"""Decoding embeddings into dendrograms -- drop-in for ``BaseSimilarityHypHC._decode_linkage``
+(hpcs/models/base_hyp_hc.py:81-86) plus a batched form that replaces the per-cloud Python loop at
+base_hyp_hc.py:135-137.
+
+``method='complete'`` is what the reference ships (scipy ``linkage(method='complete',
+metric='cosine')``); ``method='single'`` is the HypHC decoder named by the north star (same merge
+order as single linkage over hyperbolic-LCA similarity, because all leaves share one radius).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .hyperbolic import normalize_project
+
+METHODS = {"single": 0, "complete": 1}
+_WS_BUDGET = 24 << 30          # bytes of fp64 distance matrices resident at once
+
+
+def linkage_from_leaves(leaves: torch.Tensor, method: str = "complete") -> torch.Tensor:
+    """leaves[B,N,D] fp32 on the GPU -> Z[B,N-1,4] fp64 on the GPU (scipy linkage format)."""
+    if leaves.dim() != 3:
+        raise ValueError(f"expected leaves[B,N,D], got {tuple(leaves.shape)}")
+    if method not in METHODS:
+        raise ValueError(f"method must be one of {sorted(METHODS)}")
+    dev = _lib.require_cuda(leaves)
+    lib = _lib.load()
+    lv = leaves.detach().contiguous().float()
+    B, N, D = lv.shape
+    if N < 2:
+        raise ValueError("need at least two leaves")
+    Z = torch.empty((B, N - 1, 4), dtype=torch.float64, device=dev)
+    per_cloud = lib.hpcs_linkage_workspace_bytes(1, N, D, METHODS[method])
+    chunk = max(1, min(B, _WS_BUDGET // max(per_cloud, 1)))
+    for b0 in range(0, B, chunk):
+        nb = min(chunk, B - b0)
+        ws = _lib.workspace(lib.hpcs_linkage_workspace_bytes(nb, N, D, METHODS[method]), dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.hpcs_linkage_f64(lv[b0:b0 + nb].data_ptr(), nb, N, D, METHODS[method],
+                                            Z[b0:b0 + nb].data_ptr(), ws.data_ptr(), ws.numel(),
+                                            _lib.stream_ptr(dev)), "hpcs_linkage_f64")
+    return Z
+
+
+def decode_linkage_batch(x_poincare: torch.Tensor, scale: torch.Tensor, method: str = "complete",
+                         return_leaves: bool = False):
+    """x[B,N,D] -> Z[B,N-1,4] fp64 (GPU tensor): rescale to the common radius, project, link."""
+    if x_poincare.dim() != 3:
+        raise ValueError(f"expected x[B,N,D], got {tuple(x_poincare.shape)}")
+    leaves = normalize_project(x_poincare, scale.to(x_poincare.device))
+    Z = linkage_from_leaves(leaves, method)
+    return (Z, leaves) if return_leaves else Z
+
+
+def decode_linkage(leaves_embeddings: torch.Tensor, scale: torch.Tensor, method: str = "complete") -> np.ndarray:
+    """One cloud [N,D] -> numpy Z[N-1,4] float64, the reference's return type."""
+    Z = decode_linkage_batch(leaves_embeddings.unsqueeze(0), scale, method)
+    return Z[0].cpu().numpy()

@@ -1,0 +1,103 @@
+"""kNN graph and edge features -- drop-ins for ``hpcs/nn/dgcnn/utils/vn_dgcnn_util.py``.
+
+Same names, argument meaning and return layout as the reference:
+  knn(x, k)                                   vn_dgcnn_util.py:4-10
+  get_graph_feature(x, k, idx, x_coord)       vn_dgcnn_util.py:13-41
+  get_graph_feature_cross(x, k, idx)          vn_dgcnn_util.py:44-69
+(The reference's cross variant hard-codes ``torch.device('cuda')``; here the input's device is used,
+which is what makes it usable on rank != 0.)
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+
+def knn(x: torch.Tensor, k: int, return_values: bool = False):
+    """x[B,D,N] fp32 -> idx[B,N,k] int64: the k nearest points of every point (self included), by
+    descending ``-|xi-xj|^2``; exact ties resolve to the lower index (see oracle/knn_canonical.c)."""
+    if x.dim() != 3:
+        raise ValueError(f"knn expects x[B,D,N], got {tuple(x.shape)}")
+    dev = _lib.require_cuda(x)
+    if x.dtype != torch.float32:
+        raise TypeError("knn: float32 only")
+    x = x.detach().contiguous()
+    B, D, N = x.shape
+    if not 0 < k <= N:
+        raise ValueError(f"knn: need 0 < k <= N, got k={k}, N={N}")
+    lib = _lib.load()
+    idx = torch.empty((B, N, k), dtype=torch.int64, device=dev)
+    val = torch.empty((B, N, k), dtype=torch.float32, device=dev) if return_values else None
+    ws = _lib.workspace(lib.hpcs_knn_workspace_bytes(B, D, N, k), dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.hpcs_knn_f32(x.data_ptr(), B, D, N, k, idx.data_ptr(), _lib.ptr(val), ws.data_ptr(),
+                                    ws.numel(), _lib.stream_ptr(dev)), "hpcs_knn_f32")
+    return (idx, val) if return_values else idx
+
+
+class _EdgeFeature(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, idx, cross):
+        # x[B,C,3,N] contiguous fp32, idx[B,N,k] contiguous int64
+        B, C, _, N = x.shape
+        k = idx.shape[2]
+        dev = x.device
+        lib = _lib.load()
+        planes = 3 if cross else 2
+        out = torch.empty((B, planes * C, 3, N, k), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.hpcs_edge_feat_fwd_f32(x.data_ptr(), idx.data_ptr(), B, C, N, k, int(cross),
+                                                  out.data_ptr(), _lib.stream_ptr(dev)), "hpcs_edge_feat_fwd_f32")
+        ctx.save_for_backward(x, idx)
+        ctx.cross = cross
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, idx = ctx.saved_tensors
+        B, C, _, N = x.shape
+        k = idx.shape[2]
+        dev = x.device
+        lib = _lib.load()
+        gout = gout.contiguous()
+        gx = torch.empty_like(x)
+        ws = _lib.workspace(lib.hpcs_edge_feat_bwd_workspace_bytes(B, N, k), dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.hpcs_edge_feat_bwd_f32(gout.data_ptr(), x.data_ptr(), idx.data_ptr(), B, C, N, k,
+                                                  int(ctx.cross), gx.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                  _lib.stream_ptr(dev)), "hpcs_edge_feat_bwd_f32")
+        return gx, None, None
+
+
+def _edge_features(x: torch.Tensor, k: int, idx: Optional[torch.Tensor], x_coord: Optional[torch.Tensor],
+                   cross: bool) -> torch.Tensor:
+    if x.dim() != 4 or x.shape[2] != 3:
+        raise ValueError(f"expected x[B,C,3,N], got {tuple(x.shape)}")
+    dev = _lib.require_cuda(x, idx, x_coord)
+    if x.dtype != torch.float32:
+        raise TypeError("get_graph_feature: float32 only")
+    B, C, _, N = x.shape
+    xc = x.contiguous()
+    if idx is None:
+        src = xc.view(B, 3 * C, N) if x_coord is None else x_coord      # dynamic vs fixed graph
+        idx = knn(src, k)
+    else:
+        if idx.shape != (B, N, k):
+            raise ValueError(f"idx must be [B,N,k]={B, N, k}, got {tuple(idx.shape)}")
+        idx = idx.to(device=dev, dtype=torch.int64).contiguous()
+    return _EdgeFeature.apply(xc, idx, cross)
+
+
+def get_graph_feature(x: torch.Tensor, k: int = 20, idx: Optional[torch.Tensor] = None,
+                      x_coord: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x[B,C,3,N] -> [B,2C,3,N,k] contiguous: channels [0,C) = x_j - x_i, [C,2C) = x_i.
+    Differentiable wrt ``x`` (both terms); ``idx``/``x_coord`` override the graph as in the reference."""
+    return _edge_features(x, k, idx, x_coord, cross=False)
+
+
+def get_graph_feature_cross(x: torch.Tensor, k: int = 20, idx: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x[B,C,3,N] -> [B,3C,3,N,k]: as above plus channels [2C,3C) = cross(x_j, x_i)."""
+    return _edge_features(x, k, idx, None, cross=True)

@@ -1,0 +1,292 @@
+"""Triplet mining and the hyperbolic metric-learning objective -- drop-ins for ``hpcs/miner``,
+``hpcs/distances/cosine.py`` and ``hpcs/loss/ultrametric_loss.py``.
+
+  get_balanced_random_triplet_indices   hpcs/miner/loss_and_miner_utils.py:7-75
+  RandomTripletMarginMiner              hpcs/miner/triplet_margin_miner.py:6-38
+  CosineSimilarity                      hpcs/distances/cosine.py:4-16
+  MetricHyperbolicLoss                  hpcs/loss/ultrametric_loss.py:16-143
+
+The sampler stays on the host and consumes the torch CPU generator exactly like the reference, so a
+common seed gives identical triplets.  Everything downstream of the sampled indices (similarities,
+easy/semihard filter, LCA distances, softmax-weighted loss, mean similarity, gradients) is one
+fused CUDA pass (csrc/hyp_loss.cu); no (B.N)^2 matrix is built.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple, Union
+
+import torch
+import torch.nn.functional as F
+
+from . import _lib
+
+FILTER_MODES = {"all": 0, "easy": 1, "semihard": 2, "hard": 3}
+_BELOW_MARGIN = 4          # any other type_of_triplets in the reference: margin test only
+
+
+# ------------------------------------------------------------------------------------------------
+# sampling (host, RNG-parity with the reference)
+# ------------------------------------------------------------------------------------------------
+def get_balanced_random_triplet_indices(labels: torch.Tensor, ref_labels=None, t_per_anchor: Optional[int] = None,
+                                        fraction: Optional[float] = None, weights=None
+                                        ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Per label l (ascending): every member is an anchor ``k_l = int(t_per_anchor * (max_count /
+    n_l) ** fraction)`` times, with a positive drawn uniformly from the other members and a negative
+    drawn uniformly from the non-members.  Labels with < 2 members or no non-member are skipped."""
+    if ref_labels is not None or weights is not None:
+        raise NotImplementedError("only the ref_labels=None, weights=None path used by HPCS is provided")
+    device = labels.device
+    host = labels.detach().cpu()
+    counts = torch.bincount(host)
+    biggest = counts.max()
+    a_parts, p_parts, n_parts = [], [], []
+    for value in torch.unique(host):
+        inside = host == value
+        members = inside.nonzero(as_tuple=True)[0]
+        outside = (~inside).nonzero(as_tuple=True)[0]
+        m = members.numel()
+        if m < 2 or outside.numel() < 1:
+            continue
+        reps = m if t_per_anchor is None else int(t_per_anchor * torch.pow(biggest / m, fraction))
+        total = m * reps
+        pos_draw = torch.randint(0, m - 1, (total,))
+        anchor_slot = torch.arange(m).repeat_interleave(reps)
+        pos_slot = pos_draw + (pos_draw >= anchor_slot).to(pos_draw.dtype)   # skip the anchor itself
+        neg_draw = torch.randint(0, outside.numel(), (total,))
+        a_parts.append(members[anchor_slot])
+        p_parts.append(members[pos_slot])
+        n_parts.append(outside[neg_draw])
+    if not a_parts:
+        empty = torch.empty(0, dtype=torch.long, device=device)
+        return empty, empty.clone(), empty.clone()
+    return (torch.cat(a_parts).to(device, non_blocking=True), torch.cat(p_parts).to(device, non_blocking=True),
+            torch.cat(n_parts).to(device, non_blocking=True))
+
+
+# ------------------------------------------------------------------------------------------------
+# similarity
+# ------------------------------------------------------------------------------------------------
+class CosineSimilarity(torch.nn.Module):
+    """``0.5 * (1 + q_hat . r_hat)`` on L2-normalised rows; an inverted distance (larger = closer).
+    Thin PyTorch: the hot path never calls it (it would build the [n,m] matrix)."""
+
+    is_inverted = True
+    normalize_embeddings = True
+
+    def forward(self, query_emb, ref_emb=None):
+        q = F.normalize(query_emb, p=2, dim=1)
+        r = q if ref_emb is None else F.normalize(ref_emb, p=2, dim=1)
+        return self.compute_mat(q, r)
+
+    def compute_mat(self, query_emb, ref_emb):
+        return 0.5 * (1 + torch.matmul(query_emb, ref_emb.t()))
+
+    def pairwise_distance(self, query_emb, ref_emb):
+        return 0.5 * (1 + torch.sum(query_emb * ref_emb, dim=1))
+
+    def margin(self, x, y):
+        return y - x
+
+    def smallest_dist(self, *args, **kwargs):
+        return torch.max(*args, **kwargs)
+
+
+# ------------------------------------------------------------------------------------------------
+# fused objective
+# ------------------------------------------------------------------------------------------------
+def _as_index(t: torch.Tensor, dev: torch.device) -> torch.Tensor:
+    return t.to(device=dev, dtype=torch.int64).contiguous()
+
+
+def filter_triplets(x: torch.Tensor, a: torch.Tensor, p: torch.Tensor, n: torch.Tensor, margin: float = 0.0,
+                    type_of_triplets: str = "easy") -> torch.Tensor:
+    """Boolean keep-mask of the miner's margin test (hpcs/miner/triplet_margin_miner.py:16-32)."""
+    dev = _lib.require_cuda(x)
+    lib = _lib.load()
+    xc = x.detach().contiguous().float()
+    nrow, D = xc.shape
+    a, p, n = _as_index(a, dev), _as_index(p, dev), _as_index(n, dev)
+    T0 = a.numel()
+    keep = torch.empty(T0, dtype=torch.uint8, device=dev)
+    ws = _lib.workspace(lib.hpcs_hyp_triplet_workspace_bytes(nrow, D), dev)
+    mode = FILTER_MODES.get(type_of_triplets, _BELOW_MARGIN)
+    with torch.cuda.device(dev):
+        _lib.check(lib.hpcs_triplet_filter_f32(xc.data_ptr(), nrow, D, a.data_ptr(), p.data_ptr(), n.data_ptr(), T0,
+                                               mode, float(margin), keep.data_ptr(), ws.data_ptr(), ws.numel(),
+                                               _lib.stream_ptr(dev)), "hpcs_triplet_filter_f32")
+    return keep.bool()
+
+
+class RandomTripletMarginMiner(torch.nn.Module):
+    """Sample class-balanced triplets, keep those passing the margin test on the cosine similarity."""
+
+    def __init__(self, t_per_anchor, fraction, margin=0.2, type_of_triplets="all", distance=None, **kwargs):
+        super().__init__()
+        self.t_per_anchor, self.fraction = t_per_anchor, fraction
+        self.margin, self.type_of_triplets = margin, type_of_triplets
+        self.distance = distance if distance is not None else CosineSimilarity()
+
+    def sample(self, labels):
+        return get_balanced_random_triplet_indices(labels, t_per_anchor=self.t_per_anchor, fraction=self.fraction)
+
+    def forward(self, embeddings, labels, ref_emb=None, ref_labels=None):
+        with torch.no_grad():
+            a, p, n = self.sample(labels)
+            keep = filter_triplets(embeddings, a, p, n, self.margin, self.type_of_triplets)
+            return a[keep], p[keep], n[keep]
+
+
+class _HypTripletLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, scale, a, p, n, temperature, filter_mode, margin):
+        dev = x.device
+        lib = _lib.load()
+        nrow, D = x.shape
+        T0 = a.numel()
+        need_grad = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
+        loss = torch.empty(1, dtype=torch.float32, device=dev)
+        kept = torch.empty(1, dtype=torch.int64, device=dev)
+        ws = _lib.workspace(lib.hpcs_hyp_triplet_workspace_bytes(nrow, D), dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.hpcs_hyp_triplet_fwd_f32(x.data_ptr(), nrow, D, a.data_ptr(), p.data_ptr(), n.data_ptr(), T0,
+                                                    scale.data_ptr(), float(temperature), int(filter_mode),
+                                                    float(margin), int(need_grad), loss.data_ptr(), kept.data_ptr(),
+                                                    ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev)),
+                       "hpcs_hyp_triplet_fwd_f32")
+        ctx.save_for_backward(x, scale, ws)
+        ctx.mark_non_differentiable(kept)
+        return loss.reshape(()), kept
+
+    @staticmethod
+    def backward(ctx, gloss, _gkept):
+        x, scale, ws = ctx.saved_tensors
+        dev = x.device
+        lib = _lib.load()
+        nrow, D = x.shape
+        g = gloss.reshape(1).contiguous().float()
+        gx = torch.empty_like(x)
+        gscale = torch.empty(1, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.hpcs_hyp_triplet_bwd_f32(g.data_ptr(), x.data_ptr(), nrow, D, scale.data_ptr(), ws.data_ptr(),
+                                                    ws.numel(), gx.data_ptr(), gscale.data_ptr(), _lib.stream_ptr(dev)),
+                       "hpcs_hyp_triplet_bwd_f32")
+        return gx, gscale.reshape(scale.shape), None, None, None, None, None, None
+
+
+def hyp_triplet_loss(x: torch.Tensor, triplets, scale: torch.Tensor, temperature: float,
+                     type_of_triplets: str = "all", margin: float = 0.0, return_kept: bool = False):
+    """``mean_T(total) + mean(mat_sim)`` of ``compute_hyp`` for given (sampled, unfiltered) triplets.
+    ``type_of_triplets`` applies the miner's filter inside the kernel."""
+    dev = _lib.require_cuda(x, scale)
+    if x.dtype != torch.float32 or x.dim() != 2:
+        raise TypeError("hyp_triplet_loss expects x[n,D] float32")
+    a, p, n = (_as_index(t, dev) for t in triplets)
+    sc = scale.reshape(-1)
+    if sc.numel() != 1 or sc.dtype != torch.float32:
+        raise TypeError("scale must hold one float32")
+    mode = FILTER_MODES.get(type_of_triplets, _BELOW_MARGIN)
+    loss, kept = _HypTripletLoss.apply(x.contiguous(), sc if sc.is_contiguous() else sc.contiguous(), a, p, n,
+                                       temperature, mode, margin)
+    return (loss, kept) if return_kept else loss
+
+
+class CosFaceLoss(torch.nn.Module):
+    """Large-margin cosine loss, ``logits = s (cos - m onehot)`` + mean cross entropy: the arithmetic
+    the reference takes from pytorch-metric-learning (visible at
+    hpcs/loss/hierarchical_cosface_loss.py:57-74).  Outside the hot path; plain PyTorch."""
+
+    def __init__(self, num_classes, embedding_size, margin=0.35, scale=64):
+        super().__init__()
+        self.margin, self.scale = margin, scale
+        self.W = torch.nn.Parameter(torch.empty(embedding_size, num_classes))
+        torch.nn.init.normal_(self.W)
+
+    def get_cosine(self, embeddings):
+        return F.normalize(embeddings, p=2, dim=1) @ F.normalize(self.W, p=2, dim=0)
+
+    def get_logits(self, embeddings, labels):
+        cosine = self.get_cosine(embeddings)
+        onehot = F.one_hot(labels.long(), cosine.shape[1]).to(cosine.dtype)
+        return (cosine - self.margin * onehot) * self.scale
+
+    def forward(self, embeddings, labels):
+        return F.cross_entropy(self.get_logits(embeddings, labels), labels.long())
+
+
+class MetricHyperbolicLoss(torch.nn.Module):
+    """Same constructor and methods as the reference class (ultrametric_loss.py:16-143)."""
+
+    def __init__(self, margin: float = 1.0, t_per_anchor: int = 50, fraction: float = 1.2,
+                 scale: Union[float, torch.Tensor, torch.nn.Parameter] = 1e-3, temperature: float = 0.05,
+                 anneal_factor: float = 0.5, num_class: int = 4, embedding_size: int = 4, cosface: bool = True,
+                 miner: bool = False):
+        super().__init__()
+        self.margin, self.t_per_anchor, self.fraction = margin, t_per_anchor, fraction
+        self.scale = scale if isinstance(scale, torch.Tensor) else torch.tensor([float(scale)])
+        self.temperature, self.anneal_factor = temperature, anneal_factor
+        self.num_class, self.embedding_size = num_class, embedding_size
+        self.cosface, self.miner = cosface, miner
+        self.distance_sim = CosineSimilarity()
+        if self.miner:
+            self.hyp_miner = RandomTripletMarginMiner(distance=self.distance_sim, margin=0, t_per_anchor=t_per_anchor,
+                                                      fraction=fraction, type_of_triplets="easy")
+        if self.cosface:
+            self.loss_cosface = CosFaceLoss(num_classes=num_class, embedding_size=embedding_size, margin=0.35, scale=2)
+        else:
+            self.triplet_miner = RandomTripletMarginMiner(distance=self.distance_sim, margin=margin,
+                                                          t_per_anchor=t_per_anchor, fraction=fraction,
+                                                          type_of_triplets="semihard")
+
+    # -- helpers kept from the reference -----------------------------------------------------------
+    def get_triplets(self, n_samples):
+        """All pairs (i<j), each ``t_per_anchor`` times, with a random third point != i, j
+        (ultrametric_loss.py:42-55; only practical for small n)."""
+        pairs = torch.combinations(torch.arange(n_samples), r=2).repeat_interleave(self.t_per_anchor, dim=0)
+        third = torch.randint(n_samples, (pairs.shape[0],), dtype=torch.long)
+        ok = (pairs[:, 0] != third) & (pairs[:, 1] != third)
+        return pairs[ok, 0], pairs[ok, 1], third[ok]
+
+    def _scale_on(self, dev):
+        if self.scale.device != dev:
+            if isinstance(self.scale, torch.nn.Parameter):
+                raise RuntimeError("scale Parameter lives on another device than the embeddings")
+            self.scale = self.scale.to(dev)
+        return self.scale
+
+    def normalize_embeddings(self, embeddings):
+        return F.normalize(embeddings, p=2, dim=1) * torch.clamp(self._scale_on(embeddings.device), 1e-4, 1)
+
+    def compute_hyp(self, x_poincare, labels, triplets=None):
+        """HypHC triplet loss + mean similarity.  ``triplets`` (a, p, n) may be passed to reuse an
+        already sampled set; otherwise they are sampled like the reference does."""
+        dev = x_poincare.device
+        if triplets is None:
+            triplets = self.hyp_miner.sample(labels) if self.miner else self.get_triplets(x_poincare.shape[0])
+        kind = "easy" if self.miner else "all"
+        return hyp_triplet_loss(x_poincare, triplets, self._scale_on(dev), self.temperature, kind, 0.0)
+
+    def get_logits(self, embeddings, labels):
+        if not hasattr(self, "loss_cosface"):
+            raise ValueError("Cannot get logits since this class doesn't use any CosFaceLoss")
+        return self.loss_cosface.get_logits(embeddings, labels)
+
+    def compute_loss(self, x_euclidean, x_poincare, labels, *args):
+        loss_hyperbolic = self.compute_hyp(x_poincare, labels)
+        if self.cosface:
+            loss_metric = self.loss_cosface(x_poincare, labels.long())
+        else:
+            a, p, n = self.triplet_miner(x_poincare, labels)
+            if a.numel() == 0:
+                loss_metric = x_poincare.sum() * 0
+            else:
+                u = F.normalize(x_poincare, p=2, dim=1)
+                ap = self.distance_sim.pairwise_distance(u[a], u[p])
+                an = self.distance_sim.pairwise_distance(u[a], u[n])
+                viol = F.relu(an - ap + self.margin)
+                nz = (viol > 0).sum().clamp_min(1)
+                loss_metric = viol.sum() / nz
+        return {"loss_hyp": {"losses": loss_hyperbolic}, "loss_metric": {"losses": loss_metric}}
+
+    def anneal_temperature(self):
+        self.temperature *= min(max(self.anneal_factor, 0.2), 1.0)
+        return self.temperature

@@ -1,0 +1,113 @@
+/* hpcs_b200 -- C ABI of the B200 (sm_100a) hot path for HPCS.
+ *
+ * The reference (TheCrossProduct/HPCS) is pure Python; it has no FFI.  Its plugin surface for
+ * this path is the set of Python signatures listed below, and each entry point here is what a
+ * binding for that signature calls (see INTEGRATION.md for the ctypes stubs).  Paths are
+ * relative to the reference root.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; the caller owns all
+ *     buffers including workspaces (query the size with the matching *_workspace_bytes);
+ *   - `stream` is a cudaStream_t passed as void*; calls are stream-ordered, never synchronise the
+ *     device, allocate nothing, and keep no global mutable state (re-entrant across streams);
+ *   - return 0 on success, non-zero otherwise; hpcs_last_error() returns a thread-local message;
+ *   - kernels exist for sm_100a only; there is no CPU fallback.
+ */
+#ifndef HPCS_B200_H
+#define HPCS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HPCS_ABI_VERSION 1
+
+enum {
+    HPCS_OK = 0,
+    HPCS_ERR_ARG = 1,        /* bad shape / null pointer / unsupported size */
+    HPCS_ERR_WORKSPACE = 2,  /* workspace too small */
+    HPCS_ERR_CUDA = 3,       /* launch or runtime error, see hpcs_last_error() */
+    HPCS_ERR_DEVICE = 4      /* current device is not compute capability 10.x */
+};
+
+int hpcs_abi_version(void);
+const char* hpcs_last_error(void);
+/* 0 when the current CUDA device can run this library (CC 10.x), HPCS_ERR_DEVICE otherwise. */
+int hpcs_device_check(void);
+/* Number of kernels this library has launched in the calling process (monotonic counter). */
+uint64_t hpcs_launch_count(void);
+
+/* ---- part 1: kNN graph + edge features --------------------------------------------------
+ * knn(x, k)                       hpcs/nn/dgcnn/utils/vn_dgcnn_util.py:4-10
+ *   x[B,D,N] fp32 -> idx[B,N,k] int64; k largest of -|xi-xj|^2 per row, best first, self
+ *   included.  Canonical arithmetic and tie-break (lower index first): see oracle/knn_canonical.c.
+ *   Optional `val` [B,N,k] fp32 receives the selected values (may be NULL). */
+size_t hpcs_knn_workspace_bytes(int B, int D, int N, int k);
+int hpcs_knn_f32(const float* x, int B, int D, int N, int k, int64_t* idx, float* val,
+                 void* ws, size_t ws_bytes, void* stream);
+
+/* get_graph_feature(x, k, idx)    hpcs/nn/dgcnn/utils/vn_dgcnn_util.py:13-41
+ * get_graph_feature_cross         hpcs/nn/dgcnn/utils/vn_dgcnn_util.py:44-69   (cross != 0)
+ *   x[B,C,3,N] (== [B,3C,N]) fp32, idx[B,N,k] int64 -> out[B,(2|3)C,3,N,k] fp32 contiguous:
+ *   channels [0,C) x_j - x_i, [C,2C) x_i, [2C,3C) cross(x_j, x_i). */
+int hpcs_edge_feat_fwd_f32(const float* x, const int64_t* idx, int B, int C, int N, int k, int cross,
+                           float* out, void* stream);
+/* backward of the above wrt x: gx[B,C,3,N] (overwritten).  Deterministic: the scatter is turned
+ * into a gather through a reverse (target -> sources) CSR built in the workspace. */
+size_t hpcs_edge_feat_bwd_workspace_bytes(int B, int N, int k);
+int hpcs_edge_feat_bwd_f32(const float* gout, const float* x, const int64_t* idx, int B, int C, int N,
+                           int k, int cross, float* gx, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- part 2: Poincare-ball triplet objective -------------------------------------------------
+ * MetricHyperbolicLoss.compute_hyp    hpcs/loss/ultrametric_loss.py:57-93 (+ :139-143)
+ * RandomTripletMarginMiner.mine (filter part)  hpcs/miner/triplet_margin_miner.py:16-38
+ * CosineSimilarity                    hpcs/distances/cosine.py:4-16
+ * hyp_lca(.., return_coord=False) on equal-radius rows   hpcs/distances/lca.py:37-52
+ *   x[n,D] fp32, triplets (a,p,ng)[T0] int64 as produced by the sampler, scale dev[1],
+ *   filter_mode: 0 keep all, 1 'easy' (sim(a,p)-sim(a,n) > margin), 2 'semihard'
+ *   (0 < gap <= margin), 3 'hard' (gap <= margin and gap <= 0), 4 gap <= margin.
+ *   Writes loss dev[1] fp32 and kept dev[1] int64.  With need_grad != 0 the same pass also
+ *   accumulates the gradient state in `ws`, consumed by hpcs_hyp_triplet_bwd_f32.
+ *   The (B.N)^2 similarity matrix of the reference is never formed. */
+size_t hpcs_hyp_triplet_workspace_bytes(int64_t n, int D);
+int hpcs_hyp_triplet_fwd_f32(const float* x, int64_t n, int D, const int64_t* a, const int64_t* p,
+                             const int64_t* ng, int64_t T0, const float* scale, float temperature,
+                             int filter_mode, float margin, int need_grad, float* loss, int64_t* kept,
+                             void* ws, size_t ws_bytes, void* stream);
+int hpcs_hyp_triplet_bwd_f32(const float* gloss, const float* x, int64_t n, int D, const float* scale,
+                             const void* ws, size_t ws_bytes, float* gx, float* gscale, void* stream);
+/* the miner's filter alone: keep[T0] uint8 (1 = triplet survives). */
+int hpcs_triplet_filter_f32(const float* x, int64_t n, int D, const int64_t* a, const int64_t* p,
+                            const int64_t* ng, int64_t T0, int filter_mode, float margin, uint8_t* keep,
+                            void* ws, size_t ws_bytes, void* stream);
+
+/* hyp_lca(a, b, return_coord)         hpcs/distances/lca.py:37-52 (general, unequal norms)
+ *   a,b[T,D] fp32 -> out[T,D] (return_coord) or out[T,1] = 2 artanh(|proj|); scalar chain in fp64. */
+int hpcs_hyp_lca_fwd_f32(const float* a, const float* b, int64_t T, int D, int return_coord, float* out,
+                         void* stream);
+int hpcs_hyp_lca_bwd_f32(const float* gout, const float* a, const float* b, int64_t T, int D,
+                         int return_coord, float* ga, float* gb, void* stream);
+
+/* ExpMap.forward = expmap_1(u, 0)     hpcs/nn/hyperbolic/hyp_embed.py:6-10, hpcs/utils/poincare.py:50-54 */
+int hpcs_expmap0_fwd_f32(const float* u, int64_t rows, int D, float* y, void* stream);
+int hpcs_expmap0_bwd_f32(const float* gy, const float* u, int64_t rows, int D, float* gu, void* stream);
+
+/* ---- part 3: linkage decode --------------------------------------------------------------------
+ * BaseSimilarityHypHC._decode_linkage  hpcs/models/base_hyp_hc.py:81-86
+ *   leaves = project(normalize(x) * clamp(scale, 1e-4, 1))  (fp32; hpcs_leaves_f32), then
+ *   scipy.cluster.hierarchy.linkage(leaves, method, 'cosine'): fp64 cosine distances,
+ *   method 0 = 'single' (Prim MST), 1 = 'complete' (nearest-neighbour chain), stable sort by
+ *   height, union-find relabel.  Z[B,N-1,4] fp64 in scipy linkage format, one dendrogram per
+ *   cloud; the B clouds are processed by one launch sequence. */
+int hpcs_leaves_f32(const float* x, int64_t rows, int D, const float* scale, float* leaves, void* stream);
+size_t hpcs_linkage_workspace_bytes(int B, int N, int D, int method);
+int hpcs_linkage_f64(const float* leaves, int B, int N, int D, int method, double* Z,
+                     void* ws, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HPCS_B200_H */

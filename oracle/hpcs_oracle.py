@@ -102,9 +102,9 @@ def graph_feature(x: torch.Tensor, k: int = 20, idx: Optional[torch.Tensor] = No
     flat = x.reshape(B, C * 3, N)
     if idx is None:
         idx = knn_fn(flat if x_coord is None else x_coord, k)
-    rows = flat.transpose(1, 2)                                         # [B,N,3C]
-    nbr = torch.gather(rows.unsqueeze(1).expand(B, N, N, 3 * C), 2,
-                       idx.unsqueeze(-1).expand(B, N, k, 3 * C))        # [B,N,k,3C]
+    rows = flat.transpose(1, 2).reshape(B * N, 3 * C)                   # one row per point
+    base = torch.arange(B, device=idx.device).view(B, 1, 1) * N          # vn_dgcnn_util.py:25-29
+    nbr = rows.index_select(0, (idx + base).reshape(-1))                # [B*N*k, 3C]
     nbr = nbr.reshape(B, N, k, C, 3)
     ctr = rows.reshape(B, N, 1, C, 3).expand(B, N, k, C, 3)
     parts = [nbr - ctr, ctr]
@@ -280,3 +280,120 @@ def decode_linkage(x: torch.Tensor, scale: torch.Tensor, method: str = "complete
     from scipy.cluster.hierarchy import linkage
     e = project(normalize_embeddings(x, scale)).detach().cpu()
     return linkage(e.numpy(), method=method, metric="cosine")
+
+
+# --- step-by-step restatement of what scipy does inside ``linkage`` (small inputs only) ---------
+# scipy is a compiled third-party dependency of the reference (not vendored under /root/reference);
+# its published algorithms (pdist 'cosine'; Prim-style ``mst_single_linkage``; ``nn_chain`` with the
+# complete-linkage update; stable sort by height; union-find ``label``) are restated here so the
+# CUDA decoder has a line-by-line checker, and are themselves checked bit-for-bit against
+# ``scipy.cluster.hierarchy.linkage`` in tests/test_oracle_golden.py.
+def pdist_cosine_restated(X: np.ndarray) -> np.ndarray:
+    """fp64 cosine distance, full symmetric matrix.  Arithmetic of the scipy build in this image
+    (measured): dot products use TWO running sums (even / odd elements, separate
+    multiply and add, no FMA), added at the end, odd tail element added last;
+    ``1 - dot / (norm_i * norm_j)`` with ``|cos| > 1`` clipped to +-1."""
+    X = np.asarray(X, dtype=np.float64)
+    n, D = X.shape
+
+    def dot2(u, v):
+        even = np.float64(0.0)
+        odd = np.float64(0.0)
+        for q in range(0, D - 1, 2):
+            even = even + u[q] * v[q]
+            odd = odd + u[q + 1] * v[q + 1]
+        s = even + odd
+        if D % 2:
+            s = s + u[D - 1] * v[D - 1]
+        return s
+
+    norms = np.array([np.sqrt(dot2(X[i], X[i])) for i in range(n)])
+    out = np.zeros((n, n))
+    for i in range(n):
+        for j in range(i + 1, n):
+            c = dot2(X[i], X[j]) / (norms[i] * norms[j])
+            if abs(c) > 1.0:
+                c = np.copysign(1.0, c)
+            out[i, j] = out[j, i] = 1.0 - c
+    return out
+
+
+def _label(rows, n):
+    """Union-find relabel: smaller root id first, new cluster id n+i, size in column 3."""
+    parent = list(range(2 * n - 1))
+    size = [1] * n + [0] * (n - 1)
+
+    def find(v):
+        root = v
+        while parent[root] != root:
+            root = parent[root]
+        while parent[v] != root:
+            parent[v], v = root, parent[v]
+        return root
+
+    Z = np.zeros((n - 1, 4))
+    for i, (x, y, h) in enumerate(rows):
+        rx, ry = find(int(x)), find(int(y))
+        lo, hi = (rx, ry) if rx < ry else (ry, rx)
+        new = n + i
+        parent[rx] = parent[ry] = new
+        size[new] = size[rx] + size[ry]
+        Z[i] = (lo, hi, h, size[new])
+    return Z
+
+
+def linkage_restated(dm: np.ndarray, method: str) -> np.ndarray:
+    """Dendrogram from a full fp64 distance matrix, following scipy's two code paths."""
+    n = dm.shape[0]
+    rows = []
+    if method == "single":                       # Prim from node 0, strict '<' -> lowest index on ties
+        best = np.full(n, np.inf)
+        done = np.zeros(n, dtype=bool)
+        x = 0
+        for _ in range(n - 1):
+            done[x] = True
+            cur, y = np.inf, 0
+            for i in range(n):
+                if done[i]:
+                    continue
+                if best[i] > dm[x, i]:
+                    best[i] = dm[x, i]
+                if best[i] < cur:
+                    cur, y = best[i], i
+            rows.append((x, y, cur))
+            x = y
+    elif method == "complete":                   # nearest-neighbour chain, Lance-Williams max update
+        D = dm.copy()
+        size = np.ones(n, dtype=np.int64)
+        chain = []
+        for _ in range(n - 1):
+            if not chain:
+                chain.append(int(np.nonzero(size > 0)[0][0]))
+            while True:
+                x = chain[-1]
+                if len(chain) > 1:
+                    y, cur = chain[-2], D[x, chain[-2]]
+                else:
+                    y, cur = 0, np.inf
+                for i in range(n):
+                    if size[i] == 0 or i == x:
+                        continue
+                    if D[x, i] < cur:
+                        cur, y = D[x, i], i
+                if len(chain) > 1 and y == chain[-2]:
+                    break
+                chain.append(y)
+            chain = chain[:-2]
+            if x > y:
+                x, y = y, x
+            rows.append((x, y, cur))
+            nx, ny = size[x], size[y]
+            size[x], size[y] = 0, nx + ny
+            for i in range(n):
+                if size[i] == 0 or i == y:
+                    continue
+                D[i, y] = D[y, i] = max(D[i, x], D[i, y])
+    else:
+        raise ValueError(method)
+    order = np.argsort(np.array([r[2] for r in rows]), kind="stable")
+    return _label([rows[i] for i in order], n)

@@ -1,0 +1,392 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via hpcs_b200's Python mirror of the reference
+interface) against the CPU oracle on the same seeded inputs, against the committed golden vectors
+(outputs of the reference itself), and -- at BASELINE.json's full sizes -- through size-independent
+properties.  Bars: kNN indices, edge-feature gathers and dendrogram merge order bit-exact; distances,
+losses and gradients within 1e-4 relative of the fp64 oracle (tolerance written at each assert)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hpcs_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-4          # north_star tolerance for floating-point results (vs the fp64 oracle)
+
+
+@pytest.fixture(scope="module")
+def hb():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import hpcs_b200
+    return hpcs_b200
+
+
+def dev(t):
+    return t.cuda()
+
+
+def rel_err(got, want):
+    got, want = got.double().cpu(), want.double().cpu()
+    return ((got - want).norm() / want.norm().clamp_min(1e-300)).item()
+
+
+def t(a, dtype=None):
+    out = torch.from_numpy(np.asarray(a))
+    return out if dtype is None else out.to(dtype)
+
+
+def cloud(gen, B, N):
+    pts = torch.randn(B, N, 3, generator=gen)
+    pts = pts - pts.mean(1, keepdim=True)
+    return (pts / pts.norm(dim=-1).amax(1).view(B, 1, 1)).transpose(1, 2).contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# kNN
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,D,N,k", [(4, 3, 1024, 20), (2, 63, 512, 20), (2, 10, 100, 7), (1, 3, 33, 33),
+                                     (2, 3, 300, 40), (1, 63, 200, 100), (1, 70, 96, 5), (3, 1, 64, 4)])
+def test_knn_bit_exact_vs_canonical_oracle(hb, B, D, N, k):
+    gen = torch.Generator().manual_seed(B * 1000 + D * 10 + k)
+    x = cloud(gen, B, N) if D == 3 else torch.randn(B, D, N, generator=gen)
+    want_i, want_v = O.knn_canonical(x, k, return_values=True)
+    got_i, got_v = hb.knn(dev(x), k, return_values=True)
+    assert got_i.dtype == torch.int64 and tuple(got_i.shape) == (B, N, k)
+    assert torch.equal(got_i.cpu(), want_i)
+    assert torch.equal(got_v.cpu(), want_v)                      # same fp32 bits, not just close
+
+
+def test_knn_ties_lower_index_first(hb):
+    x = torch.zeros(1, 3, 64)
+    x[0, 0] = torch.arange(64).div(4, rounding_mode="floor").float()   # groups of 4 identical points
+    got = hb.knn(dev(x), 6).cpu()
+    assert torch.equal(got, O.knn_canonical(x, 6))
+    assert got[0, 5].tolist()[:4] == [4, 5, 6, 7]
+
+
+@pytest.mark.parametrize("key,k", [("3", 20), ("63", 10)])
+def test_knn_vs_reference_golden(hb, golden, key, k):
+    """Indices produced by the reference's own knn (torch CPU) on the committed inputs: equal
+    wherever the fp64 gap between adjacent ranks exceeds the fp32 error bound (Finding 5)."""
+    g = golden("knn")
+    x, ref = t(g["x" + key]), t(g["idx" + key], torch.int64)
+    got = hb.knn(dev(x), k).cpu()
+    d = O.neg_sqdist_fp64(x)
+    top = d.topk(k + 1, dim=-1)[0]
+    sq = (x.double() ** 2).sum(1)
+    bound = 64 * np.finfo(np.float32).eps * (sq.unsqueeze(-1) + sq.amax(-1, keepdim=True).unsqueeze(-1))
+    amb = ((top[..., :-1] - top[..., 1:]) < bound).any(-1)
+    assert torch.equal(got[~amb], ref[~amb])
+    assert amb.float().mean() < 0.05
+
+
+def test_knn_full_size_properties(hb):
+    """BASELINE config: B=32, N=1024, k=20 for D=3 and D=63."""
+    gen = torch.Generator().manual_seed(7)
+    for x in (cloud(gen, 32, 1024), torch.randn(32, 63, 1024, generator=gen)):
+        idx, val = hb.knn(dev(x), 20, return_values=True)
+        idx, val = idx.cpu(), val.cpu()
+        assert (val[..., :-1] >= val[..., 1:]).all()                           # sorted best-first
+        assert (idx == torch.arange(1024).view(1, -1, 1)).any(-1).all()        # self is a neighbour
+        assert idx.min() >= 0 and idx.max() < 1024
+        assert (idx.sort(-1)[0].diff(dim=-1) > 0).all()                        # no duplicates in a row
+        # k-th selected value bounds every unselected one (checked in fp64 on 2 clouds)
+        d = O.neg_sqdist_fp64(x[:2])
+        kth = torch.gather(d, 2, idx[:2])[..., -1:]
+        mask = torch.ones_like(d, dtype=torch.bool).scatter_(2, idx[:2], False)
+        slack = 1e-5 * (x[:2].double() ** 2).sum(1).amax(-1).view(2, 1, 1)
+        assert (d[mask].view(2, 1024, -1) <= kth + slack).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# edge features
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,C,N,k,cross", [(2, 1, 128, 20, False), (2, 21, 96, 20, False), (2, 3, 33, 5, False),
+                                           (1, 2, 40, 6, True), (2, 1, 64, 8, True)])
+def test_edge_features_fwd_bwd_vs_oracle(hb, B, C, N, k, cross):
+    gen = torch.Generator().manual_seed(C * 100 + N)
+    x = torch.randn(B, C, 3, N, generator=gen)
+    idx = O.knn_canonical(x.view(B, 3 * C, N), k)
+    xo = x.clone().requires_grad_(True)
+    want = O.graph_feature(xo, k, idx=idx, cross=cross)
+    xg = dev(x).requires_grad_(True)
+    fn = hb.get_graph_feature_cross if cross else hb.get_graph_feature
+    got = fn(xg, k=k, idx=dev(idx))
+    assert got.is_contiguous() and tuple(got.shape) == tuple(want.shape)
+    planes = 2 * C
+    assert torch.equal(got[:, :planes].cpu(), want[:, :planes].detach())       # gathers / one subtraction: exact
+    if cross:
+        torch.testing.assert_close(got[:, planes:].cpu(), want[:, planes:].detach(), rtol=1e-6, atol=1e-6)
+    gout = torch.randn(want.shape, generator=gen)
+    (gw,) = torch.autograd.grad(want, xo, gout)
+    (gg,) = torch.autograd.grad(got, xg, dev(gout))
+    assert rel_err(gg, gw) < 1e-5                                               # fp32 sums, different order
+    # dynamic graph (idx=None) must equal the explicit-idx call
+    assert torch.equal(fn(dev(x), k=k), got.detach())
+
+
+def test_edge_features_golden(hb, golden):
+    g = golden("edge_feat")
+    x = dev(t(g["x"])).requires_grad_(True)
+    out = hb.get_graph_feature(x, k=6, idx=dev(t(g["idx"], torch.int64)))
+    assert torch.equal(out.cpu(), t(g["out"]))
+    (gx,) = torch.autograd.grad(out, x, dev(t(g["gout"])))
+    assert rel_err(gx, t(g["gx"])) < 1e-5
+    xc = dev(t(g["xc"])).requires_grad_(True)
+    outc = hb.get_graph_feature_cross(xc, k=5, idx=dev(t(g["idxc"], torch.int64)))
+    torch.testing.assert_close(outc.cpu(), t(g["outc"]), rtol=1e-6, atol=1e-7)
+    (gxc,) = torch.autograd.grad(outc, xc, dev(t(g["goutc"])))
+    assert rel_err(gxc, t(g["gxc"])) < 1e-5
+    fixed = hb.get_graph_feature(dev(t(g["x"])), k=6, x_coord=dev(t(g["coord"])))
+    # fixed graph from coordinates: same neighbours as the reference unless a row is a near-tie
+    same = (fixed.cpu() == t(g["out_fixed"])).float().mean()
+    assert same > 0.99
+
+
+def test_edge_features_full_size_linearity(hb):
+    """B=32, C=21, N=1024, k=20 (330 MB output): out is linear in x for a fixed graph, and the
+    backward is its exact adjoint: <out(x), g> == <x, bwd(g)>."""
+    gen = torch.Generator().manual_seed(11)
+    x = dev(torch.randn(32, 21, 3, 1024, generator=gen))
+    idx = hb.knn(x.view(32, 63, 1024), 20)
+    y1 = hb.get_graph_feature(x, 20, idx=idx)
+    y2 = hb.get_graph_feature(2.0 * x, 20, idx=idx)
+    assert torch.equal(y2, 2.0 * y1)                                            # scaling by 2 is exact in fp32
+    xg = x.clone().requires_grad_(True)
+    y = hb.get_graph_feature(xg, 20, idx=idx)
+    g = torch.randn_like(y)
+    (gx,) = torch.autograd.grad(y, xg, g)
+    lhs = (y.double() * g.double()).sum()
+    rhs = (x.double() * gx.double()).sum()
+    assert abs(lhs - rhs) <= 1e-5 * abs(lhs)
+
+
+# ------------------------------------------------------------------------------------------------
+# hyperbolic ops
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["s1e-3", "s1e-2", "s0.1", "s0.5", "s0.9", "mixed"])
+def test_hyp_lca_vs_reference_fp64_golden(hb, golden, tag):
+    g = golden("hyp_lca")
+    a = dev(t(g[tag + "_a"])).requires_grad_(True)
+    b = dev(t(g[tag + "_b"])).requires_grad_(True)
+    dist = hb.hyp_lca(a, b, return_coord=False)
+    assert tuple(dist.shape) == (a.shape[0], 1)
+    assert rel_err(dist, t(g[tag + "_dist"])) < REL
+    ga, gb = torch.autograd.grad(dist.sum(), (a, b))
+    assert rel_err(ga, t(g[tag + "_ga"])) < REL and rel_err(gb, t(g[tag + "_gb"])) < REL
+    coord = hb.hyp_lca(a, b, return_coord=True)
+    assert rel_err(coord, t(g[tag + "_coord"])) < REL
+    gca, gcb = torch.autograd.grad((coord * dev(t(g[tag + "_gc"]).float())).sum(), (a, b))
+    assert rel_err(gca, t(g[tag + "_gca"])) < REL and rel_err(gcb, t(g[tag + "_gcb"])) < REL
+
+
+def test_expmap_golden_and_grad(hb, golden):
+    g = golden("expmap")
+    u = dev(t(g["u"])).requires_grad_(True)
+    y = hb.ExpMap()(u)
+    assert rel_err(y, t(g["y64"])) < 1e-6
+    gy = torch.randn(y.shape, generator=torch.Generator().manual_seed(0))
+    (gu,) = torch.autograd.grad(y, u, dev(gy))
+    ud = t(g["u"]).double().requires_grad_(True)
+    (want,) = torch.autograd.grad(O.expmap0(ud), ud, gy.double())
+    assert rel_err(gu, want) < REL
+    x3 = dev(torch.randn(2, 5, 32))
+    assert torch.equal(hb.expmap0(x3).view(-1, 32), hb.expmap0(x3.view(-1, 32)))   # any leading shape
+
+
+# ------------------------------------------------------------------------------------------------
+# triplet objective
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["s1e-3", "s0.1", "s0.5"])
+def test_compute_hyp_vs_reference_fp64_golden(hb, golden, tag):
+    """Golden = the reference's MetricHyperbolicLoss.compute_hyp (miner on) evaluated in fp64."""
+    g = golden("compute_hyp")
+    x = dev(t(g["x"])).requires_grad_(True)
+    scale = torch.nn.Parameter(dev(torch.tensor([float(g[tag + "_scale"])])))
+    trip = tuple(t(g["f0.0_" + s], torch.int64) for s in "apn")
+    loss, kept = hb.hyp_triplet_loss(x, trip, scale, float(g[tag + "_temp"]), "easy", 0.0, return_kept=True)
+    assert abs(int(kept) - int(g[tag + "_kept64"])) <= 2          # borderline sim(a,p) == sim(a,n) only
+    assert abs(loss.item() - float(g[tag + "_loss64"])) <= REL * abs(float(g[tag + "_loss64"]))
+    gx, gs = torch.autograd.grad(loss, (x, scale))
+    assert rel_err(gx, t(g[tag + "_gx64"])) < REL
+    assert rel_err(gs, t(g[tag + "_gscale64"])) < REL
+
+
+@pytest.mark.parametrize("n,D,scale,temp,kind", [(2048, 32, 1e-3, 0.05, "easy"), (1024, 50, 0.1, 0.1, "easy"),
+                                                  (512, 4, 0.5, 0.05, "all"), (768, 32, 0.9, 0.05, "semihard"),
+                                                  (640, 128, 0.1, 0.05, "hard"), (300, 7, 0.3, 0.07, "easy")])
+def test_hyp_triplet_loss_vs_oracle_fp64(hb, n, D, scale, temp, kind):
+    gen = torch.Generator().manual_seed(n + D)
+    x = O.expmap0(torch.randn(n, D, generator=gen))
+    labels = torch.randint(0, 6, (n,), generator=gen)
+    torch.manual_seed(5)
+    a, p, ng = O.sample_triplets(labels, t_per_anchor=9, fraction=1.2)
+    margin = 0.05 if kind in ("semihard", "hard") else 0.0
+    xd = x.double().requires_grad_(True)
+    sd = torch.tensor([scale], dtype=torch.float64, requires_grad=True)
+    if kind == "all":
+        fa, fp_, fn_ = a, p, ng
+    else:
+        fa, fp_, fn_ = O.filter_triplets(xd.detach(), a, p, ng, margin=margin, kind=kind)
+    want = O.compute_hyp(xd, fa, fp_, fn_, sd, temp)
+    wgx, wgs = torch.autograd.grad(want, (xd, sd))
+    xg = dev(x).requires_grad_(True)
+    sg = dev(torch.tensor([scale])).requires_grad_(True)
+    got, kept = hb.hyp_triplet_loss(xg, (a, p, ng), sg, temp, kind, margin, return_kept=True)
+    assert abs(int(kept) - fa.numel()) <= max(2, fa.numel() // 20000)
+    assert abs(got.item() - want.item()) <= REL * abs(want.item())
+    ggx, ggs = torch.autograd.grad(got, (xg, sg))
+    assert rel_err(ggx, wgx) < REL
+    assert rel_err(ggs, wgs) < REL
+    # the stand-alone filter agrees with the oracle's filter except on borderline gaps
+    if kind != "all":
+        keep = hb.filter_triplets(dev(x), a, p, ng, margin, kind).cpu()
+        sim = O.cosine_similarity_matrix(x.double())
+        gap = sim[a, p] - sim[a, ng]
+        if kind == "easy":
+            ref_keep = gap > margin
+        elif kind == "semihard":
+            ref_keep = (gap <= margin) & (gap > 0)
+        else:
+            ref_keep = (gap <= margin) & (gap <= 0)
+        differ = keep != ref_keep
+        if differ.any():                                    # only gaps sitting on a threshold may flip in fp32
+            border = torch.minimum(gap[differ].abs(), (gap[differ] - margin).abs())
+            assert (border < 1e-6).all()
+
+
+def test_loss_module_api_and_sampler_parity(hb):
+    """MetricHyperbolicLoss / RandomTripletMarginMiner keep the reference's call shapes; the host
+    sampler consumes the CPU RNG like the reference (same seed -> same triplets as the oracle)."""
+    gen = torch.Generator().manual_seed(3)
+    n, D = 512, 32
+    x = dev(O.expmap0(torch.randn(n, D, generator=gen))).requires_grad_(True)
+    labels = dev(torch.randint(0, 5, (n,), generator=gen))
+    scale = torch.nn.Parameter(dev(torch.tensor([1e-3])))
+    mod = hb.MetricHyperbolicLoss(margin=0.35, t_per_anchor=10, fraction=0.0, scale=scale, temperature=0.05,
+                                  num_class=5, embedding_size=D, cosface=True, miner=True).cuda()
+    torch.manual_seed(9)
+    a, p, ng = hb.get_balanced_random_triplet_indices(labels, t_per_anchor=10, fraction=0.0)
+    torch.manual_seed(9)
+    oa, op, on = O.sample_triplets(labels.cpu(), 10, 0.0)
+    assert torch.equal(a.cpu(), oa) and torch.equal(p.cpu(), op) and torch.equal(ng.cpu(), on)
+    assert a.numel() == 10 * n
+    torch.manual_seed(9)
+    out = mod.compute_loss(x, x, labels)
+    assert set(out) == {"loss_hyp", "loss_metric"}
+    total = out["loss_hyp"]["losses"] + out["loss_metric"]["losses"]
+    total.backward()
+    assert x.grad is not None and torch.isfinite(x.grad).all() and scale.grad is not None
+    want = O.compute_hyp(x.detach().cpu().double(), *O.filter_triplets(x.detach().cpu().double(), oa, op, on),
+                         torch.tensor([1e-3], dtype=torch.float64), 0.05)
+    assert abs(out["loss_hyp"]["losses"].item() - want.item()) <= REL * abs(want.item())
+    torch.manual_seed(9)
+    ma, mp, mn = mod.hyp_miner(x.detach(), labels)
+    assert ma.numel() == mp.numel() == mn.numel() and 0 < ma.numel() < a.numel()
+    logits = mod.get_logits(x.detach(), labels)
+    assert tuple(logits.shape) == (n, 5)
+
+
+def test_loss_full_size_properties(hb):
+    """n = 32*1024 rows, 50 triplets per anchor (1.64 M mined): loss finite, kept count plausible,
+    gradient orthogonal to each row (the objective only sees directions), zero-sum consistency of
+    the closed-form mean term."""
+    gen = torch.Generator().manual_seed(1)
+    n, D = 32 * 1024, 32
+    x = dev(O.expmap0(torch.randn(n, D, generator=gen))).requires_grad_(True)
+    labels = torch.randint(0, 50, (n,), generator=gen)
+    torch.manual_seed(2)
+    a, p, ng = hb.get_balanced_random_triplet_indices(labels, t_per_anchor=50, fraction=0.0)
+    assert a.numel() == 50 * n
+    scale = dev(torch.tensor([1e-3])).requires_grad_(True)
+    loss, kept = hb.hyp_triplet_loss(x, (a, p, ng), scale, 0.05, "easy", 0.0, return_kept=True)
+    assert torch.isfinite(loss) and 0.3 * a.numel() < int(kept) < 0.7 * a.numel()
+    gx, gs = torch.autograd.grad(loss, (x, scale))
+    radial = (gx * x.detach()).sum(-1).abs().max().item()
+    assert radial <= 1e-4 * gx.norm(dim=-1).max().item() * x.detach().norm(dim=-1).max().item() + 1e-9
+    # determinism of the forward value
+    loss2 = hb.hyp_triplet_loss(x.detach(), (a, p, ng), scale.detach(), 0.05, "easy", 0.0)
+    assert abs(loss2.item() - loss.item()) <= 1e-6 * abs(loss.item())
+    # a sub-sample evaluated by the fp64 oracle (dense matrix is only 8192^2 there)
+    sub = 8192
+    keep = (a < sub) & (p < sub) & (ng < sub)
+    sa, sp, sn = a[keep][:200000], p[keep][:200000], ng[keep][:200000]
+    xs = x.detach()[:sub].cpu().double()
+    fa, fp_, fn_ = O.filter_triplets(xs, sa, sp, sn)
+    want = O.compute_hyp(xs, fa, fp_, fn_, torch.tensor([1e-3], dtype=torch.float64), 0.05)
+    got = hb.hyp_triplet_loss(x.detach()[:sub].contiguous(), (sa, sp, sn), scale.detach(), 0.05, "easy", 0.0)
+    assert abs(got.item() - want.item()) <= REL * abs(want.item())
+
+
+# ------------------------------------------------------------------------------------------------
+# decode
+# ------------------------------------------------------------------------------------------------
+def _check_Z(Z, ref):
+    assert np.array_equal(Z[:, [0, 1, 3]], ref[:, [0, 1, 3]])                 # merge order, ids, counts: exact
+    assert np.array_equal(Z[:, 2], ref[:, 2])                                  # heights: same fp64 bits
+
+
+@pytest.mark.parametrize("method", ["single", "complete"])
+@pytest.mark.parametrize("N,D", [(96, 32), (200, 32), (1024, 32), (150, 5), (64, 50)])
+def test_linkage_bit_exact_vs_scipy(hb, method, N, D):
+    from scipy.cluster.hierarchy import linkage
+    gen = torch.Generator().manual_seed(N + D)
+    x = O.expmap0(torch.randn(3, N, D, generator=gen))
+    scale = dev(torch.tensor([1e-3]))
+    Z, leaves = hb.decode_linkage_batch(dev(x), scale, method, return_leaves=True)
+    assert Z.dtype == torch.float64 and tuple(Z.shape) == (3, N - 1, 4)
+    for b in range(3):
+        ref = linkage(leaves[b].cpu().numpy(), method=method, metric="cosine")   # scipy on the SAME fp32 leaves
+        _check_Z(Z[b].cpu().numpy(), ref)
+    # leaves kernel == the reference's normalize_embeddings + project (fp32, elementwise)
+    want = O.project(O.normalize_embeddings(x.view(-1, D), torch.tensor([1e-3]))).view(3, N, D)
+    torch.testing.assert_close(leaves.cpu(), want, rtol=2e-7, atol=0)
+
+
+def test_linkage_duplicates_and_single_cloud_api(hb):
+    from scipy.cluster.hierarchy import linkage
+    gen = torch.Generator().manual_seed(4)
+    x = O.expmap0(torch.randn(120, 32, generator=gen))
+    x[10] = x[3]; x[77] = x[3]; x[50] = x[51]                                   # exact distance ties
+    scale = dev(torch.tensor([0.5]))
+    for method in ("single", "complete"):
+        Z = hb.decode_linkage(dev(x), scale, method)
+        assert isinstance(Z, np.ndarray) and Z.dtype == np.float64 and Z.shape == (119, 4)
+        leaves = hb.normalize_project(dev(x), scale).cpu().numpy()
+        _check_Z(Z, linkage(leaves, method=method, metric="cosine"))
+
+
+@pytest.mark.parametrize("key", ["96", "200", "clu"])
+def test_linkage_vs_reference_golden(hb, golden, key):
+    """Golden Z comes from the reference pipeline (torch-CPU normalize + project + scipy).  The leaves
+    kernel may differ from torch's F.normalize in the last fp32 bit, so heights are compared at
+    1e-6 relative and the merge structure exactly wherever adjacent heights are not within that."""
+    g = golden("decode")
+    x = dev(t(g["x" + key]))
+    for method, z in (("complete", "Zc"), ("single", "Zs")):
+        Z = hb.decode_linkage(x, dev(torch.tensor([1e-3])), method)
+        ref = g[z + key]
+        np.testing.assert_allclose(Z[:, 2], ref[:, 2], rtol=1e-6)
+        assert np.array_equal(Z[:, 3], ref[:, 3]) or np.isclose(np.diff(ref[:, 2]), 0, atol=1e-9).any()
+        assert Z[-1, 3] == x.shape[0]
+
+
+def test_linkage_full_size_valid_dendrogram(hb):
+    """Config 5 shape (N=1024..2048 here, B=8): a valid scipy linkage -- monotone heights, every id
+    used once, root holds all leaves -- and fcluster on it agrees with fcluster on scipy's own Z."""
+    from scipy.cluster.hierarchy import fcluster, is_valid_linkage, linkage
+    gen = torch.Generator().manual_seed(8)
+    cen = torch.randn(6, 32, generator=gen)
+    x = O.expmap0(cen[torch.randint(0, 6, (8, 2048), generator=gen)] + 0.3 * torch.randn(8, 2048, 32, generator=gen))
+    for method in ("single", "complete"):
+        Z, leaves = hb.decode_linkage_batch(dev(x), dev(torch.tensor([1e-3])), method, return_leaves=True)
+        Zc = Z.cpu().numpy()
+        for b in range(8):
+            assert is_valid_linkage(Zc[b])
+            assert (np.diff(Zc[b][:, 2]) >= 0).all() and Zc[b][-1, 3] == 2048
+            ids = np.sort(Zc[b][:, :2].ravel())
+            assert np.array_equal(ids, np.arange(2 * 2048 - 2))
+        ref = linkage(leaves[0].cpu().numpy(), method=method, metric="cosine")
+        _check_Z(Zc[0], ref)
+        assert np.array_equal(fcluster(Zc[0], 6, "maxclust"), fcluster(ref, 6, "maxclust"))

@@ -135,3 +135,18 @@ def test_decode_linkage(golden, key, method, z):
     ref = g[z + key]
     assert np.array_equal(Z[:, [0, 1, 3]], ref[:, [0, 1, 3]])
     np.testing.assert_allclose(Z[:, 2], ref[:, 2], rtol=1e-15, atol=1e-16)
+
+
+@pytest.mark.parametrize("method", ["single", "complete"])
+@pytest.mark.parametrize("D", [32, 5])
+def test_linkage_restatement_matches_scipy(method, D):
+    from scipy.cluster.hierarchy import linkage
+    from scipy.spatial.distance import pdist, squareform
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((60, D)).astype(np.float32)
+    X[7] = X[3]                                        # exact duplicate -> distance ties
+    X[20] = X[3]
+    dm = O.pdist_cosine_restated(X)
+    assert np.array_equal(dm, squareform(pdist(X.astype(np.float64), "cosine")))
+    Z = O.linkage_restated(dm, method)
+    assert np.array_equal(Z, linkage(X.astype(np.float64), method=method, metric="cosine"))
