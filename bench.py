@@ -221,7 +221,7 @@ def run_native(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = ms.item() / args.steps
     value = world * B / (ms_per_step * 1e-3)
-    loss_val, kept_val = float(out[0]), int(out[1])
+    loss_val, kept_val = float(out[0].detach()), int(out[1])
 
     # ---- end-to-end from pinned host buffers ----------------------------------------------------
     pin = {k: host[k].pin_memory() for k in ("pts", "f1", "f2", "emb")}

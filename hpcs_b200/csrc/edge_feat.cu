@@ -106,35 +106,50 @@ edge_feat_fwd_kernel(const float* __restrict__ x, const int64_t* __restrict__ id
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward: reverse CSR
+// backward: reverse graph (target -> sources) in degree-sorted sliced-ELL form
 // ------------------------------------------------------------------------------------------------
-// One CTA per cloud.  rev_ptr[b][N+1], rev_src[b][N*k] (source encoded as n'*k + j, ascending per
-// target).  Shared memory: N counters.
-__global__ void __launch_bounds__(1024)
-edge_rev_csr_kernel(const int64_t* __restrict__ idx, int N, int k, int* __restrict__ rev_ptr,
-                    int* __restrict__ rev_src, int* __restrict__ slot_tmp) {
-    extern __shared__ int cnt[];                            // [N] counts, then running offsets
-    __shared__ int warp_tot[32];
-    const int b = blockIdx.x;
-    const int E = N * k;
-    const int64_t* idb = idx + (size_t)b * E;
-    int* ptr = rev_ptr + (size_t)b * (N + 1);
-    int* src = rev_src + (size_t)b * E;
-    int* slot = slot_tmp + (size_t)b * E;
-    for (int i = threadIdx.x; i < N; i += blockDim.x) cnt[i] = 0;
-    __syncthreads();
-    for (int e = threadIdx.x; e < E; e += blockDim.x) {
-        unsigned m = (unsigned)__ldg(idb + e);
-        m = m < (unsigned)N ? m : (unsigned)(N - 1);
-        slot[e] = atomicAdd(&cnt[m], 1);                    // arrival order, fixed up by the sort below
-    }
-    __syncthreads();
-    // exclusive scan of cnt[0..N) -> ptr; block-wide, chunked by blockDim
+// kNN graphs in feature space are hub-heavy (in-degree up to ~N/4 at mean k), so the reverse lists are
+// stored so that a warp of 32 targets of SIMILAR in-degree reads them coalesced:
+//   perm[r]          target with degree rank r (descending)
+//   group g          = ranks [32g, 32g+32); gslots[g] = largest in-degree in the group; goff[g] = start
+//   ell[goff[g] + s*32 + l]  = s-th source (encoded n'*k + j, ascending) of target perm[32g+l], or the
+//                              sentinel E (points at a zero) past the end of that target's list.
+// Size: sum_g 32*gslots[g] <= E + 32*maxdeg.  The workspace holds E + 32*N entries, enough for any idx
+// whose rows are duplicate-free (every kNN result); otherwise the build falls back to plain CSR
+// (mode = 1) and the gather takes its thread-per-row path.
+struct RevGraph {
+    int* hdr;      // [8]: mode, total
+    int* perm;     // [N]
+    int* gslots;   // [G]
+    int* goff;     // [G+1]
+    int* ptr;      // [N+1]  CSR offsets (always written)
+    int* ell;      // [E + 32N]  (CSR src[E] in fallback mode)
+    size_t ints_per_cloud;
+};
+
+__host__ __device__ inline RevGraph rev_graph(int* base, int b, int N, int k) {
+    const size_t E = (size_t)N * k, G = (N + 31) / 32;
+    RevGraph r;
+    size_t per = 8 + (size_t)N + G + (G + 1) + (N + 1) + (E + 32 * (size_t)N);
+    per = (per + 63) / 64 * 64;
+    int* p = base + (size_t)b * per;
+    r.hdr = p;            p += 8;
+    r.perm = p;           p += N;
+    r.gslots = p;         p += G;
+    r.goff = p;           p += G + 1;
+    r.ptr = p;            p += N + 1;
+    r.ell = p;
+    r.ints_per_cloud = per;
+    return r;
+}
+
+// exclusive scan of in[0..L) into out[0..L] (out[L] = total); whole block takes part; L arbitrary
+__device__ inline void block_excl_scan(const int* in, int* out, int L, int* warp_tot) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     int carry = 0;
-    for (int base = 0; base < N; base += blockDim.x) {
+    for (int base = 0; base < L; base += blockDim.x) {
         const int i = base + threadIdx.x;
-        const int v = i < N ? cnt[i] : 0;
+        const int v = i < L ? in[i] : 0;
         int inc = v;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -150,43 +165,137 @@ edge_rev_csr_kernel(const int64_t* __restrict__ idx, int N, int k, int* __restri
                 const int t = __shfl_up_sync(kFull, w, o);
                 if (lane >= o) w += t;
             }
-            warp_tot[lane] = w;                             // inclusive totals
+            warp_tot[lane] = w;
         }
         __syncthreads();
-        const int before = carry + (warp > 0 ? warp_tot[warp - 1] : 0) + inc - v;
-        if (i < N) { ptr[i] = before; cnt[i] = before; }
+        if (i < L) out[i] = carry + (warp > 0 ? warp_tot[warp - 1] : 0) + inc - v;
         carry += warp_tot[nwarp - 1];
         __syncthreads();
     }
-    if (threadIdx.x == 0) ptr[N] = E;
+    if (threadIdx.x == 0) out[L] = carry;
     __syncthreads();
-    for (int e = threadIdx.x; e < E; e += blockDim.x) {
-        unsigned m = (unsigned)__ldg(idb + e);
-        m = m < (unsigned)N ? m : (unsigned)(N - 1);
-        src[cnt[m] + slot[e]] = e;
+}
+
+// One CTA (NW warps) per cloud.  A stable counting sort of the E edges by target without atomics: warp w
+// owns the contiguous edge range [w*chunk, (w+1)*chunk) and a private histogram row hist[w][.]; inside a
+// 32-edge step __match_any_sync ranks equal targets by lane.  The resulting lists are ascending in e, so
+// the gather sums in a fixed order (deterministic gradients).
+__global__ void __launch_bounds__(1024)
+edge_rev_build_kernel(const int64_t* __restrict__ idx, int N, int k, int* __restrict__ ws) {
+    extern __shared__ int sm_i[];
+    __shared__ int warp_tot[32];
+    __shared__ int s_mode;
+    const int NW = blockDim.x >> 5;
+    const int G = (N + 31) / 32;
+    int* hist = sm_i;                         // [NW][N]
+    int* deg = hist + (size_t)NW * N;         // [N]
+    int* off = deg + N;                       // [N+1]
+    int* bins = off + N + 1;                  // [N+2]  rows per degree key, then start offsets
+    int* rank = bins + N + 2;                 // [N]
+    int* gsl = rank + N;                      // [G] group slots, then [G+1] offsets in gof
+    int* gof = gsl + G;                       // [G+1]
+    const int b = blockIdx.x;
+    const int E = N * k;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t* idb = idx + (size_t)b * E;
+    const RevGraph R = rev_graph(ws, b, N, k);
+    const int chunk = ((E + NW - 1) / NW + 31) / 32 * 32;
+
+    for (int i = threadIdx.x; i < NW * N; i += blockDim.x) hist[i] = 0;
+    for (int i = threadIdx.x; i < N + 2; i += blockDim.x) bins[i] = 0;
+    __syncthreads();
+    // target of edge e, or a per-lane dummy key past N for idle lanes (so they never match a real target)
+    auto target_of = [&](int e) -> unsigned {
+        if (e >= E) return (unsigned)(N + lane);
+        const unsigned t = (unsigned)__ldg(idb + e);
+        return t < (unsigned)N ? t : (unsigned)(N - 1);
+    };
+    // per-warp histograms (loads issued 4 steps at a time so their L2 latency overlaps)
+    for (int i0 = 0; i0 < chunk; i0 += 128) {
+        unsigned tq[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) tq[u] = target_of(i0 + 32 * u < chunk ? warp * chunk + i0 + 32 * u + lane : E);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned t = tq[u];
+            const unsigned mask = __match_any_sync(kFull, t);
+            if (t < (unsigned)N && lane == __ffs(mask) - 1) hist[warp * N + t] += __popc(mask);
+            __syncwarp();
+        }
     }
     __syncthreads();
-    // make each list ascending (deterministic summation order); lists are short (mean k)
-    for (int i = threadIdx.x; i < N; i += blockDim.x) {
-        const int lo = cnt[i], hi = (i + 1 < N) ? cnt[i + 1] : E;
-        for (int p = lo + 1; p < hi; ++p) {
-            const int key = src[p];
-            int q = p - 1;
-            while (q >= lo && src[q] > key) { src[q + 1] = src[q]; --q; }
-            src[q + 1] = key;
+    // exclusive prefix over warps per target -> in-degree
+    for (int t = threadIdx.x; t < N; t += blockDim.x) {
+        int run = 0;
+        for (int w = 0; w < NW; ++w) { const int c = hist[w * N + t]; hist[w * N + t] = run; run += c; }
+        deg[t] = run;
+        atomicAdd(&bins[N - min(run, N)], 1);                   // key 0 = largest degree
+    }
+    __syncthreads();
+    block_excl_scan(deg, off, N, warp_tot);
+    for (int t = threadIdx.x; t <= N; t += blockDim.x) R.ptr[t] = off[t];
+    block_excl_scan(bins, bins, N + 1, warp_tot);               // bins[key] = first rank of that key
+    for (int t = threadIdx.x; t < N; t += blockDim.x) {
+        const int r = atomicAdd(&bins[N - min(deg[t], N)], 1);  // order inside one degree is irrelevant
+        rank[t] = r;
+        R.perm[r] = t;
+    }
+    __syncthreads();
+    for (int g = threadIdx.x; g < G; g += blockDim.x) gsl[g] = deg[R.perm[g * 32]];   // largest of the group
+    __syncthreads();
+    block_excl_scan(gsl, gof, G, warp_tot);
+    if (threadIdx.x == 0) {
+        const long long total = 32ll * gof[G];
+        s_mode = total <= (long long)E + 32ll * N ? 0 : 1;
+        R.hdr[0] = s_mode;
+        R.hdr[1] = (int)(s_mode == 0 ? total : E);
+    }
+    __syncthreads();
+    const int mode = s_mode;
+    if (mode == 0) {
+        for (int g = threadIdx.x; g < G; g += blockDim.x) { R.gslots[g] = gsl[g]; R.goff[g] = 32 * gof[g]; }
+        if (threadIdx.x == 0) R.goff[G] = 32 * gof[G];
+        const int total = 32 * gof[G];
+        for (int i = threadIdx.x; i < total; i += blockDim.x) R.ell[i] = E;      // sentinel
+        __syncthreads();
+    }
+    // placement, same edge order as the counting pass
+    for (int i0 = 0; i0 < chunk; i0 += 128) {
+        unsigned tq[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) tq[u] = target_of(i0 + 32 * u < chunk ? warp * chunk + i0 + 32 * u + lane : E);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const unsigned t = tq[u];
+            const int e = warp * chunk + i0 + 32 * u + lane;
+            const bool valid = t < (unsigned)N;
+            const unsigned mask = __match_any_sync(kFull, t);
+            if (valid) {
+                const int pos = hist[warp * N + t] + __popc(mask & ((1u << lane) - 1u));
+                if (mode == 0) {
+                    const int r = rank[t];
+                    R.ell[32 * gof[r >> 5] + pos * 32 + (r & 31)] = e;
+                } else {
+                    R.ell[off[t] + pos] = e;
+                }
+            }
+            __syncwarp();
+            if (valid && lane == __ffs(mask) - 1) hist[warp * N + t] += __popc(mask);
+            __syncwarp();
         }
     }
 }
 
-// grid: (3C, B); block 512.  One (cloud, channel*3+component) plane per CTA.
+// grid: (3C, B); block 1024.  One (cloud, channel*3+component) plane per CTA.
 //   gx[n] = sum_j gctr[n,j] - sum_j gdiff[n,j] + sum_{(n',j): idx[n',j]=n} gdiff[n',j]   (+ cross terms)
-// STAGED: the gdiff plane is copied to shared memory first.
+// STAGED: the gdiff plane is copied to shared memory (+ a zero at [E] for the ELL sentinel) and, when
+// rows are float4-aligned, the per-float4 partial row sums of (gctr - gdiff) are formed during that same
+// coalesced pass, so both planes are read from HBM exactly once with 128-bit loads.
 template <bool STAGED, bool CROSS>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(1024)
 edge_feat_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ x, const int64_t* __restrict__ idx,
-                     const int* __restrict__ rev_ptr, const int* __restrict__ rev_src, int C, int N, int k,
-                     int vec, float* __restrict__ gx) {
-    extern __shared__ __align__(16) float gs[];            // STAGED: [N*k] (+ 2 more planes for CROSS)
+                     int* __restrict__ ws, int C, int N, int k, int vec, float* __restrict__ gx) {
+    extern __shared__ __align__(16) float gs[];            // STAGED: [E + 4] plane, then [E/4] row partials
     const int b = blockIdx.y;
     const int ch = blockIdx.x;                              // c*3 + a
     const int c = ch / 3, a = ch % 3;
@@ -195,61 +304,126 @@ edge_feat_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ x
     const float* gb = gout + (size_t)b * planes * C * 3 * E;
     const float* g_diff = gb + ((size_t)c * 3 + a) * E;
     const float* g_ctr = gb + ((size_t)(C + c) * 3 + a) * E;
-    const int* ptr = rev_ptr + (size_t)b * (N + 1);
-    const int* src = rev_src + (size_t)b * E;
+    const RevGraph R = rev_graph(ws, b, N, k);
+    float* rpart = gs + (E + 4);
+    const bool fused_rows = STAGED && vec;
 
     if (STAGED) {
         if (vec) {
-            const float4* s4 = reinterpret_cast<const float4*>(g_diff);
-            float4* d4 = reinterpret_cast<float4*>(gs);
-            for (int e = threadIdx.x; e < E / 4; e += blockDim.x) d4[e] = __ldcs(s4 + e);
+            const float4* d4 = reinterpret_cast<const float4*>(g_diff);
+            const float4* c4 = reinterpret_cast<const float4*>(g_ctr);
+            float4* s4 = reinterpret_cast<float4*>(gs);
+            for (int f = threadIdx.x; f < E / 4; f += blockDim.x) {
+                const float4 d = __ldcs(d4 + f), t = __ldcs(c4 + f);
+                s4[f] = d;
+                rpart[f] = (t.x - d.x) + (t.y - d.y) + (t.z - d.z) + (t.w - d.w);
+            }
         } else {
             for (int e = threadIdx.x; e < E; e += blockDim.x) gs[e] = __ldcs(g_diff + e);
         }
+        if (threadIdx.x == 0) gs[E] = 0.f;
         __syncthreads();
     }
     const float* gd = STAGED ? gs : g_diff;
 
-    // cross(f, x) with f = x_m (neighbour), x = x_n (centre):
-    //   out_a = f_{a+1} x_{a+2} - f_{a+2} x_{a+1}
-    // d/d x_n[a]: from out_{a+1} = f_{a+2} x_a - f_a x_{a+2}  -> +f_{a+2} g_{a+1}
-    //             from out_{a+2} = f_a x_{a+1} - f_{a+1} x_a  -> -f_{a+1} g_{a+2}
-    // d/d f[a]  : from out_{a+1}: -x_{a+2} g_{a+1};  from out_{a+2}: +x_{a+1} g_{a+2}
+    // cross(f, x) with f = x_m (neighbour), x = x_n (centre):  out_a = f_{a+1} x_{a+2} - f_{a+2} x_{a+1}
+    // d/d x_n[a]: +f_{a+2} g_{a+1} - f_{a+1} g_{a+2};   d/d f[a]: -x_{a+2} g_{a+1} + x_{a+1} g_{a+2}
     const int a1 = (a + 1) % 3, a2 = (a + 2) % 3;
     const float* g_c1 = gb + ((size_t)(2 * C + c) * 3 + a1) * E;
     const float* g_c2 = gb + ((size_t)(2 * C + c) * 3 + a2) * E;
     const float* xc = x + ((size_t)b * C + c) * 3 * N;
     const int64_t* idb = idx + (size_t)b * E;
+    float* out = gx + ((size_t)b * C * 3 + ch) * N;
 
-    for (int n = threadIdx.x; n < N; n += blockDim.x) {
-        float acc = 0.f;
+    auto own_row = [&](int n) -> float {
+        float own = 0.f;
         const size_t row = (size_t)n * k;
-        if (vec) {
-            for (int j = 0; j < k; j += 4) {
-                const float4 d = *reinterpret_cast<const float4*>(gd + row + j);
-                const float4 t = __ldcs(reinterpret_cast<const float4*>(g_ctr + row + j));
-                acc += (t.x - d.x) + (t.y - d.y) + (t.z - d.z) + (t.w - d.w);
-            }
+        if (fused_rows) {
+            const int q = k >> 2;
+            for (int i = 0; i < q; ++i) own += rpart[n * q + i];
         } else {
-            for (int j = 0; j < k; ++j) acc += __ldcs(g_ctr + row + j) - gd[row + j];
+            for (int j = 0; j < k; ++j) own += __ldg(g_ctr + row + j) - gd[row + j];
         }
-        const int lo = __ldg(ptr + n), hi = __ldg(ptr + n + 1);
-        for (int p = lo; p < hi; ++p) acc += gd[__ldg(src + p)];
         if (CROSS) {
-            // centre role of n
             for (int j = 0; j < k; ++j) {
                 unsigned m = (unsigned)__ldg(idb + row + j);
                 m = m < (unsigned)N ? m : (unsigned)(N - 1);
-                acc += __ldg(xc + a2 * N + m) * __ldg(g_c1 + row + j) - __ldg(xc + a1 * N + m) * __ldg(g_c2 + row + j);
-            }
-            // neighbour role of n
-            for (int p = lo; p < hi; ++p) {
-                const int e = __ldg(src + p);
-                const int nn = e / k;
-                acc += __ldg(xc + a1 * N + nn) * __ldg(g_c2 + e) - __ldg(xc + a2 * N + nn) * __ldg(g_c1 + e);
+                own += __ldg(xc + a2 * N + m) * __ldg(g_c1 + row + j) - __ldg(xc + a1 * N + m) * __ldg(g_c2 + row + j);
             }
         }
-        gx[((size_t)b * C * 3 + ch) * N + n] = acc;
+        return own;
+    };
+    auto edge_val = [&](int e) -> float {
+        if (!STAGED && e >= E) return 0.f;
+        float v = gd[e];
+        if (CROSS && e < E) {
+            const int nn = e / k;
+            v += __ldg(xc + a1 * N + nn) * __ldg(g_c2 + e) - __ldg(xc + a2 * N + nn) * __ldg(g_c1 + e);
+        }
+        return v;
+    };
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    if (R.hdr[0] == 0) {
+        const int G = (N + 31) / 32;
+        auto ell_sum = [&](int g, int s_begin, int s_end) -> float {
+            const int* col = R.ell + __ldg(R.goff + g) + lane;
+            float acc = 0.f;
+            int s = s_begin;
+            for (; s + 16 <= s_end; s += 16) {                // 16 independent coalesced loads in flight
+                int e[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) e[q] = __ldg(col + (s + q) * 32);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) acc += edge_val(e[q]);
+            }
+            if (s + 8 <= s_end) {
+                int e[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) e[q] = __ldg(col + (s + q) * 32);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc += edge_val(e[q]);
+                s += 8;
+            }
+            for (; s < s_end; ++s) acc += edge_val(__ldg(col + s * 32));
+            return acc;
+        };
+        // groups are sorted by in-degree: the few hub groups first, all warps sharing each of them (partials
+        // combined in warp order, so the sum stays deterministic), then one warp per ordinary group
+        constexpr int kBig = 96;
+        __shared__ float part[32][32];
+        int g0 = 0;
+        for (; g0 < G && __ldg(R.gslots + g0) > kBig; ++g0) {
+            const int slots = __ldg(R.gslots + g0);
+            const int per = (slots + nwarp - 1) / nwarp;
+            part[warp][lane] = ell_sum(g0, min(warp * per, slots), min((warp + 1) * per, slots));
+            __syncthreads();
+            if (warp == 0) {
+                float acc = 0.f;
+                for (int w = 0; w < nwarp; ++w) acc += part[w][lane];
+                const int r = g0 * 32 + lane;
+                if (r < N) {
+                    const int t = __ldg(R.perm + r);
+                    out[t] = own_row(t) + acc;
+                }
+            }
+            __syncthreads();
+        }
+        for (int g = g0 + warp; g < G; g += nwarp) {
+            const float acc = ell_sum(g, 0, __ldg(R.gslots + g));
+            const int r = g * 32 + lane;
+            if (r < N) {
+                const int t = __ldg(R.perm + r);
+                out[t] = own_row(t) + acc;
+            }
+        }
+    } else {                                                 // CSR fallback: thread per target
+        for (int n = threadIdx.x; n < N; n += blockDim.x) {
+            float acc = 0.f;
+            const int lo = __ldg(R.ptr + n), hi = __ldg(R.ptr + n + 1);
+            for (int p = lo; p < hi; ++p) acc += edge_val(__ldg(R.ell + p));
+            out[n] = own_row(n) + acc;
+        }
     }
 }
 
@@ -289,8 +463,8 @@ int hpcs_edge_feat_fwd_f32(const float* x, const int64_t* idx, int B, int C, int
 }
 
 size_t hpcs_edge_feat_bwd_workspace_bytes(int B, int N, int k) {
-    const size_t E = (size_t)N * k;
-    return hpcs::align_up((size_t)B * (N + 1) * sizeof(int), 256) + 2 * hpcs::align_up((size_t)B * E * sizeof(int), 256);
+    if (B <= 0 || N <= 0 || k <= 0) return 0;
+    return hpcs::align_up((size_t)B * hpcs::rev_graph(nullptr, 0, N, k).ints_per_cloud * sizeof(int), 256);
 }
 
 int hpcs_edge_feat_bwd_f32(const float* gout, const float* x, const int64_t* idx, int B, int C, int N, int k,
@@ -299,33 +473,31 @@ int hpcs_edge_feat_bwd_f32(const float* gout, const float* x, const int64_t* idx
     if (!gout || !idx || !gx || !ws || (cross && !x)) return fail(HPCS_ERR_ARG, "edge_feat_bwd: null pointer");
     if (B <= 0 || C <= 0 || N <= 0 || k <= 0) return fail(HPCS_ERR_ARG, "edge_feat_bwd: bad shape");
     if (ws_bytes < hpcs_edge_feat_bwd_workspace_bytes(B, N, k)) return fail(HPCS_ERR_WORKSPACE, "edge_feat_bwd: workspace too small");
-    if ((size_t)N * sizeof(int) > 200 * 1024) return fail(HPCS_ERR_ARG, "edge_feat_bwd: N=%d too large (max 51200)", N);
     if (B > 65535) return fail(HPCS_ERR_ARG, "edge_feat_bwd: B > 65535");
     cudaStream_t st = as_stream(stream);
     const size_t E = (size_t)N * k;
-    char* w = static_cast<char*>(ws);
-    int* rev_ptr = reinterpret_cast<int*>(w);
-    w += align_up((size_t)B * (N + 1) * sizeof(int), 256);
-    int* rev_src = reinterpret_cast<int*>(w);
-    w += align_up((size_t)B * E * sizeof(int), 256);
-    int* slot_tmp = reinterpret_cast<int*>(w);
-
+    int* wsi = static_cast<int*>(ws);
     {
-        const size_t smem = (size_t)N * sizeof(int);
-        cudaFuncSetAttribute(edge_rev_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        edge_rev_csr_kernel<<<B, 1024, smem, st>>>(idx, N, k, rev_ptr, rev_src, slot_tmp);
-        int rc = check_launch("edge_rev_csr_kernel");
+        // warps per CTA: as many private histogram rows as fit in ~128 KB of shared memory
+        const int G = (N + 31) / 32;
+        int nw = 32;
+        while (nw > 1 && (size_t)nw * N * sizeof(int) > 128 * 1024) nw >>= 1;
+        const size_t smem = ((size_t)nw * N + (size_t)N + (N + 1) + (N + 2) + N + G + (G + 1)) * sizeof(int);
+        if (smem > 220 * 1024) return fail(HPCS_ERR_ARG, "edge_feat_bwd: N=%d too large (max ~9000)", N);
+        cudaFuncSetAttribute(edge_rev_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        edge_rev_build_kernel<<<B, nw * 32, smem, st>>>(idx, N, k, wsi);
+        int rc = check_launch("edge_rev_build_kernel");
         if (rc) return rc;
     }
-    dim3 grid(3 * C, B), block(512);
-    const size_t smem = E * sizeof(float);
-    const bool staged = smem <= 200 * 1024;
+    dim3 grid(3 * C, B), block(1024);
     const int vec = (k % 4 == 0) && ((reinterpret_cast<uintptr_t>(gout) & 15) == 0);
+    const size_t smem = (E + 4) * sizeof(float) + (vec ? E / 4 * sizeof(float) : 0);
+    const bool staged = smem <= 200 * 1024;
 #define HPCS_LAUNCH_BWD(S, X)                                                                          \
     {                                                                                                  \
         auto kern = edge_feat_bwd_kernel<S, X>;                                                        \
         if (S) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
-        kern<<<grid, block, S ? smem : 0, st>>>(gout, x, idx, rev_ptr, rev_src, C, N, k, vec, gx);          \
+        kern<<<grid, block, S ? smem : 0, st>>>(gout, x, idx, wsi, C, N, k, vec, gx);                  \
     }
     if (staged) { if (cross) HPCS_LAUNCH_BWD(true, true) else HPCS_LAUNCH_BWD(true, false) }
     else        { if (cross) HPCS_LAUNCH_BWD(false, true) else HPCS_LAUNCH_BWD(false, false) }

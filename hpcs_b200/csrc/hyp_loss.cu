@@ -65,16 +65,20 @@ hyp_prep_kernel(const float* __restrict__ x, int64_t n, int D, const float* __re
     __shared__ float red[256][4];
     const int sub = threadIdx.x % LPT, grp = threadIdx.x / LPT;
     float4 colsum = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int64_t row = (int64_t)blockIdx.x * RPB + grp; row < n; row += (int64_t)gridDim.x * RPB) {
+    // the trip count is uniform per block (every lane takes part in the shuffles); rows past n are masked
+    for (int64_t row0 = (int64_t)blockIdx.x * RPB; row0 < n; row0 += (int64_t)gridDim.x * RPB) {
+        const int64_t row = row0 + grp;
+        const bool live = row < n;
         float v[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
             const int d = sub * 4 + t;
-            v[t] = d < D ? __ldg(x + row * D + d) : 0.f;
+            v[t] = (live && d < D) ? __ldg(x + row * D + d) : 0.f;
         }
         float ss = v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
 #pragma unroll
         for (int o = LPT / 2; o > 0; o >>= 1) ss += __shfl_xor_sync(kFull, ss, o);
+        if (!live) continue;
         const float inv = 1.f / fmaxf(sqrtf(ss), kNormEps);
         const float4 r = make_float4(v[0] * inv, v[1] * inv, v[2] * inv, v[3] * inv);
         *reinterpret_cast<float4*>(u + row * DP + sub * 4) = r;
@@ -112,7 +116,6 @@ hyp_triplet_kernel(const float* __restrict__ u, float* __restrict__ G, HypHeader
                    const int64_t* __restrict__ a, const int64_t* __restrict__ p, const int64_t* __restrict__ ng,
                    int64_t T0, int64_t n, float inv_temp, int filter_mode, float margin,
                    uint8_t* __restrict__ keep_out) {
-    constexpr int TPR = 32 / LPT;                   // triplets per round
     const int lane = threadIdx.x & 31;
     const int sub = lane % LPT, grp = lane / LPT;
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -137,7 +140,7 @@ hyp_triplet_kernel(const float* __restrict__ u, float* __restrict__ G, HypHeader
         float c_ap = 0.f, c_an = 0.f, c_pn = 0.f;
 #pragma unroll
         for (int r = 0; r < LPT; ++r) {
-            const int slot = r * TPR + grp;
+            const int slot = grp * LPT + r;       // triplet grp*LPT+r: its owner lane sits in this group
             const unsigned ra = __shfl_sync(kFull, ia, slot);
             const unsigned rp = __shfl_sync(kFull, ip, slot);
             const unsigned rn = __shfl_sync(kFull, in_, slot);
@@ -165,7 +168,7 @@ hyp_triplet_kernel(const float* __restrict__ u, float* __restrict__ G, HypHeader
             const unsigned keep_mask = __ballot_sync(kFull, keep);
 #pragma unroll
             for (int r = 0; r < LPT; ++r) {
-                const int slot = r * TPR + grp;
+                const int slot = grp * LPT + r;       // triplet grp*LPT+r: its owner lane sits in this group
                 const unsigned ra = __shfl_sync(kFull, ia, slot);
                 const unsigned rp = __shfl_sync(kFull, ip, slot);
                 const unsigned rn = __shfl_sync(kFull, in_, slot);
@@ -221,13 +224,17 @@ hyp_bwd_kernel(const float* __restrict__ gloss, const float* __restrict__ scale,
     const float inv_n2 = (float)(1.0 / ((double)n * (double)n));
     float4 sv = make_float4((float)hdr->S[sub * 4] * inv_n2, (float)hdr->S[sub * 4 + 1] * inv_n2,
                             (float)hdr->S[sub * 4 + 2] * inv_n2, (float)hdr->S[sub * 4 + 3] * inv_n2);
-    for (int64_t row = (int64_t)blockIdx.x * RPB + grp; row < n; row += (int64_t)gridDim.x * RPB) {
-        const float4 uu = *reinterpret_cast<const float4*>(u + row * DP + sub * 4);
-        const float4 gg = *reinterpret_cast<const float4*>(G + row * DP + sub * 4);
+    for (int64_t row0 = (int64_t)blockIdx.x * RPB; row0 < n; row0 += (int64_t)gridDim.x * RPB) {
+        const int64_t row = row0 + grp;
+        const bool live = row < n;
+        const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 uu = live ? *reinterpret_cast<const float4*>(u + row * DP + sub * 4) : zero4;
+        const float4 gg = live ? *reinterpret_cast<const float4*>(G + row * DP + sub * 4) : zero4;
         float4 gu = make_float4(fmaf(gg.x, inv_k, sv.x), fmaf(gg.y, inv_k, sv.y), fmaf(gg.z, inv_k, sv.z), fmaf(gg.w, inv_k, sv.w));
         float dt = dot4(gu, uu);
 #pragma unroll
         for (int o = LPT / 2; o > 0; o >>= 1) dt += __shfl_xor_sync(kFull, dt, o);
+        if (!live) continue;
         const float inv = invn[row];
         // |x| below eps: F.normalize divides by the constant eps, so the Jacobian is I / eps
         if (inv >= 1.f / kNormEps) dt = 0.f;

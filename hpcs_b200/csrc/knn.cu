@@ -15,10 +15,12 @@
 #include <float.h>
 
 #include "common.cuh"
+#include "knn_rows.cuh"
 
 namespace hpcs {
 
 constexpr int kKnnWarps = 8;
+constexpr int kRowQueue = 48;          // per-thread FIFO depth of the row-parallel kernel (flush when > 16 pending)
 
 __global__ void knn_sqnorm_kernel(const float* __restrict__ x, int D, int N, float* __restrict__ sq) {
     const int b = blockIdx.y;
@@ -165,6 +167,110 @@ knn_kernel(const float* __restrict__ x, const float* __restrict__ sq, int D, int
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Row-parallel exact kernel (the fast path for D = 3 and D = 63, k <= 40)
+// ------------------------------------------------------------------------------------------------
+// One thread = one query row, its D features in registers.  The CTA streams candidate tiles
+// [D][TC] (+ their norms) through shared memory; a warp reads 4 consecutive candidates of one
+// feature with a single broadcast LDS.128, so the inner loop is 4 independent canonical fma chains.
+// Selection: RowSelector (knn_rows.cuh).  Same canonical arithmetic and order as knn_kernel.
+template <int D, int K, int THREADS, int TC>
+__global__ void __launch_bounds__(THREADS)
+knn_rows_kernel(const float* __restrict__ x, const float* __restrict__ sq, int N, int k,
+                int64_t* __restrict__ idx, float* __restrict__ val) {
+    constexpr int QCAP = kRowQueue;
+    extern __shared__ __align__(16) float smem[];
+    float* cs = smem;                                  // [D][TC]
+    float* sqc = cs + D * TC;                          // [TC]
+    float* qv = sqc + TC;                              // [QCAP][THREADS]
+    int* qj = reinterpret_cast<int*>(qv + QCAP * THREADS);
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * THREADS + threadIdx.x;  // query row (may be >= N in the last CTA)
+    const float* xb = x + (size_t)b * D * N;
+    const float* sqb = sq + (size_t)b * N;
+    const int iq = i < N ? i : N - 1;                  // idle rows shadow the last one (keeps warps uniform)
+
+    float q[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) q[d] = __ldg(xb + (size_t)d * N + iq);
+    const float nsq = -__ldg(sqb + iq);
+
+    RowSelector<K, QCAP> sel;
+    sel.init(qv + threadIdx.x, qj + threadIdx.x, THREADS);
+
+    for (int j0 = 0; j0 < N; j0 += TC) {
+        __syncthreads();                               // previous tile fully consumed
+        for (int e = threadIdx.x; e < D * TC; e += THREADS) {
+            const int d = e / TC, c = e - d * TC;
+            cs[e] = j0 + c < N ? __ldg(xb + (size_t)d * N + j0 + c) : 0.f;
+        }
+        for (int c = threadIdx.x; c < TC; c += THREADS) sqc[c] = j0 + c < N ? __ldg(sqb + j0 + c) : 0.f;
+        __syncthreads();
+        const int lim = min(TC, N - j0);
+        for (int c0 = 0; c0 < lim; c0 += 32) {
+            sel.maybe_flush(32);
+#pragma unroll
+            for (int c = c0; c < c0 + 32; c += 4) {
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    const float4 cv = *reinterpret_cast<const float4*>(cs + d * TC + c);
+                    a0 = __fmaf_rn(q[d], cv.x, a0);
+                    a1 = __fmaf_rn(q[d], cv.y, a1);
+                    a2 = __fmaf_rn(q[d], cv.z, a2);
+                    a3 = __fmaf_rn(q[d], cv.w, a3);
+                }
+                const float4 sv = *reinterpret_cast<const float4*>(sqc + c);
+                const float p0 = __fsub_rn(__fmaf_rn(2.f, a0, nsq), sv.x);
+                const float p1 = __fsub_rn(__fmaf_rn(2.f, a1, nsq), sv.y);
+                const float p2 = __fsub_rn(__fmaf_rn(2.f, a2, nsq), sv.z);
+                const float p3 = __fsub_rn(__fmaf_rn(2.f, a3, nsq), sv.w);
+                const int j = j0 + c;
+                if (j + 0 < N) sel.offer(p0, j + 0);
+                if (j + 1 < N) sel.offer(p1, j + 1);
+                if (j + 2 < N) sel.offer(p2, j + 2);
+                if (j + 3 < N) sel.offer(p3, j + 3);
+            }
+        }
+    }
+    sel.flush();
+    if (i < N) {
+        int64_t* oi = idx + ((size_t)b * N + i) * k;
+        float* ov = val ? val + ((size_t)b * N + i) * k : nullptr;
+#pragma unroll
+        for (int m = 0; m < K; ++m) {
+            if (m < k) {
+                const int jj = sel.top.idx[m];
+                oi[m] = jj < N ? jj : i;
+                if (ov) ov[m] = sel.top.val[m];
+            }
+        }
+    }
+}
+
+template <int D, int K>
+static int launch_knn_rows(const float* x, const float* sq, int B, int N, int k, int64_t* idx, float* val,
+                           cudaStream_t st) {
+    constexpr int THREADS = 64;
+    constexpr int TC = D <= 4 ? 512 : 128;
+    constexpr size_t smem = ((size_t)D * TC + TC + 2 * kRowQueue * THREADS) * sizeof(float);
+    auto kern = knn_rows_kernel<D, K, THREADS, TC>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<dim3((N + THREADS - 1) / THREADS, B), THREADS, smem, st>>>(x, sq, N, k, idx, val);
+    return check_launch("knn_rows_kernel");
+}
+
+template <int D>
+static int dispatch_rows(const float* x, const float* sq, int B, int N, int k, int64_t* idx, float* val,
+                         cudaStream_t st, bool* handled) {
+    *handled = true;
+    if (k <= 10) return launch_knn_rows<D, 10>(x, sq, B, N, k, idx, val, st);
+    if (k <= 20) return launch_knn_rows<D, 20>(x, sq, B, N, k, idx, val, st);
+    if (k <= 40) return launch_knn_rows<D, 40>(x, sq, B, N, k, idx, val, st);
+    *handled = false;
+    return HPCS_OK;
+}
+
 template <int DREG, int QW, int SLOTS>
 static int launch_knn(const float* x, const float* sq, int B, int D, int N, int k, int64_t* idx, float* val,
                       cudaStream_t st) {
@@ -215,6 +321,10 @@ int hpcs_knn_f32(const float* x, int B, int D, int N, int k, int64_t* idx, float
     knn_sqnorm_kernel<<<dim3((N + 255) / 256, B), 256, 0, st>>>(x, D, N, sq);
     int rc = check_launch("knn_sqnorm_kernel");
     if (rc) return rc;
+    bool handled = false;
+    if (D == 3) rc = dispatch_rows<3>(x, sq, B, N, k, idx, val, st, &handled);
+    else if (D == 63) rc = dispatch_rows<63>(x, sq, B, N, k, idx, val, st, &handled);
+    if (handled) return rc;
     if (D <= 4) return dispatch_slots<4, 4>(x, sq, B, D, N, k, idx, val, st);
     if (D <= 32) return dispatch_slots<32, 4>(x, sq, B, D, N, k, idx, val, st);
     return dispatch_slots<64, 4>(x, sq, B, D, N, k, idx, val, st);
