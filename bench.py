@@ -152,7 +152,7 @@ def run_native(args):
 
     d = {k: v.to(dev) for k, v in host.items()}
     trip = tuple(t.to(dev) for t in trip_host)
-    scale = torch.tensor([SCALE], device=dev, requires_grad=True)
+    scale = torch.tensor([SCALE], device=dev)
     gen = torch.Generator(device=dev).manual_seed(rank)
     E = N_PTS * K_NN
     g1 = torch.randn(B, 2, 3, N_PTS, K_NN, device=dev, generator=gen)
@@ -185,10 +185,11 @@ def run_native(args):
         gx2 = layer(inp["f1"], g2, "knn_d63", "edge_fwd_c21", "edge_bwd_c21", record)
         gx3 = layer(inp["f2"], g3, "knn_d63", "edge_fwd_c21", "edge_bwd_c21", record)
         emb = inp["emb"].detach().requires_grad_(True)
+        sc = scale.detach().requires_grad_(True)            # fresh leaves: keeps autograd on the capturing stream
 
         def loss_fb():
-            loss, kept = hb.hyp_triplet_loss(emb, tr, scale, TEMPERATURE, "easy", 0.0, return_kept=True)
-            ge, gs = torch.autograd.grad(loss, (emb, scale))
+            loss, kept = hb.hyp_triplet_loss(emb, tr, sc, TEMPERATURE, "easy", 0.0, return_kept=True)
+            ge, gs = torch.autograd.grad(loss, (emb, sc))
             return loss, kept, ge, gs
         loss, kept, ge, gs = timed("hyp_loss_fwd_bwd", loss_fb, record)
         if world > 1:
@@ -201,21 +202,49 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- resident-input timing ------------------------------------------------------------------
+    def capture(inp, tr):
+        """Warm up on a side stream, then capture one step over static buffers into a CUDA graph."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                step(inp, tr)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            outs = step(inp, tr)
+        return graph, outs
+
+    # ---- resident-input timing: K replays of the captured step ------------------------------------
     for _ in range(max(args.warmup, 3)):
         out = step(d, trip)
+    launches_per_step = None
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count()
+    out = step(d, trip)
+    launches_per_step = _lib.launch_count() - l0
+    use_graph = not args.no_graph
+    if use_graph:
+        graph, out = capture(d, trip)
+        run_step = graph.replay
+    else:
+        def run_step():
+            nonlocal out
+            out = step(d, trip)
+    for _ in range(max(args.warmup, 3)):
+        run_step()
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    launches0 = _lib.launch_count()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(args.steps):
-        out = step(d, trip, record=True)
+        run_step()
     t1.record()
     barrier()
-    launches = _lib.launch_count() - launches0
     clocks = sampler.stop()
+    launches = launches_per_step * args.steps
     ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -223,32 +252,84 @@ def run_native(args):
     value = world * B / (ms_per_step * 1e-3)
     loss_val, kept_val = float(out[0].detach()), int(out[1])
 
-    # ---- end-to-end from pinned host buffers ----------------------------------------------------
+    # ---- per-op durations: same steps, eager, CUDA events around every op ---------------------------
+    for _ in range(args.steps):
+        step(d, trip, record=True)
+    barrier()
+
+    # ---- end-to-end from pinned host buffers ----------------------------------------------------------
+    # Every step uploads its inputs (points, layer inputs, embeddings, mined triplets) from pinned host
+    # memory and downloads its results (loss, kept, d scale, the four input gradients).  Two device
+    # buffer sets alternate, so the upload of step i+1 and the download of step i-1 overlap the compute
+    # of step i on separate streams; all of it is inside the timed region.
     pin = {k: host[k].pin_memory() for k in ("pts", "f1", "f2", "emb")}
     trip_pin = tuple(t.pin_memory() for t in trip_host)
     h2d_bytes = sum(v.numel() * v.element_size() for v in pin.values()) + sum(t.numel() * 8 for t in trip_pin)
-    res_host = None
+    sets = []
+    for _ in range(2):
+        inp = {k: torch.empty_like(v, device=dev) for k, v in pin.items()}
+        tr = tuple(torch.empty_like(t, device=dev) for t in trip_pin)
+        for k in pin:
+            inp[k].copy_(pin[k])
+        for a_, b_ in zip(tr, trip_pin):
+            a_.copy_(b_)
+        if use_graph:
+            g_, outs = capture(inp, tr)
+        else:
+            g_, outs = None, None
+        sets.append({"inp": inp, "tr": tr, "graph": g_, "outs": outs})
 
-    def e2e_step():
-        inp = {k: v.to(dev, non_blocking=True) for k, v in pin.items()}
-        tr = tuple(t.to(dev, non_blocking=True) for t in trip_pin)
-        loss, kept, gs, grads = step(inp, tr)
-        outs = [loss.reshape(1), kept.reshape(1).float(), gs.reshape(1)] + [g.reshape(-1) for g in grads]
-        return [o.to("cpu", non_blocking=True) for o in outs]
+    def flat_outs(outs):
+        loss, kept, gs, grads = outs
+        return [loss.reshape(1), kept.reshape(1), gs.reshape(1)] + [g.reshape(-1) for g in grads]
 
-    for _ in range(3):
-        res_host = e2e_step()
+    probe = flat_outs(sets[0]["outs"] if use_graph else step(sets[0]["inp"], sets[0]["tr"]))
+    res_pin = [[torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in probe] for _ in range(2)]
+    d2h_bytes = sum(o.numel() * o.element_size() for o in probe)
+    s_up, s_run, s_down = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    ev_up = [torch.cuda.Event() for _ in range(2)]
+    ev_run = [torch.cuda.Event() for _ in range(2)]
+    ev_down = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_loop(n_steps):
+        for i in range(n_steps):
+            st_ = sets[i % 2]
+            with torch.cuda.stream(s_up):
+                s_up.wait_event(ev_run[i % 2])               # buffer set free (its previous compute finished)
+                for k in pin:
+                    st_["inp"][k].copy_(pin[k], non_blocking=True)
+                for a_, b_ in zip(st_["tr"], trip_pin):
+                    a_.copy_(b_, non_blocking=True)
+                ev_up[i % 2].record(s_up)
+            with torch.cuda.stream(s_run):
+                s_run.wait_event(ev_up[i % 2])
+                s_run.wait_event(ev_down[i % 2])             # previous results of this set already copied out
+                if use_graph:
+                    st_["graph"].replay()
+                    outs = st_["outs"]
+                else:
+                    outs = step(st_["inp"], st_["tr"])
+                ev_run[i % 2].record(s_run)
+            with torch.cuda.stream(s_down):
+                s_down.wait_event(ev_run[i % 2])
+                for dst, src in zip(res_pin[i % 2], flat_outs(outs)):
+                    dst.copy_(src, non_blocking=True)
+                ev_down[i % 2].record(s_down)
+
+    e2e_loop(4)
     barrier()
-    d2h_bytes = sum(o.numel() * o.element_size() for o in res_host)
-    t0.record()
-    for _ in range(args.steps):
-        res_host = e2e_step()
-    t1.record()
+    te0, te1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    te0.record()
+    e2e_loop(args.steps)
+    for s_ in (s_up, s_run, s_down):
+        torch.cuda.current_stream().wait_stream(s_)
+    te1.record()
     barrier()
-    ms_e = torch.tensor([t0.elapsed_time(t1)], device=dev)
+    ms_e = torch.tensor([te0.elapsed_time(te1)], device=dev)
     if world > 1:
         dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
     e2e_value = world * B / (ms_e.item() / args.steps * 1e-3)
+    e2e_loss = float(res_pin[(args.steps - 1) % 2][0])
 
     if rank != 0:
         return
@@ -282,7 +363,10 @@ def run_native(args):
                    "clouds_per_gpu": B, "points": N_PTS, "k": K_NN, "feat_channels": [1, C_FEAT, C_FEAT],
                    "emb_dim": D_EMB, "triplets_mined": T0, "triplets_kept": kept_val, "filter": "easy",
                    "scale": SCALE, "temperature": TEMPERATURE, "parallelism": f"dp{world}",
-                   "l2": "per-step working set ~1.4 GB (edge-feature tensors) exceeds the 126 MB L2; no explicit flush"},
+                   "l2": "per-step working set ~1.4 GB (edge-feature tensors) exceeds the 126 MB L2; no explicit flush",
+                   "launch": "cuda-graph replay of one captured step" if use_graph else "eager",
+                   "ops_timing": "same step run eagerly with CUDA events around every op, after the timed region",
+                   "e2e_pipeline": "2 device buffer sets; upload / compute / download on 3 streams"},
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                 "d2h_bytes_per_step": int(d2h_bytes)},
         "gpu_launches": int(launches),
@@ -290,6 +374,7 @@ def run_native(args):
         "roofline": roofline,
         "ops": ops,
         "loss": loss_val,
+        "e2e_loss": e2e_loss,
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_pass(steps=2, warmup=1)
@@ -365,6 +450,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
