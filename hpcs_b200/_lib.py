@@ -30,6 +30,7 @@ SIGNATURES = {
     "hpcs_launch_count": (_c.c_uint64, []),
     "hpcs_knn_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "hpcs_knn_f32": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
+    "hpcs_knn_ffma_f32": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "hpcs_edge_feat_fwd_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "hpcs_edge_feat_bwd_workspace_bytes": (_Z, [_I, _I, _I]),
     "hpcs_edge_feat_bwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _Z, _P]),

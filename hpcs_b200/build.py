@@ -14,12 +14,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libhpcs_b200.so")
+OBJ_DIR = os.path.join(LIB_DIR, "obj")
 
-SOURCES = ["abi.cu", "knn.cu", "edge_feat.cu", "hyp_loss.cu", "hyp_ops.cu", "linkage.cu"]
+SOURCES = ["abi.cu", "knn.cu", "knn_tc.cu", "edge_feat.cu", "hyp_loss.cu", "hyp_ops.cu", "linkage.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
 
 
@@ -30,28 +31,51 @@ def _nvcc() -> str:
     return cand
 
 
-def _stale() -> bool:
-    if not os.path.exists(LIB_PATH):
+def _headers():
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hs.append(os.path.join(os.path.dirname(HERE), "include", "hpcs_b200.h"))
+    return hs
+
+
+def _newer(target: str, deps) -> bool:
+    if not os.path.exists(target):
         return True
-    built = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)]
-    deps.append(os.path.join(os.path.dirname(HERE), "include", "hpcs_b200.h"))
+    built = os.path.getmtime(target)
     return any(os.path.getmtime(d) > built for d in deps)
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
-        return LIB_PATH
-    os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc(), *NVCC_FLAGS]
-    if verbose:
-        cmd += ["-Xptxas", "-v"]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB_PATH]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or proc.returncode != 0:
-        sys.stderr.write(proc.stdout + proc.stderr)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed building libhpcs_b200.so")
+    """Compile each .cu to an object (in parallel, only the stale ones) and link the shared library."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    headers = _headers()
+    jobs = []
+    for src in SOURCES:
+        path = os.path.join(CSRC, src)
+        obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+        if force or _newer(obj, [path, *headers]):
+            cmd = [_nvcc(), *NVCC_FLAGS, "-c", path, "-o", obj]
+            if verbose:
+                cmd += ["-Xptxas", "-v"]
+            jobs.append(cmd)
+    objs = [os.path.join(OBJ_DIR, s.replace(".cu", ".o")) for s in SOURCES]
+
+    def run(cmd):
+        return cmd, subprocess.run(cmd, capture_output=True, text=True)
+
+    if jobs:
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as pool:
+            for cmd, proc in pool.map(run, jobs):
+                if verbose or proc.returncode != 0:
+                    sys.stderr.write(" ".join(cmd[-3:]) + "\n" + proc.stdout + proc.stderr)
+                if proc.returncode != 0:
+                    raise RuntimeError(f"nvcc failed on {cmd[-3]}")
+    if jobs or not os.path.exists(LIB_PATH):
+        proc = subprocess.run([_nvcc(), "-shared", *objs, "-o", LIB_PATH], capture_output=True, text=True)
+        if proc.returncode != 0:
+            sys.stderr.write(proc.stdout + proc.stderr)
+            raise RuntimeError("link of libhpcs_b200.so failed")
     return LIB_PATH
 
 

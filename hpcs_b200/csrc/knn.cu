@@ -19,6 +19,12 @@
 
 namespace hpcs {
 
+// tensor-core path (knn_tc.cu)
+bool knn_tc_applicable(int D, int N, int k);
+size_t knn_tc_workspace_bytes(int B, int D, int N, int k);
+int knn_tc_run(const float* x, int B, int D, int N, int k, int64_t* idx, float* val, void* ws, size_t ws_bytes,
+               cudaStream_t st);
+
 constexpr int kKnnWarps = 8;
 constexpr int kRowQueue = 48;          // per-thread FIFO depth of the row-parallel kernel (flush when > 16 pending)
 
@@ -303,20 +309,8 @@ static int dispatch_slots(const float* x, const float* sq, int B, int D, int N, 
 
 }  // namespace hpcs
 
-extern "C" {
-
-size_t hpcs_knn_workspace_bytes(int B, int D, int N, int k) {
-    (void)D; (void)k;
-    return hpcs::align_up((size_t)B * N * sizeof(float), 256);
-}
-
-int hpcs_knn_f32(const float* x, int B, int D, int N, int k, int64_t* idx, float* val, void* ws,
-                 size_t ws_bytes, void* stream) {
+static int knn_ffma(const float* x, int B, int D, int N, int k, int64_t* idx, float* val, void* ws, cudaStream_t st) {
     using namespace hpcs;
-    if (!x || !idx || !ws) return fail(HPCS_ERR_ARG, "knn: null pointer");
-    if (B <= 0 || D <= 0 || N <= 0 || k <= 0 || k > N) return fail(HPCS_ERR_ARG, "knn: bad shape B=%d D=%d N=%d k=%d", B, D, N, k);
-    if (ws_bytes < hpcs_knn_workspace_bytes(B, D, N, k)) return fail(HPCS_ERR_WORKSPACE, "knn: workspace too small");
-    cudaStream_t st = as_stream(stream);
     float* sq = static_cast<float*>(ws);
     knn_sqnorm_kernel<<<dim3((N + 255) / 256, B), 256, 0, st>>>(x, D, N, sq);
     int rc = check_launch("knn_sqnorm_kernel");
@@ -328,6 +322,42 @@ int hpcs_knn_f32(const float* x, int B, int D, int N, int k, int64_t* idx, float
     if (D <= 4) return dispatch_slots<4, 4>(x, sq, B, D, N, k, idx, val, st);
     if (D <= 32) return dispatch_slots<32, 4>(x, sq, B, D, N, k, idx, val, st);
     return dispatch_slots<64, 4>(x, sq, B, D, N, k, idx, val, st);
+}
+
+static int knn_check(const float* x, int B, int D, int N, int k, int64_t* idx, void* ws, size_t ws_bytes) {
+    using namespace hpcs;
+    if (!x || !idx || !ws) return fail(HPCS_ERR_ARG, "knn: null pointer");
+    if (B <= 0 || D <= 0 || N <= 0 || k <= 0 || k > N) return fail(HPCS_ERR_ARG, "knn: bad shape B=%d D=%d N=%d k=%d", B, D, N, k);
+    if (ws_bytes < hpcs_knn_workspace_bytes(B, D, N, k)) return fail(HPCS_ERR_WORKSPACE, "knn: workspace too small");
+    return HPCS_OK;
+}
+
+extern "C" {
+
+size_t hpcs_knn_workspace_bytes(int B, int D, int N, int k) {
+    size_t need = hpcs::align_up((size_t)B * N * sizeof(float), 256);
+    if (hpcs::knn_tc_applicable(D, N, k)) {
+        const size_t tc = hpcs::knn_tc_workspace_bytes(B, D, N, k);
+        if (tc > need) need = tc;
+    }
+    return need;
+}
+
+int hpcs_knn_f32(const float* x, int B, int D, int N, int k, int64_t* idx, float* val, void* ws,
+                 size_t ws_bytes, void* stream) {
+    using namespace hpcs;
+    int rc = knn_check(x, B, D, N, k, idx, ws, ws_bytes);
+    if (rc) return rc;
+    if (knn_tc_applicable(D, N, k)) return knn_tc_run(x, B, D, N, k, idx, val, ws, ws_bytes, as_stream(stream));
+    return knn_ffma(x, B, D, N, k, idx, val, ws, as_stream(stream));
+}
+
+int hpcs_knn_ffma_f32(const float* x, int B, int D, int N, int k, int64_t* idx, float* val, void* ws,
+                      size_t ws_bytes, void* stream) {
+    using namespace hpcs;
+    int rc = knn_check(x, B, D, N, k, idx, ws, ws_bytes);
+    if (rc) return rc;
+    return knn_ffma(x, B, D, N, k, idx, val, ws, as_stream(stream));
 }
 
 }  // extern "C"

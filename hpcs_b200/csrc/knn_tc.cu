@@ -1,0 +1,496 @@
+// kNN for the feature-space EdgeConv layers (16 <= D <= 63): Gram term on the 5th-generation tensor
+// cores, exact fp32 re-rank, so the selected indices stay bit-exact with the canonical order.
+//
+//   1. knn_pack_kernel      x[B,D,N] -> K-major rows  xa[i] = (x_i, 1, 0..)   xb[j] = (x_j, -|x_j|^2/2, 0..)
+//                           (64 fp32 per row) + canonical norms.  With the extra column the tensor-core
+//                           product is directly the ranking key  S_ij = x_i.x_j - |x_j|^2/2  (= pd_ij/2 + const_i).
+//   2. knn_tc_kernel        one CTA per (cloud, 128 query rows).  A producer warp streams 128-candidate
+//                           tiles of xb with TMA (128B-swizzled boxes) and issues tcgen05.mma kind::tf32
+//                           (M=128, N=128, K=8 x 8) into a double-buffered TMEM accumulator; four epilogue
+//                           warps (thread = query row = TMEM lane) read the scores with tcgen05.ld and keep
+//                           the KL best per row.  A key is the shifted score pd/2 with the candidate index
+//                           embedded in its low mantissa bits, so the sorted insert is 2 min/max per slot.
+//   3. knn_rerank_kernel    one warp per row: canonical fp32 fma-chain distance of the KL candidates
+//                           (rows of xb staged coalesced through shared memory), bitonic sort by
+//                           (value desc, index asc), and a safety test: the k-th exact value must beat the
+//                           best value any non-candidate can have (KL-th key + TF32/quantisation error bound).
+//   4. knn_fallback_kernel  rows that fail the test (near-ties denser than the error bound, duplicates)
+//                           are redone exactly over all N candidates; the list lives on the device, no sync.
+#include <cuda.h>
+#include <float.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace hpcs {
+
+constexpr int kKP = 64;                 // padded row length (fp32) of xa / xb
+constexpr int kTM = 128;                // query rows per CTA  (UMMA M)
+constexpr int kTN = 128;                // candidates per tile  (UMMA N)
+constexpr int kTcQueue = 48;            // per-row FIFO depth in the epilogue
+constexpr int kAtomBytes = kTM * 128;   // one 32-fp32 K-atom of a 128-row tile
+
+// ---- 1. pack ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+knn_pack_kernel(const float* __restrict__ x, int D, int N, float* __restrict__ xa, float* __restrict__ xb,
+                float* __restrict__ sq, unsigned* __restrict__ xmax_bits) {
+    __shared__ float tile[kKP][33];
+    const int b = blockIdx.y;
+    const int n0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+    const float* xb_in = x + (size_t)b * D * N;
+    for (int d = ty; d < kKP; d += 8) tile[d][tx] = (d < D && n0 + tx < N) ? __ldg(xb_in + (size_t)d * N + n0 + tx) : 0.f;
+    __syncthreads();
+    if (ty == 0 && n0 + tx < N) {                                      // canonical norm: fma chain over d ascending
+        float s = 0.f;
+        for (int d = 0; d < D; ++d) s = __fmaf_rn(tile[d][tx], tile[d][tx], s);
+        sq[(size_t)b * N + n0 + tx] = s;
+        tile[kKP - 1][tx] = s;                                         // column 63 is free (D <= 63)
+        atomicMax(xmax_bits + b, __float_as_uint(s));                  // s >= 0: uint order == float order
+    }
+    __syncthreads();
+    // write rows: thread (ty, tx) -> rows ty, ty+8, ..; columns tx and tx+32 (coalesced 128 B per half row)
+    for (int r = ty; r < 32; r += 8) {
+        const int n = n0 + r;
+        if (n >= N) continue;
+        const size_t row = ((size_t)b * N + n) * kKP;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int d = tx + 32 * h;
+            float va = tile[d][r], vb = va;
+            if (d == kKP - 1) { va = 1.f; vb = -0.5f * tile[kKP - 1][r]; }
+            xa[row + d] = va;
+            xb[row + d] = vb;
+        }
+    }
+}
+
+// ---- key helpers -------------------------------------------------------------------------------------------
+// key = fp32 (score - h_i) with the low `bits` mantissa bits replaced by the candidate index
+__device__ __forceinline__ float make_key(float shifted, unsigned j, unsigned keep_mask) {
+    return __uint_as_float((__float_as_uint(shifted) & keep_mask) | j);
+}
+
+template <int KL>
+struct KeyTopK {
+    float key[KL];
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int m = 0; m < KL; ++m) key[m] = -INFINITY;
+    }
+    __device__ __forceinline__ void insert(float v) {               // v = -inf is a no-op
+#pragma unroll
+        for (int m = KL - 1; m >= 1; --m) key[m] = fmaxf(key[m], fminf(key[m - 1], v));
+        key[0] = fmaxf(key[0], v);
+    }
+};
+
+// ---- 2. tensor-core candidate kernel --------------------------------------------------------------------------
+template <int KL>
+__global__ void __launch_bounds__(160, 2)
+knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+              const float* __restrict__ sq, int N, unsigned keep_mask, float* __restrict__ cand /*[B*N][KL] keys*/) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char* sA = smem;                                          // 2 K-atoms x 16 KB
+    unsigned char* sB = smem + 2 * kAtomBytes;                         // 2 K-atoms x 16 KB
+    float* qk = reinterpret_cast<float*>(smem + 4 * kAtomBytes);       // [kTcQueue][128] pending keys
+    uint64_t* bars = reinterpret_cast<uint64_t*>(qk + kTcQueue * kTM); // full_a, full_b, mma[2], epi[2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+    uint64_t* full_a = bars, *full_b = bars + 1, *mma_done = bars + 2, *epi_done = bars + 4;
+
+    const int b = blockIdx.y;
+    const int m0 = blockIdx.x * kTM;                                   // first query row of this CTA (in the cloud)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int T = (N + kTN - 1) / kTN;
+
+    if (threadIdx.x == 0) {
+        ptx::mbar_init(full_a, 1);
+        ptx::mbar_init(full_b, 1);
+        ptx::mbar_init(mma_done, 1); ptx::mbar_init(mma_done + 1, 1);
+        ptx::mbar_init(epi_done, 4); ptx::mbar_init(epi_done + 1, 4);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 4) ptx::tmem_alloc<2 * kTN>(tmem_slot);
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    ptx::tc_fence_after_sync();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ===== producer: TMA + MMA issue (one elected lane) =====
+        if (lane == 0) {
+            ptx::tma_prefetch_desc(&map_a);
+            ptx::tma_prefetch_desc(&map_b);
+            const int rowA = b * N + m0;
+            ptx::mbar_arrive_expect_tx(full_a, 2 * kAtomBytes);
+            ptx::tma_load_2d(sA, &map_a, full_a, 0, rowA);
+            ptx::tma_load_2d(sA + kAtomBytes, &map_a, full_a, 32, rowA);
+            const uint32_t idesc = ptx::umma_idesc_tf32(kTM, kTN);
+            const uint32_t a_addr = ptx::smem_u32(sA), b_addr = ptx::smem_u32(sB);
+            for (int t = 0; t < T; ++t) {
+                if (t >= 1) ptx::mbar_wait(mma_done + ((t - 1) & 1), ((t - 1) >> 1) & 1);   // B buffer free
+                const int rowB = b * N + t * kTN;
+                ptx::mbar_arrive_expect_tx(full_b, 2 * kAtomBytes);
+                ptx::tma_load_2d(sB, &map_b, full_b, 0, rowB);
+                ptx::tma_load_2d(sB + kAtomBytes, &map_b, full_b, 32, rowB);
+                if (t == 0) ptx::mbar_wait(full_a, 0);
+                ptx::mbar_wait(full_b, t & 1);
+                if (t >= 2) ptx::mbar_wait(epi_done + (t & 1), ((t >> 1) - 1) & 1);         // accumulator drained
+                ptx::tc_fence_after_sync();
+                const uint32_t acc = tmem_base + (t & 1) * kTN;
+#pragma unroll
+                for (int ka = 0; ka < 2; ++ka) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {                                       // 8 tf32 = 32 bytes per MMA
+                        const uint64_t da = ptx::umma_desc_k_sw128(a_addr + ka * kAtomBytes + kk * 32);
+                        const uint64_t db = ptx::umma_desc_k_sw128(b_addr + ka * kAtomBytes + kk * 32);
+                        ptx::umma_tf32(acc, da, db, idesc, (ka | kk) != 0);
+                    }
+                }
+                ptx::umma_commit(mma_done + (t & 1));
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue: thread = query row = TMEM lane =====
+        const int row = warp * 32 + lane;                              // row in tile
+        const int i = m0 + row;                                        // row in cloud
+        const float h = 0.5f * __ldg(sq + (size_t)b * N + min(i, N - 1));
+        KeyTopK<KL> top;
+        top.init();
+        float tau = -INFINITY;
+        int qlen = 0;
+        float* myq = qk + row;
+        auto flush = [&]() {
+            int rounds = qlen;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) rounds = max(rounds, __shfl_xor_sync(kFull, rounds, o));
+            for (int r = 0; r < rounds; ++r) top.insert(r < qlen ? myq[r * kTM] : -INFINITY);
+            qlen = 0;
+            tau = top.key[KL - 1];
+        };
+        for (int t = 0; t < T; ++t) {
+            ptx::mbar_wait(mma_done + (t & 1), (t >> 1) & 1);
+            ptx::tc_fence_after_sync();
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (t & 1) * kTN;
+#pragma unroll 1
+            for (int c0 = 0; c0 < kTN; c0 += 32) {
+                if (__any_sync(kFull, qlen > kTcQueue - 32)) flush();
+                float v[32];
+                ptx::tmem_ld_32x32(taddr + c0, v);
+                const unsigned jbase = t * kTN + c0;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const unsigned j = jbase + c;
+                    const float key = make_key(v[c] - h, j, keep_mask);
+                    if (j < (unsigned)N && key > tau) { myq[qlen * kTM] = key; ++qlen; }
+                }
+            }
+            ptx::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(epi_done + (t & 1));
+        }
+        flush();
+        if (i < N) {
+            float* out = cand + ((size_t)b * N + i) * KL;
+#pragma unroll
+            for (int m = 0; m < KL; m += 4)
+                *reinterpret_cast<float4*>(out + m) = make_float4(top.key[m], top.key[m + 1], top.key[m + 2], top.key[m + 3]);
+        }
+    }
+    ptx::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 4) ptx::tmem_dealloc<2 * kTN>(tmem_base);
+}
+
+// ---- 3. exact re-rank ------------------------------------------------------------------------------------------
+// One warp per query row, lane c <-> candidate c (KL == 32) or candidates c, c+32 (KL == 64).
+template <int KL>
+__global__ void __launch_bounds__(256)
+knn_rerank_kernel(const float* __restrict__ xb, const float* __restrict__ sq, const float* __restrict__ cand,
+                  const unsigned* __restrict__ xmax_bits, int D, int N, int k, unsigned keep_mask, int idx_bits,
+                  int64_t* __restrict__ idx, float* __restrict__ val, int* __restrict__ fb_list, int* __restrict__ fb_count) {
+    constexpr int CPL = KL / 32;                                       // candidates per lane
+    constexpr int RS = kKP + 4;                                        // padded smem row stride
+    extern __shared__ __align__(16) float sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* rows = sm + (size_t)warp * (KL * RS + kKP);                 // [KL][RS] candidate rows
+    float* qrow = rows + KL * RS;                                      // [64] query row
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * 8 + warp;
+    if (i >= N) return;
+    const size_t gi = (size_t)b * N + i;
+    const float sq_i = __ldg(sq + gi);
+
+    float key[CPL];
+    int cj[CPL];
+#pragma unroll
+    for (int u = 0; u < CPL; ++u) {
+        key[u] = __ldg(cand + gi * KL + u * 32 + lane);
+        const unsigned jj = __float_as_uint(key[u]) & ~keep_mask;
+        cj[u] = (key[u] == -INFINITY || jj >= (unsigned)N) ? -1 : (int)jj;
+    }
+    // stage: query row (coalesced) and candidate rows, two rows per warp instruction (16 lanes x float4 each)
+    *reinterpret_cast<float2*>(qrow + 2 * lane) = __ldg(reinterpret_cast<const float2*>(xb + gi * kKP) + lane);
+    const int half = lane >> 4, q4 = lane & 15;
+#pragma unroll
+    for (int u = 0; u < CPL; ++u) {
+#pragma unroll 4
+        for (int r = 0; r < 32; r += 2) {
+            const int src = __shfl_sync(kFull, cj[u], r + half);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (src >= 0) v = __ldg(reinterpret_cast<const float4*>(xb + ((size_t)b * N + src) * kKP) + q4);
+            *reinterpret_cast<float4*>(rows + (size_t)(u * 32 + r + half) * RS + 4 * q4) = v;
+        }
+    }
+    __syncwarp();
+    // canonical distance: fma chain over d ascending, pd = fmaf(2, dot, -sq_i) - sq_j
+    float pd[CPL];
+#pragma unroll
+    for (int u = 0; u < CPL; ++u) {
+        const float* cr = rows + (size_t)(u * 32 + lane) * RS;
+        float acc = 0.f;
+        for (int d = 0; d < D; d += 4) {
+            const float4 c4 = *reinterpret_cast<const float4*>(cr + d);
+            const float4 a4 = *reinterpret_cast<const float4*>(qrow + d);
+            acc = __fmaf_rn(a4.x, c4.x, acc);
+            if (d + 1 < D) acc = __fmaf_rn(a4.y, c4.y, acc);
+            if (d + 2 < D) acc = __fmaf_rn(a4.z, c4.z, acc);
+            if (d + 3 < D) acc = __fmaf_rn(a4.w, c4.w, acc);
+        }
+        const float sq_j = -2.f * cr[kKP - 1];                         // column 63 holds -|x_j|^2 / 2 exactly
+        pd[u] = cj[u] >= 0 ? __fsub_rn(__fmaf_rn(2.f, acc, -sq_i), sq_j) : -INFINITY;
+        if (cj[u] < 0) cj[u] = 0x7fffffff;
+    }
+    // bitonic sort of the KL = 32*CPL elements (position e = u*32 + lane): descending value, ascending index
+    // on ties.  Strides >= 32 pair two registers of the same lane, smaller strides pair lanes by shuffle.
+    auto before = [](float va, int ja, float vb, int jb) { return va > vb || (va == vb && ja < jb); };
+#pragma unroll
+    for (int size = 2; size <= KL; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            if (stride >= 32) {
+                const int us = stride >> 5;
+#pragma unroll
+                for (int u = 0; u < CPL; ++u) {
+                    if ((u & us) == 0) {                               // u holds the earlier position of the pair
+                        const int w = u | us;
+                        const bool desc = (((u << 5) | lane) & size) == 0;
+                        const bool first_ok = before(pd[u], cj[u], pd[w], cj[w]);
+                        if (first_ok != desc) {
+                            const float tv = pd[u]; pd[u] = pd[w]; pd[w] = tv;
+                            const int tj = cj[u]; cj[u] = cj[w]; cj[w] = tj;
+                        }
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < CPL; ++u) {
+                    const int e = (u << 5) | lane;
+                    const float ov = __shfl_xor_sync(kFull, pd[u], stride);
+                    const int oj = __shfl_xor_sync(kFull, cj[u], stride);
+                    const bool lower = (lane & stride) == 0;           // this lane holds the earlier position
+                    const bool desc = (e & size) == 0;
+                    const bool mine_first = before(pd[u], cj[u], ov, oj);
+                    const bool keep = (lower == desc) ? mine_first : !mine_first;
+                    if (!keep) { pd[u] = ov; cj[u] = oj; }
+                }
+            }
+        }
+    }
+    // safety: best possible exact value of any non-candidate < k-th exact value of the candidates
+    const float kth = __shfl_sync(kFull, pd[(k - 1) >> 5], (k - 1) & 31);
+    float tau = key[CPL - 1];                                          // keys arrive sorted: last one is the KL-th
+    tau = __shfl_sync(kFull, tau, 31);
+    const float xmax2 = __uint_as_float(__ldg(xmax_bits + b));         // max_j |x_j|^2
+    const float ni = sqrtf(sq_i), nmax = sqrtf(xmax2);
+    // TF32 truncation of both operands (2^-9 relative per product, Cauchy-Schwarz), of the norm column
+    // (2^-11), fp32 accumulation of the chain and of the tensor-core sum, plus key quantisation
+    const float eps = 1.01f * (ni * nmax * (1.f / 512.f + 1.f / 65536.f) + xmax2 * (1.f / 2048.f));
+    const float quant = fabsf(tau) * exp2f((float)(idx_bits - 22));
+    const bool safe = (tau == -INFINITY) ? (kth > -INFINITY) : (0.5f * kth > tau + quant + eps);
+    if (!safe) {
+        if (lane == 0) fb_list[atomicAdd(fb_count, 1)] = (int)gi;
+        return;
+    }
+#pragma unroll
+    for (int u = 0; u < CPL; ++u) {
+        const int r = u * 32 + lane;
+        if (r < k) {
+            idx[gi * k + r] = cj[u];
+            if (val) val[gi * k + r] = pd[u];
+        }
+    }
+}
+
+// ---- 4. exact fallback for flagged rows ----------------------------------------------------------------------------
+// One warp per flagged row (grid-stride over the device-side list): lane-distributed sorted list over all N.
+template <int SLOTS>
+__global__ void __launch_bounds__(256)
+knn_fallback_kernel(const float* __restrict__ x, const float* __restrict__ sq, int D, int N, int k,
+                    const int* __restrict__ fb_list, const int* __restrict__ fb_count,
+                    int64_t* __restrict__ idx, float* __restrict__ val) {
+    const int lane = threadIdx.x & 31;
+    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    const int count = *fb_count;
+    const int tau_slot = (k - 1) >> 5, tau_lane = (k - 1) & 31;
+    for (int f = gw; f < count; f += nw) {
+        const int gi = fb_list[f];
+        const int b = gi / N, i = gi - b * N;
+        const float* xb = x + (size_t)b * D * N;
+        const float* sqb = sq + (size_t)b * N;
+        const float sq_i = __ldg(sqb + i);
+        float lv[SLOTS]; int li[SLOTS];
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) { lv[s] = -INFINITY; li[s] = 0x7fffffff; }
+        float tau = -INFINITY;
+        for (int j0 = 0; j0 < N; j0 += 32) {
+            const int j = j0 + lane;
+            float acc = 0.f;
+            if (j < N) for (int d = 0; d < D; ++d) acc = __fmaf_rn(__ldg(xb + (size_t)d * N + i), __ldg(xb + (size_t)d * N + j), acc);
+            const float pd = j < N ? __fsub_rn(__fmaf_rn(2.f, acc, -sq_i), __ldg(sqb + j)) : -INFINITY;
+            unsigned bm = __ballot_sync(kFull, pd > tau);
+            while (bm) {
+                const int src = __ffs(bm) - 1;
+                bm &= bm - 1;
+                const float v = __shfl_sync(kFull, pd, src);
+                if (v > tau) {
+                    int pos = 0;
+#pragma unroll
+                    for (int s = 0; s < SLOTS; ++s) pos += __popc(__ballot_sync(kFull, lv[s] >= v));
+#pragma unroll
+                    for (int s = SLOTS - 1; s >= 0; --s) {
+                        float pv = __shfl_up_sync(kFull, lv[s], 1);
+                        int pi = __shfl_up_sync(kFull, li[s], 1);
+                        if (s > 0) {
+                            const float cv = __shfl_sync(kFull, lv[s - 1], 31);
+                            const int ci = __shfl_sync(kFull, li[s - 1], 31);
+                            if (lane == 0) { pv = cv; pi = ci; }
+                        }
+                        const int r = s * 32 + lane;
+                        if (r > pos) { lv[s] = pv; li[s] = pi; }
+                        else if (r == pos) { lv[s] = v; li[s] = j0 + src; }
+                    }
+                    float tv = lv[0];
+#pragma unroll
+                    for (int s = 1; s < SLOTS; ++s) if (s == tau_slot) tv = lv[s];
+                    tau = __shfl_sync(kFull, tv, tau_lane);
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < SLOTS; ++s) {
+            const int r = s * 32 + lane;
+            if (r < k) {
+                idx[(size_t)gi * k + r] = li[s] < N ? li[s] : i;
+                if (val) val[(size_t)gi * k + r] = lv[s];
+            }
+        }
+    }
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// rows x 64 fp32, row-major; box = 32 fp32 (128 B) x 128 rows, 128B swizzle
+static bool make_row_map(CUtensorMap* map, const float* base, size_t rows) {
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return false;
+    const cuuint64_t gdim[2] = {kKP, rows};
+    const cuuint64_t gstride[1] = {kKP * sizeof(float)};
+    const cuuint32_t box[2] = {32, kTM};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct TcLayout {
+    float *xa, *xb, *sq, *cand;
+    unsigned* xmax;
+    int *fb_count, *fb_list;
+    size_t bytes;
+};
+
+static TcLayout tc_layout(void* ws, int B, int N, int KL) {
+    TcLayout L;
+    char* p = static_cast<char*>(ws);
+    size_t off = 0;
+    const size_t rows = (size_t)B * N;
+    L.xa = reinterpret_cast<float*>(p + off);   off += align_up(rows * kKP * sizeof(float), 1024);
+    L.xb = reinterpret_cast<float*>(p + off);   off += align_up(rows * kKP * sizeof(float), 1024);
+    L.sq = reinterpret_cast<float*>(p + off);   off += align_up(rows * sizeof(float), 256);
+    L.cand = reinterpret_cast<float*>(p + off); off += align_up(rows * KL * sizeof(float), 256);
+    L.xmax = reinterpret_cast<unsigned*>(p + off);  off += align_up((size_t)B * sizeof(unsigned) + sizeof(int), 256);
+    L.fb_count = reinterpret_cast<int*>(L.xmax + B);
+    L.fb_list = reinterpret_cast<int*>(p + off); off += align_up(rows * sizeof(int), 256);
+    L.bytes = off;
+    return L;
+}
+
+bool knn_tc_applicable(int D, int N, int k) { return D >= 16 && D <= kKP - 1 && N >= kTN && N <= 4096 && k <= 48; }
+
+static int tc_list_len(int k) { return k <= 24 ? 32 : 64; }
+
+size_t knn_tc_workspace_bytes(int B, int D, int N, int k) {
+    (void)D;
+    return tc_layout(nullptr, B, N, tc_list_len(k)).bytes;
+}
+
+template <int KL>
+static int run_tc(const float* x, int B, int D, int N, int k, int64_t* idx, float* val, const TcLayout& L, cudaStream_t st) {
+    const size_t rows = (size_t)B * N;
+    int idx_bits = 1;
+    while ((1 << idx_bits) < N) ++idx_bits;
+    const unsigned keep_mask = ~((1u << idx_bits) - 1u);
+    cudaMemsetAsync(L.xmax, 0, (size_t)B * sizeof(unsigned) + sizeof(int), st);   // also clears fb_count
+    knn_pack_kernel<<<dim3((N + 31) / 32, B), 256, 0, st>>>(x, D, N, L.xa, L.xb, L.sq, L.xmax);
+    int rc = check_launch("knn_pack_kernel");
+    if (rc) return rc;
+    CUtensorMap map_a, map_b;
+    if (!make_row_map(&map_a, L.xa, rows) || !make_row_map(&map_b, L.xb, rows)) return fail(HPCS_ERR_CUDA, "knn_tc: cuTensorMapEncodeTiled failed");
+    {
+        const size_t smem = 4 * (size_t)kAtomBytes + (size_t)kTcQueue * kTM * sizeof(float) + 6 * sizeof(uint64_t) + 16 + 1024;
+        auto kern = knn_tc_kernel<KL>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<dim3((N + kTM - 1) / kTM, B), 160, smem, st>>>(map_a, map_b, L.sq, N, keep_mask, L.cand);
+        rc = check_launch("knn_tc_kernel");
+        if (rc) return rc;
+    }
+    {
+        const size_t smem = 8 * ((size_t)KL * (kKP + 4) + kKP) * sizeof(float);
+        auto kern = knn_rerank_kernel<KL>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<dim3((N + 7) / 8, B), 256, smem, st>>>(L.xb, L.sq, L.cand, L.xmax, D, N, k, keep_mask, idx_bits, idx, val,
+                                                      L.fb_list, L.fb_count);
+        rc = check_launch("knn_rerank_kernel");
+        if (rc) return rc;
+    }
+    const int blocks = 2 * sm_count();
+    if (k <= 32) knn_fallback_kernel<1><<<blocks, 256, 0, st>>>(x, L.sq, D, N, k, L.fb_list, L.fb_count, idx, val);
+    else knn_fallback_kernel<2><<<blocks, 256, 0, st>>>(x, L.sq, D, N, k, L.fb_list, L.fb_count, idx, val);
+    return check_launch("knn_fallback_kernel");
+}
+
+int knn_tc_run(const float* x, int B, int D, int N, int k, int64_t* idx, float* val, void* ws, size_t ws_bytes, cudaStream_t st) {
+    const int KL = tc_list_len(k);
+    const TcLayout L = tc_layout(ws, B, N, KL);
+    if (ws_bytes < L.bytes) return fail(HPCS_ERR_WORKSPACE, "knn: workspace too small");
+    if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return fail(HPCS_ERR_ARG, "knn: workspace must be 256-byte aligned");
+    return KL == 32 ? run_tc<32>(x, B, D, N, k, idx, val, L, st) : run_tc<64>(x, B, D, N, k, idx, val, L, st);
+}
+
+}  // namespace hpcs

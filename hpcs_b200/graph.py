@@ -16,9 +16,11 @@ import torch
 from . import _lib
 
 
-def knn(x: torch.Tensor, k: int, return_values: bool = False):
+def knn(x: torch.Tensor, k: int, return_values: bool = False, method: str = "auto"):
     """x[B,D,N] fp32 -> idx[B,N,k] int64: the k nearest points of every point (self included), by
-    descending ``-|xi-xj|^2``; exact ties resolve to the lower index (see oracle/knn_canonical.c)."""
+    descending ``-|xi-xj|^2``; exact ties resolve to the lower index (see oracle/knn_canonical.c).
+    ``method``: "auto" (tensor-core Gram + exact re-rank where it applies) or "ffma" (all-FFMA exact
+    kernel); both give the same bits."""
     if x.dim() != 3:
         raise ValueError(f"knn expects x[B,D,N], got {tuple(x.shape)}")
     dev = _lib.require_cuda(x)
@@ -28,13 +30,16 @@ def knn(x: torch.Tensor, k: int, return_values: bool = False):
     B, D, N = x.shape
     if not 0 < k <= N:
         raise ValueError(f"knn: need 0 < k <= N, got k={k}, N={N}")
+    if method not in ("auto", "ffma"):
+        raise ValueError(f"knn: unknown method {method!r}")
     lib = _lib.load()
+    entry = lib.hpcs_knn_f32 if method == "auto" else lib.hpcs_knn_ffma_f32
     idx = torch.empty((B, N, k), dtype=torch.int64, device=dev)
     val = torch.empty((B, N, k), dtype=torch.float32, device=dev) if return_values else None
     ws = _lib.workspace(lib.hpcs_knn_workspace_bytes(B, D, N, k), dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.hpcs_knn_f32(x.data_ptr(), B, D, N, k, idx.data_ptr(), _lib.ptr(val), ws.data_ptr(),
-                                    ws.numel(), _lib.stream_ptr(dev)), "hpcs_knn_f32")
+        _lib.check(entry(x.data_ptr(), B, D, N, k, idx.data_ptr(), _lib.ptr(val), ws.data_ptr(),
+                         ws.numel(), _lib.stream_ptr(dev)), "hpcs_knn_f32")
     return (idx, val) if return_values else idx
 
 
