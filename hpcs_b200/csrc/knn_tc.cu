@@ -90,7 +90,9 @@ template <int KL>
 __global__ void __launch_bounds__(160, 2)
 knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
               const float* __restrict__ sq, int N, unsigned keep_mask, float* __restrict__ cand /*[B*N][KL] keys*/) {
-    extern __shared__ __align__(1024) unsigned char smem[];
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // the 128B-swizzle atoms must start on 1024-byte boundaries of the shared window
+    unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* sA = smem;                                          // 2 K-atoms x 16 KB
     unsigned char* sB = smem + 2 * kAtomBytes;                         // 2 K-atoms x 16 KB
     float* qk = reinterpret_cast<float*>(smem + 4 * kAtomBytes);       // [kTcQueue][128] pending keys
@@ -483,6 +485,15 @@ static int run_tc(const float* x, int B, int D, int N, int k, int64_t* idx, floa
     if (k <= 32) knn_fallback_kernel<1><<<blocks, 256, 0, st>>>(x, L.sq, D, N, k, L.fb_list, L.fb_count, idx, val);
     else knn_fallback_kernel<2><<<blocks, 256, 0, st>>>(x, L.sq, D, N, k, L.fb_list, L.fb_count, idx, val);
     return check_launch("knn_fallback_kernel");
+}
+
+// rows redone by the exact fallback in the last call that used this workspace (synchronises the stream)
+int knn_tc_fallback_rows(const void* ws, int B, int N, int k, cudaStream_t st, int* out_host) {
+    const TcLayout L = tc_layout(const_cast<void*>(ws), B, N, tc_list_len(k));
+    cudaError_t e = cudaMemcpyAsync(out_host, L.fb_count, sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return fail(HPCS_ERR_CUDA, "knn_tc_fallback_rows: %s", cudaGetErrorString(e));
+    return HPCS_OK;
 }
 
 int knn_tc_run(const float* x, int B, int D, int N, int k, int64_t* idx, float* val, void* ws, size_t ws_bytes, cudaStream_t st) {

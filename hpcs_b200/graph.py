@@ -16,11 +16,12 @@ import torch
 from . import _lib
 
 
-def knn(x: torch.Tensor, k: int, return_values: bool = False, method: str = "auto"):
+def knn(x: torch.Tensor, k: int, return_values: bool = False, method: str = "auto", stats: Optional[dict] = None):
     """x[B,D,N] fp32 -> idx[B,N,k] int64: the k nearest points of every point (self included), by
     descending ``-|xi-xj|^2``; exact ties resolve to the lower index (see oracle/knn_canonical.c).
     ``method``: "auto" (tensor-core Gram + exact re-rank where it applies) or "ffma" (all-FFMA exact
-    kernel); both give the same bits."""
+    kernel); both give the same bits.  ``stats`` (a dict) receives ``fallback_rows``: rows the
+    tensor-core path had to redo exactly (this synchronises the stream; leave it None on hot paths)."""
     if x.dim() != 3:
         raise ValueError(f"knn expects x[B,D,N], got {tuple(x.shape)}")
     dev = _lib.require_cuda(x)
@@ -40,6 +41,13 @@ def knn(x: torch.Tensor, k: int, return_values: bool = False, method: str = "aut
     with torch.cuda.device(dev):
         _lib.check(entry(x.data_ptr(), B, D, N, k, idx.data_ptr(), _lib.ptr(val), ws.data_ptr(),
                          ws.numel(), _lib.stream_ptr(dev)), "hpcs_knn_f32")
+        if stats is not None:
+            import ctypes
+            rows = ctypes.c_int(0)
+            if method == "auto":
+                _lib.check(lib.hpcs_knn_fallback_rows(ws.data_ptr(), ws.numel(), B, D, N, k, _lib.stream_ptr(dev),
+                                                      ctypes.byref(rows)), "hpcs_knn_fallback_rows")
+            stats["fallback_rows"] = rows.value
     return (idx, val) if return_values else idx
 
 

@@ -54,6 +54,11 @@ int hpcs_knn_f32(const float* x, int B, int D, int N, int k, int64_t* idx, float
  * same bits, which the parity tests check against each other and against the oracle. */
 int hpcs_knn_ffma_f32(const float* x, int B, int D, int N, int k, int64_t* idx, float* val,
                       void* ws, size_t ws_bytes, void* stream);
+/* Statistics: number of rows the last hpcs_knn_f32 call on this workspace redid with the exact
+ * fallback (0 when the tensor-core path does not apply).  Synchronises `stream`; rows_host is a
+ * HOST pointer. */
+int hpcs_knn_fallback_rows(const void* ws, size_t ws_bytes, int B, int D, int N, int k, void* stream,
+                           int* rows_host);
 
 /* get_graph_feature(x, k, idx)    hpcs/nn/dgcnn/utils/vn_dgcnn_util.py:13-41
  * get_graph_feature_cross         hpcs/nn/dgcnn/utils/vn_dgcnn_util.py:44-69   (cross != 0)

@@ -57,6 +57,33 @@ def test_knn_bit_exact_vs_canonical_oracle(hb, B, D, N, k):
     assert torch.equal(got_v.cpu(), want_v)                      # same fp32 bits, not just close
 
 
+@pytest.mark.parametrize("B,D,N,k,kind", [(2, 63, 128, 20, "randn"), (2, 63, 1024, 20, "randn"), (3, 32, 300, 10, "randn"),
+                                          (1, 16, 128, 40, "randn"), (2, 63, 1024, 20, "clustered"), (2, 63, 512, 20, "dups"),
+                                          (2, 48, 640, 48, "randn"), (1, 63, 4096, 20, "randn"), (2, 63, 1000, 24, "offset")])
+def test_knn_tensor_core_path_bit_exact(hb, B, D, N, k, kind):
+    """hpcs_knn_f32 takes the tcgen05 path for 16 <= D <= 63, 128 <= N <= 4096, k <= 48: its indices AND value
+    bits must equal the canonical oracle and the all-FFMA kernel, including inputs built to defeat the
+    TF32 candidate stage (near-duplicate clusters, exact duplicates, a large common offset)."""
+    gen = torch.Generator().manual_seed(B * 977 + D * 13 + N + k)
+    x = torch.randn(B, D, N, generator=gen)
+    if kind == "clustered":
+        x = x * 1e-3 + torch.randn(B, D, 1, generator=gen) * 5
+    elif kind == "dups":
+        x[:, :, N // 2:] = x[:, :, :N // 2]
+    elif kind == "offset":
+        x = x + 30.0
+    stats = {}
+    got_i, got_v = hb.knn(dev(x), k, return_values=True, stats=stats)
+    ffma_i, ffma_v = hb.knn(dev(x), k, return_values=True, method="ffma")
+    assert torch.equal(got_i, ffma_i) and torch.equal(got_v.view(torch.int32), ffma_v.view(torch.int32))
+    if N <= 1024:
+        want_i, want_v = O.knn_canonical(x, k, return_values=True)
+        assert torch.equal(got_i.cpu(), want_i) and torch.equal(got_v.cpu(), want_v)
+    assert 0 <= stats["fallback_rows"] <= B * N
+    if kind == "randn":
+        assert stats["fallback_rows"] <= B * N // 100          # the candidate stage decides almost every row itself
+
+
 def test_knn_ties_lower_index_first(hb):
     x = torch.zeros(1, 3, 64)
     x[0, 0] = torch.arange(64).div(4, rounding_mode="floor").float()   # groups of 4 identical points
