@@ -159,39 +159,26 @@ def run_native(args):
     g2 = torch.randn(B, 2 * C_FEAT, 3, N_PTS, K_NN, device=dev, generator=gen)
     g3 = torch.randn(B, 2 * C_FEAT, 3, N_PTS, K_NN, device=dev, generator=gen)
 
-    op_names = ["knn_d3", "edge_fwd_c1", "edge_bwd_c1", "knn_d63", "edge_fwd_c21", "edge_bwd_c21", "hyp_loss_fwd_bwd"]
-    op_events = {n: [] for n in op_names}
-
-    def timed(name, fn, record):
-        if not record:
-            return fn()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        out = fn()
-        e.record()
-        op_events[name].append((s, e))
-        return out
-
-    def layer(x, g, tag_knn, tag_f, tag_b, record):
+    def layer(x, g):
         xr = x.detach().requires_grad_(True)
         Bc, C, _, Np = xr.shape
-        idx = timed(tag_knn, lambda: hb.knn(xr.detach().view(Bc, 3 * C, Np), K_NN), record)
-        y = timed(tag_f, lambda: hb.get_graph_feature(xr, K_NN, idx=idx), record)
-        (gx,) = timed(tag_b, lambda: torch.autograd.grad(y, xr, g), record)
+        idx = hb.knn(xr.detach().view(Bc, 3 * C, Np), K_NN)
+        y = hb.get_graph_feature(xr, K_NN, idx=idx)
+        (gx,) = torch.autograd.grad(y, xr, g)
         return gx
 
-    def step(inp, tr, record=False):
-        gx1 = layer(inp["pts"], g1, "knn_d3", "edge_fwd_c1", "edge_bwd_c1", record)
-        gx2 = layer(inp["f1"], g2, "knn_d63", "edge_fwd_c21", "edge_bwd_c21", record)
-        gx3 = layer(inp["f2"], g3, "knn_d63", "edge_fwd_c21", "edge_bwd_c21", record)
-        emb = inp["emb"].detach().requires_grad_(True)
+    def loss_fwd_bwd(emb_in, tr):
+        emb = emb_in.detach().requires_grad_(True)
         sc = scale.detach().requires_grad_(True)            # fresh leaves: keeps autograd on the capturing stream
+        loss, kept = hb.hyp_triplet_loss(emb, tr, sc, TEMPERATURE, "easy", 0.0, return_kept=True)
+        ge, gs = torch.autograd.grad(loss, (emb, sc))
+        return loss, kept, ge, gs
 
-        def loss_fb():
-            loss, kept = hb.hyp_triplet_loss(emb, tr, sc, TEMPERATURE, "easy", 0.0, return_kept=True)
-            ge, gs = torch.autograd.grad(loss, (emb, sc))
-            return loss, kept, ge, gs
-        loss, kept, ge, gs = timed("hyp_loss_fwd_bwd", loss_fb, record)
+    def step(inp, tr):
+        gx1 = layer(inp["pts"], g1)
+        gx2 = layer(inp["f1"], g2)
+        gx3 = layer(inp["f2"], g3)
+        loss, kept, ge, gs = loss_fwd_bwd(inp["emb"], tr)
         if world > 1:
             dist.all_reduce(gs, op=dist.ReduceOp.SUM)           # d loss / d scale: the path's only parameter
             gs = gs / world
@@ -202,19 +189,22 @@ def run_native(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def capture(inp, tr):
-        """Warm up on a side stream, then capture one step over static buffers into a CUDA graph."""
+    def capture_fn(fn):
+        """Warm up on a side stream, then capture one call of fn over static buffers into a CUDA graph."""
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(3):
-                step(inp, tr)
+                fn()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            outs = step(inp, tr)
+            outs = fn()
         return graph, outs
+
+    def capture(inp, tr):
+        return capture_fn(lambda: step(inp, tr))
 
     # ---- resident-input timing: K replays of the captured step ------------------------------------
     for _ in range(max(args.warmup, 3)):
@@ -252,9 +242,38 @@ def run_native(args):
     value = world * B / (ms_per_step * 1e-3)
     loss_val, kept_val = float(out[0].detach()), int(out[1])
 
-    # ---- per-op durations: same steps, eager, CUDA events around every op ---------------------------
-    for _ in range(args.steps):
-        step(d, trip, record=True)
+    # ---- per-op durations: every op of the step captured into its OWN CUDA graph and replayed K times
+    # between CUDA events on the launching stream (no host gaps; an op = all kernels of one C-ABI call).
+    from hpcs_b200 import graph as hgraph
+    op_ms, op_launches = {}, {}
+
+    def time_op(name, fn, calls_per_step):
+        l0_ = _lib.launch_count()
+        fn()
+        op_launches[name] = (_lib.launch_count() - l0_, calls_per_step)
+        g_, _ = capture_fn(fn)
+        for _ in range(3):
+            g_.replay()
+        torch.cuda.synchronize()
+        s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s_.record()
+        for _ in range(args.steps):
+            g_.replay()
+        e_.record()
+        torch.cuda.synchronize()
+        op_ms[name] = s_.elapsed_time(e_) / args.steps
+
+    with torch.no_grad():
+        x3 = d["pts"].view(B, 3, N_PTS)
+        x63 = d["f1"].view(B, 3 * C_FEAT, N_PTS)
+        idx3, idx63 = hb.knn(x3, K_NN), hb.knn(x63, K_NN)
+        time_op("knn_d3", lambda: hb.knn(x3, K_NN), 1)
+        time_op("knn_d63", lambda: hb.knn(x63, K_NN), 2)
+        time_op("edge_fwd_c1", lambda: hgraph.edge_features_forward(d["pts"], idx3), 1)
+        time_op("edge_fwd_c21", lambda: hgraph.edge_features_forward(d["f1"], idx63), 2)
+        time_op("edge_bwd_c1", lambda: hgraph.edge_features_backward(g1, d["pts"], idx3), 1)
+        time_op("edge_bwd_c21", lambda: hgraph.edge_features_backward(g2, d["f1"], idx63), 2)
+    time_op("hyp_loss_fwd_bwd", lambda: loss_fwd_bwd(d["emb"], trip), 1)
     barrier()
 
     # ---- end-to-end from pinned host buffers ----------------------------------------------------------
@@ -336,14 +355,10 @@ def run_native(args):
     pk = peaks()
     work = algorithmic_work(B)
     ops = {}
-    for name in op_names:
-        evs = op_events[name]
-        if not evs:
-            continue
-        avg_ms = sum(s.elapsed_time(e) for s, e in evs) / len(evs)
-        calls_per_step = len(evs) / args.steps
+    for name, avg_ms in op_ms.items():
+        n_launch, calls_per_step = op_launches[name]
         w = work[name]
-        ent = {"ms": round(avg_ms, 4), "calls_per_step": calls_per_step,
+        ent = {"ms": round(avg_ms, 4), "calls_per_step": calls_per_step, "kernels_per_call": n_launch,
                "share": round(avg_ms * calls_per_step / ms_per_step, 4)}
         if name.startswith("edge"):
             ent.update(bound="hbm", achieved=round(w["bytes"] / (avg_ms * 1e-3) / 1e9, 1), peak=pk["hbm_gbs"], unit="GB/s")
@@ -365,7 +380,7 @@ def run_native(args):
                    "scale": SCALE, "temperature": TEMPERATURE, "parallelism": f"dp{world}",
                    "l2": "per-step working set ~1.4 GB (edge-feature tensors) exceeds the 126 MB L2; no explicit flush",
                    "launch": "cuda-graph replay of one captured step" if use_graph else "eager",
-                   "ops_timing": "same step run eagerly with CUDA events around every op, after the timed region",
+                   "ops_timing": "each op captured into its own CUDA graph, replayed `steps` times between CUDA events, after the timed region",
                    "e2e_pipeline": "2 device buffer sets; upload / compute / download on 3 streams"},
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
                 "d2h_bytes_per_step": int(d2h_bytes)},

@@ -24,7 +24,7 @@ bool knn_tc_applicable(int D, int N, int k);
 size_t knn_tc_workspace_bytes(int B, int D, int N, int k);
 int knn_tc_run(const float* x, int B, int D, int N, int k, int64_t* idx, float* val, void* ws, size_t ws_bytes,
                cudaStream_t st);
-int knn_tc_fallback_rows(const void* ws, int B, int N, int k, cudaStream_t st, int* out_host);
+int knn_tc_fallback_rows(const void* ws, int B, int D, int N, int k, cudaStream_t st, int* out_host);
 
 constexpr int kKnnWarps = 8;
 constexpr int kRowQueue = 48;          // per-thread FIFO depth of the row-parallel kernel (flush when > 16 pending)
@@ -359,7 +359,7 @@ int hpcs_knn_fallback_rows(const void* ws, size_t ws_bytes, int B, int D, int N,
     *rows_host = 0;
     if (!knn_tc_applicable(D, N, k)) return HPCS_OK;
     if (ws_bytes < hpcs_knn_workspace_bytes(B, D, N, k)) return fail(HPCS_ERR_WORKSPACE, "knn_fallback_rows: workspace too small");
-    return knn_tc_fallback_rows(ws, B, N, k, as_stream(stream), rows_host);
+    return knn_tc_fallback_rows(ws, B, D, N, k, as_stream(stream), rows_host);
 }
 
 int hpcs_knn_ffma_f32(const float* x, int B, int D, int N, int k, int64_t* idx, float* val, void* ws,

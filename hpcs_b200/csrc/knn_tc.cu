@@ -1,9 +1,15 @@
 // kNN for the feature-space EdgeConv layers (16 <= D <= 63): Gram term on the 5th-generation tensor
 // cores, exact fp32 re-rank, so the selected indices stay bit-exact with the canonical order.
 //
-//   1. knn_pack_kernel      x[B,D,N] -> K-major rows  xa[i] = (x_i, 1, 0..)   xb[j] = (x_j, -|x_j|^2/2, 0..)
-//                           (64 fp32 per row) + canonical norms.  With the extra column the tensor-core
-//                           product is directly the ranking key  S_ij = x_i.x_j - |x_j|^2/2  (= pd_ij/2 + const_i).
+//   0. knn_mean_kernel      per-cloud feature means mu[b,d] (distances are translation invariant: the tensor
+//                           cores see x - mu, so a common offset costs no TF32 precision; the exact stages
+//                           below always use the raw x).
+//   1. knn_pack_kernel      x[B,D,N] -> two K-major row arrays of 64 fp32 per point:
+//                             xc[j] = (x_j - mu, -|x_j - mu|^2/2)   tensor-core operand (A and B),
+//                             xr[j] = (x_j,      -|x_j|^2/2)        raw rows for the exact re-rank,
+//                           + canonical raw norms, centred norms and their per-cloud maximum.  The A tile gets
+//                           a 1 patched into column 63 in shared memory, so the tensor-core product is directly
+//                           the ranking key  S_ij = c_i.c_j - |c_j|^2/2  (= pd_ij/2 + |c_i|^2/2).
 //   2. knn_tc_kernel        one CTA per (cloud, 128 query rows).  A producer warp streams 128-candidate
 //                           tiles of xb with TMA (128B-swizzled boxes) and issues tcgen05.mma kind::tf32
 //                           (M=128, N=128, K=8 x 8) into a double-buffered TMEM accumulator; four epilogue
@@ -30,26 +36,52 @@ constexpr int kTN = 128;                // candidates per tile  (UMMA N)
 constexpr int kTcQueue = 48;            // per-row FIFO depth in the epilogue
 constexpr int kAtomBytes = kTM * 128;   // one 32-fp32 K-atom of a 128-row tile
 
+// ---- 0. per-cloud feature means ---------------------------------------------------------------------------
+// one warp per (cloud, feature) row of x; block 0 also clears the per-call counters
+__global__ void __launch_bounds__(256)
+knn_mean_kernel(const float* __restrict__ x, int rows, int N, float* __restrict__ mu, unsigned* __restrict__ zero_words,
+                int n_zero) {
+    if (blockIdx.x == 0) for (int i = threadIdx.x; i < n_zero; i += blockDim.x) zero_words[i] = 0u;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    const float* xr = x + (size_t)row * N;
+    float s = 0.f;
+    for (int j = lane; j < N; j += 32) s += __ldg(xr + j);
+    s = warp_sum(s);
+    if (lane == 0) mu[row] = s / (float)N;
+}
+
 // ---- 1. pack ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-knn_pack_kernel(const float* __restrict__ x, int D, int N, float* __restrict__ xa, float* __restrict__ xb,
-                float* __restrict__ sq, unsigned* __restrict__ xmax_bits) {
+knn_pack_kernel(const float* __restrict__ x, const float* __restrict__ mu, int D, int N, float* __restrict__ xc,
+                float* __restrict__ xr, float* __restrict__ sq, float* __restrict__ sqc, unsigned* __restrict__ cmax_bits) {
     __shared__ float tile[kKP][33];
+    __shared__ float nrm[2][32];
     const int b = blockIdx.y;
     const int n0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
     const float* xb_in = x + (size_t)b * D * N;
     for (int d = ty; d < kKP; d += 8) tile[d][tx] = (d < D && n0 + tx < N) ? __ldg(xb_in + (size_t)d * N + n0 + tx) : 0.f;
     __syncthreads();
-    if (ty == 0 && n0 + tx < N) {                                      // canonical norm: fma chain over d ascending
+    if (ty < 2 && n0 + tx < N) {                                       // fma chains over d ascending (ty 0: raw = canonical)
         float s = 0.f;
-        for (int d = 0; d < D; ++d) s = __fmaf_rn(tile[d][tx], tile[d][tx], s);
-        sq[(size_t)b * N + n0 + tx] = s;
-        tile[kKP - 1][tx] = s;                                         // column 63 is free (D <= 63)
-        atomicMax(xmax_bits + b, __float_as_uint(s));                  // s >= 0: uint order == float order
+        for (int d = 0; d < D; ++d) {
+            const float v = ty == 0 ? tile[d][tx] : __fsub_rn(tile[d][tx], __ldg(mu + b * D + d));
+            s = __fmaf_rn(v, v, s);
+        }
+        nrm[ty][tx] = s;
+        if (ty == 0) {
+            sq[(size_t)b * N + n0 + tx] = s;
+            atomicMax(cmax_bits + gridDim.y + b, __float_as_uint(s));  // raw maximum lives behind the centred one
+        } else {
+            sqc[(size_t)b * N + n0 + tx] = s;
+            atomicMax(cmax_bits + b, __float_as_uint(s));              // s >= 0: uint order == float order
+        }
     }
     __syncthreads();
     // write rows: thread (ty, tx) -> rows ty, ty+8, ..; columns tx and tx+32 (coalesced 128 B per half row)
+    const float m0 = tx < D ? __ldg(mu + b * D + tx) : 0.f;
+    const float m1 = tx + 32 < D ? __ldg(mu + b * D + tx + 32) : 0.f;
     for (int r = ty; r < 32; r += 8) {
         const int n = n0 + r;
         if (n >= N) continue;
@@ -57,10 +89,11 @@ knn_pack_kernel(const float* __restrict__ x, int D, int N, float* __restrict__ x
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int d = tx + 32 * h;
-            float va = tile[d][r], vb = va;
-            if (d == kKP - 1) { va = 1.f; vb = -0.5f * tile[kKP - 1][r]; }
-            xa[row + d] = va;
-            xb[row + d] = vb;
+            float vr = tile[d][r];
+            float vc = d < D ? __fsub_rn(vr, h ? m1 : m0) : 0.f;
+            if (d == kKP - 1) { vr = -0.5f * nrm[0][r]; vc = -0.5f * nrm[1][r]; }   // column 63 is free (D <= 63)
+            xr[row + d] = vr;
+            xc[row + d] = vc;
         }
     }
 }
@@ -88,17 +121,17 @@ struct KeyTopK {
 // ---- 2. tensor-core candidate kernel --------------------------------------------------------------------------
 template <int KL>
 __global__ void __launch_bounds__(160, 2)
-knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-              const float* __restrict__ sq, int N, unsigned keep_mask, float* __restrict__ cand /*[B*N][KL] keys*/) {
+knn_tc_kernel(const __grid_constant__ CUtensorMap map_c, const float* __restrict__ sqc, int N, unsigned keep_mask,
+              float* __restrict__ cand /*[B*N][KL] keys*/) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // the 128B-swizzle atoms must start on 1024-byte boundaries of the shared window
     unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* sA = smem;                                          // 2 K-atoms x 16 KB
     unsigned char* sB = smem + 2 * kAtomBytes;                         // 2 K-atoms x 16 KB
     float* qk = reinterpret_cast<float*>(smem + 4 * kAtomBytes);       // [kTcQueue][128] pending keys
-    uint64_t* bars = reinterpret_cast<uint64_t*>(qk + kTcQueue * kTM); // full_a, full_b, mma[2], epi[2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
-    uint64_t* full_a = bars, *full_b = bars + 1, *mma_done = bars + 2, *epi_done = bars + 4;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(qk + kTcQueue * kTM); // full_a, full_b, mma[2], epi[2], a_ready
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+    uint64_t* full_a = bars, *full_b = bars + 1, *mma_done = bars + 2, *epi_done = bars + 4, *a_ready = bars + 6;
 
     const int b = blockIdx.y;
     const int m0 = blockIdx.x * kTM;                                   // first query row of this CTA (in the cloud)
@@ -110,6 +143,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         ptx::mbar_init(full_b, 1);
         ptx::mbar_init(mma_done, 1); ptx::mbar_init(mma_done + 1, 1);
         ptx::mbar_init(epi_done, 4); ptx::mbar_init(epi_done + 1, 4);
+        ptx::mbar_init(a_ready, 4);
         ptx::fence_barrier_init();
     }
     if (warp == 4) ptx::tmem_alloc<2 * kTN>(tmem_slot);
@@ -121,21 +155,20 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     if (warp == 4) {
         // ===== producer: TMA + MMA issue (one elected lane) =====
         if (lane == 0) {
-            ptx::tma_prefetch_desc(&map_a);
-            ptx::tma_prefetch_desc(&map_b);
+            ptx::tma_prefetch_desc(&map_c);
             const int rowA = b * N + m0;
             ptx::mbar_arrive_expect_tx(full_a, 2 * kAtomBytes);
-            ptx::tma_load_2d(sA, &map_a, full_a, 0, rowA);
-            ptx::tma_load_2d(sA + kAtomBytes, &map_a, full_a, 32, rowA);
+            ptx::tma_load_2d(sA, &map_c, full_a, 0, rowA);
+            ptx::tma_load_2d(sA + kAtomBytes, &map_c, full_a, 32, rowA);
             const uint32_t idesc = ptx::umma_idesc_tf32(kTM, kTN);
             const uint32_t a_addr = ptx::smem_u32(sA), b_addr = ptx::smem_u32(sB);
             for (int t = 0; t < T; ++t) {
                 if (t >= 1) ptx::mbar_wait(mma_done + ((t - 1) & 1), ((t - 1) >> 1) & 1);   // B buffer free
                 const int rowB = b * N + t * kTN;
                 ptx::mbar_arrive_expect_tx(full_b, 2 * kAtomBytes);
-                ptx::tma_load_2d(sB, &map_b, full_b, 0, rowB);
-                ptx::tma_load_2d(sB + kAtomBytes, &map_b, full_b, 32, rowB);
-                if (t == 0) ptx::mbar_wait(full_a, 0);
+                ptx::tma_load_2d(sB, &map_c, full_b, 0, rowB);
+                ptx::tma_load_2d(sB + kAtomBytes, &map_c, full_b, 32, rowB);
+                if (t == 0) ptx::mbar_wait(a_ready, 0);                                     // A landed and patched
                 ptx::mbar_wait(full_b, t & 1);
                 if (t >= 2) ptx::mbar_wait(epi_done + (t & 1), ((t >> 1) - 1) & 1);         // accumulator drained
                 ptx::tc_fence_after_sync();
@@ -157,7 +190,14 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
         // ===== epilogue: thread = query row = TMEM lane =====
         const int row = warp * 32 + lane;                              // row in tile
         const int i = m0 + row;                                        // row in cloud
-        const float h = 0.5f * __ldg(sq + (size_t)b * N + min(i, N - 1));
+        const float h = 0.5f * __ldg(sqc + (size_t)b * N + min(i, N - 1));
+        // A = the same rows as B, with column 63 (-|c_i|^2/2 in global memory) replaced by 1: element (row, 63) of
+        // K-atom 1 sits in 16-byte chunk 7 ^ (row & 7) of its 128-byte swizzled line
+        ptx::mbar_wait(full_a, 0);
+        *reinterpret_cast<float*>(sA + kAtomBytes + row * 128 + ((7 ^ (row & 7)) << 4) + 12) = 1.0f;
+        ptx::fence_proxy_async_smem();                                 // generic-proxy write -> visible to the MMA
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(a_ready);
         KeyTopK<KL> top;
         top.init();
         float tau = -INFINITY;
@@ -209,8 +249,8 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
 // One warp per query row, lane c <-> candidate c (KL == 32) or candidates c, c+32 (KL == 64).
 template <int KL>
 __global__ void __launch_bounds__(256)
-knn_rerank_kernel(const float* __restrict__ xb, const float* __restrict__ sq, const float* __restrict__ cand,
-                  const unsigned* __restrict__ xmax_bits, int D, int N, int k, unsigned keep_mask, int idx_bits,
+knn_rerank_kernel(const float* __restrict__ xb /* raw rows xr */, const float* __restrict__ sq, const float* __restrict__ sqc,
+                  const float* __restrict__ cand, const unsigned* __restrict__ cmax_bits, int D, int N, int k, unsigned keep_mask, int idx_bits,
                   int64_t* __restrict__ idx, float* __restrict__ val, int* __restrict__ fb_list, int* __restrict__ fb_count) {
     constexpr int CPL = KL / 32;                                       // candidates per lane
     constexpr int RS = kKP + 4;                                        // padded smem row stride
@@ -304,11 +344,20 @@ knn_rerank_kernel(const float* __restrict__ xb, const float* __restrict__ sq, co
     const float kth = __shfl_sync(kFull, pd[(k - 1) >> 5], (k - 1) & 31);
     float tau = key[CPL - 1];                                          // keys arrive sorted: last one is the KL-th
     tau = __shfl_sync(kFull, tau, 31);
-    const float xmax2 = __uint_as_float(__ldg(xmax_bits + b));         // max_j |x_j|^2
-    const float ni = sqrtf(sq_i), nmax = sqrtf(xmax2);
-    // TF32 truncation of both operands (2^-9 relative per product, Cauchy-Schwarz), of the norm column
-    // (2^-11), fp32 accumulation of the chain and of the tensor-core sum, plus key quantisation
-    const float eps = 1.01f * (ni * nmax * (1.f / 512.f + 1.f / 65536.f) + xmax2 * (1.f / 2048.f));
+    const float cmax2 = __uint_as_float(__ldg(cmax_bits + b));         // max_j |x_j - mu|^2
+    const float rmax2 = __uint_as_float(__ldg(cmax_bits + gridDim.y + b));   // max_j |x_j|^2
+    const float ni = sqrtf(__ldg(sqc + gi)), nmax = sqrtf(cmax2);
+    const float rsum = sqrtf(sq_i) + sqrtf(rmax2);
+    // |tensor-core score - exact pd/2| <= TF32 truncation of both operands (2^-9 relative per product, summed with
+    // Cauchy-Schwarz) and of the norm column (2^-10 of |c_j|^2/2), + fp32 rounding of x - mu, of both accumulations
+    // and of the shift (2^-16 and 2^-20 terms are generous), all on the CENTRED data; plus the rounding error
+    // of the canonical fp32 arithmetic itself, which works on the RAW data: D-step fma chains for the dot and
+    // both norms and two final roundings, |pd_canonical - pd_true| / 2 <= (D + 8) 2^-25 (|x_i| + max|x_j|)^2
+    // (taken twice).  A cloud far from the origin relative to its extent fails this test honestly: its
+    // canonical order is decided by fp32 rounding, which only the exact kernels reproduce.
+    const float eps = 1.01f * (ni * nmax * (1.f / 512.f + 1.f / 65536.f) + cmax2 * (1.f / 2048.f) +
+                               (ni + nmax) * (ni + nmax) * (1.f / 1048576.f) +
+                               (float)(D + 8) * rsum * rsum * (1.f / 16777216.f));
     const float quant = fabsf(tau) * exp2f((float)(idx_bits - 22));
     const bool safe = (tau == -INFINITY) ? (kth > -INFINITY) : (0.5f * kth > tau + quant + eps);
     if (!safe) {
@@ -421,23 +470,27 @@ static bool make_row_map(CUtensorMap* map, const float* base, size_t rows) {
 }
 
 struct TcLayout {
-    float *xa, *xb, *sq, *cand;
-    unsigned* xmax;
+    float *xc, *xr, *sq, *sqc, *cand, *mu;
+    unsigned* cmax;
     int *fb_count, *fb_list;
+    int n_zero;
     size_t bytes;
 };
 
-static TcLayout tc_layout(void* ws, int B, int N, int KL) {
+static TcLayout tc_layout(void* ws, int B, int D, int N, int KL) {
     TcLayout L;
     char* p = static_cast<char*>(ws);
     size_t off = 0;
     const size_t rows = (size_t)B * N;
-    L.xa = reinterpret_cast<float*>(p + off);   off += align_up(rows * kKP * sizeof(float), 1024);
-    L.xb = reinterpret_cast<float*>(p + off);   off += align_up(rows * kKP * sizeof(float), 1024);
+    L.xc = reinterpret_cast<float*>(p + off);   off += align_up(rows * kKP * sizeof(float), 1024);
+    L.xr = reinterpret_cast<float*>(p + off);   off += align_up(rows * kKP * sizeof(float), 1024);
     L.sq = reinterpret_cast<float*>(p + off);   off += align_up(rows * sizeof(float), 256);
+    L.sqc = reinterpret_cast<float*>(p + off);  off += align_up(rows * sizeof(float), 256);
     L.cand = reinterpret_cast<float*>(p + off); off += align_up(rows * KL * sizeof(float), 256);
-    L.xmax = reinterpret_cast<unsigned*>(p + off);  off += align_up((size_t)B * sizeof(unsigned) + sizeof(int), 256);
-    L.fb_count = reinterpret_cast<int*>(L.xmax + B);
+    L.mu = reinterpret_cast<float*>(p + off);   off += align_up((size_t)B * D * sizeof(float), 256);
+    L.cmax = reinterpret_cast<unsigned*>(p + off);  off += align_up((size_t)(2 * B + 1) * sizeof(unsigned), 256);
+    L.fb_count = reinterpret_cast<int*>(L.cmax + 2 * B);              // [B] centred max, [B] raw max, counter
+    L.n_zero = 2 * B + 1;
     L.fb_list = reinterpret_cast<int*>(p + off); off += align_up(rows * sizeof(int), 256);
     L.bytes = off;
     return L;
@@ -448,8 +501,7 @@ bool knn_tc_applicable(int D, int N, int k) { return D >= 16 && D <= kKP - 1 && 
 static int tc_list_len(int k) { return k <= 24 ? 32 : 64; }
 
 size_t knn_tc_workspace_bytes(int B, int D, int N, int k) {
-    (void)D;
-    return tc_layout(nullptr, B, N, tc_list_len(k)).bytes;
+    return tc_layout(nullptr, B, D, N, tc_list_len(k)).bytes;
 }
 
 template <int KL>
@@ -458,17 +510,19 @@ static int run_tc(const float* x, int B, int D, int N, int k, int64_t* idx, floa
     int idx_bits = 1;
     while ((1 << idx_bits) < N) ++idx_bits;
     const unsigned keep_mask = ~((1u << idx_bits) - 1u);
-    cudaMemsetAsync(L.xmax, 0, (size_t)B * sizeof(unsigned) + sizeof(int), st);   // also clears fb_count
-    knn_pack_kernel<<<dim3((N + 31) / 32, B), 256, 0, st>>>(x, D, N, L.xa, L.xb, L.sq, L.xmax);
-    int rc = check_launch("knn_pack_kernel");
+    knn_mean_kernel<<<(B * D + 7) / 8, 256, 0, st>>>(x, B * D, N, L.mu, L.cmax, L.n_zero);   // also clears cmax / fb_count
+    int rc = check_launch("knn_mean_kernel");
     if (rc) return rc;
-    CUtensorMap map_a, map_b;
-    if (!make_row_map(&map_a, L.xa, rows) || !make_row_map(&map_b, L.xb, rows)) return fail(HPCS_ERR_CUDA, "knn_tc: cuTensorMapEncodeTiled failed");
+    knn_pack_kernel<<<dim3((N + 31) / 32, B), 256, 0, st>>>(x, L.mu, D, N, L.xc, L.xr, L.sq, L.sqc, L.cmax);
+    rc = check_launch("knn_pack_kernel");
+    if (rc) return rc;
+    CUtensorMap map_c;
+    if (!make_row_map(&map_c, L.xc, rows)) return fail(HPCS_ERR_CUDA, "knn_tc: cuTensorMapEncodeTiled failed");
     {
-        const size_t smem = 4 * (size_t)kAtomBytes + (size_t)kTcQueue * kTM * sizeof(float) + 6 * sizeof(uint64_t) + 16 + 1024;
+        const size_t smem = 4 * (size_t)kAtomBytes + (size_t)kTcQueue * kTM * sizeof(float) + 7 * sizeof(uint64_t) + 16 + 1024;
         auto kern = knn_tc_kernel<KL>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<dim3((N + kTM - 1) / kTM, B), 160, smem, st>>>(map_a, map_b, L.sq, N, keep_mask, L.cand);
+        kern<<<dim3((N + kTM - 1) / kTM, B), 160, smem, st>>>(map_c, L.sqc, N, keep_mask, L.cand);
         rc = check_launch("knn_tc_kernel");
         if (rc) return rc;
     }
@@ -476,7 +530,7 @@ static int run_tc(const float* x, int B, int D, int N, int k, int64_t* idx, floa
         const size_t smem = 8 * ((size_t)KL * (kKP + 4) + kKP) * sizeof(float);
         auto kern = knn_rerank_kernel<KL>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<dim3((N + 7) / 8, B), 256, smem, st>>>(L.xb, L.sq, L.cand, L.xmax, D, N, k, keep_mask, idx_bits, idx, val,
+        kern<<<dim3((N + 7) / 8, B), 256, smem, st>>>(L.xr, L.sq, L.sqc, L.cand, L.cmax, D, N, k, keep_mask, idx_bits, idx, val,
                                                       L.fb_list, L.fb_count);
         rc = check_launch("knn_rerank_kernel");
         if (rc) return rc;
@@ -488,8 +542,8 @@ static int run_tc(const float* x, int B, int D, int N, int k, int64_t* idx, floa
 }
 
 // rows redone by the exact fallback in the last call that used this workspace (synchronises the stream)
-int knn_tc_fallback_rows(const void* ws, int B, int N, int k, cudaStream_t st, int* out_host) {
-    const TcLayout L = tc_layout(const_cast<void*>(ws), B, N, tc_list_len(k));
+int knn_tc_fallback_rows(const void* ws, int B, int D, int N, int k, cudaStream_t st, int* out_host) {
+    const TcLayout L = tc_layout(const_cast<void*>(ws), B, D, N, tc_list_len(k));
     cudaError_t e = cudaMemcpyAsync(out_host, L.fb_count, sizeof(int), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return fail(HPCS_ERR_CUDA, "knn_tc_fallback_rows: %s", cudaGetErrorString(e));
@@ -498,7 +552,7 @@ int knn_tc_fallback_rows(const void* ws, int B, int N, int k, cudaStream_t st, i
 
 int knn_tc_run(const float* x, int B, int D, int N, int k, int64_t* idx, float* val, void* ws, size_t ws_bytes, cudaStream_t st) {
     const int KL = tc_list_len(k);
-    const TcLayout L = tc_layout(ws, B, N, KL);
+    const TcLayout L = tc_layout(ws, B, D, N, KL);
     if (ws_bytes < L.bytes) return fail(HPCS_ERR_WORKSPACE, "knn: workspace too small");
     if ((reinterpret_cast<uintptr_t>(ws) & 255) != 0) return fail(HPCS_ERR_ARG, "knn: workspace must be 256-byte aligned");
     return KL == 32 ? run_tc<32>(x, B, D, N, k, idx, val, L, st) : run_tc<64>(x, B, D, N, k, idx, val, L, st);

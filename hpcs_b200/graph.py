@@ -51,19 +51,39 @@ def knn(x: torch.Tensor, k: int, return_values: bool = False, method: str = "aut
     return (idx, val) if return_values else idx
 
 
+def edge_features_forward(x: torch.Tensor, idx: torch.Tensor, cross: bool = False) -> torch.Tensor:
+    """Raw forward launch (no autograd): x[B,C,3,N] contiguous fp32, idx[B,N,k] contiguous int64."""
+    B, C, _, N = x.shape
+    k = idx.shape[2]
+    dev = x.device
+    lib = _lib.load()
+    out = torch.empty((B, (3 if cross else 2) * C, 3, N, k), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.hpcs_edge_feat_fwd_f32(x.data_ptr(), idx.data_ptr(), B, C, N, k, int(cross),
+                                              out.data_ptr(), _lib.stream_ptr(dev)), "hpcs_edge_feat_fwd_f32")
+    return out
+
+
+def edge_features_backward(gout: torch.Tensor, x: torch.Tensor, idx: torch.Tensor, cross: bool = False) -> torch.Tensor:
+    """Raw backward launch: gradient of the edge features wrt x (deterministic gather, see csrc/edge_feat.cu)."""
+    B, C, _, N = x.shape
+    k = idx.shape[2]
+    dev = x.device
+    lib = _lib.load()
+    gout = gout.contiguous()
+    gx = torch.empty_like(x)
+    ws = _lib.workspace(lib.hpcs_edge_feat_bwd_workspace_bytes(B, N, k), dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.hpcs_edge_feat_bwd_f32(gout.data_ptr(), x.data_ptr(), idx.data_ptr(), B, C, N, k,
+                                              int(cross), gx.data_ptr(), ws.data_ptr(), ws.numel(),
+                                              _lib.stream_ptr(dev)), "hpcs_edge_feat_bwd_f32")
+    return gx
+
+
 class _EdgeFeature(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, idx, cross):
-        # x[B,C,3,N] contiguous fp32, idx[B,N,k] contiguous int64
-        B, C, _, N = x.shape
-        k = idx.shape[2]
-        dev = x.device
-        lib = _lib.load()
-        planes = 3 if cross else 2
-        out = torch.empty((B, planes * C, 3, N, k), dtype=torch.float32, device=dev)
-        with torch.cuda.device(dev):
-            _lib.check(lib.hpcs_edge_feat_fwd_f32(x.data_ptr(), idx.data_ptr(), B, C, N, k, int(cross),
-                                                  out.data_ptr(), _lib.stream_ptr(dev)), "hpcs_edge_feat_fwd_f32")
+        out = edge_features_forward(x, idx, cross)
         ctx.save_for_backward(x, idx)
         ctx.cross = cross
         return out
@@ -71,18 +91,7 @@ class _EdgeFeature(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gout):
         x, idx = ctx.saved_tensors
-        B, C, _, N = x.shape
-        k = idx.shape[2]
-        dev = x.device
-        lib = _lib.load()
-        gout = gout.contiguous()
-        gx = torch.empty_like(x)
-        ws = _lib.workspace(lib.hpcs_edge_feat_bwd_workspace_bytes(B, N, k), dev)
-        with torch.cuda.device(dev):
-            _lib.check(lib.hpcs_edge_feat_bwd_f32(gout.data_ptr(), x.data_ptr(), idx.data_ptr(), B, C, N, k,
-                                                  int(ctx.cross), gx.data_ptr(), ws.data_ptr(), ws.numel(),
-                                                  _lib.stream_ptr(dev)), "hpcs_edge_feat_bwd_f32")
-        return gx, None, None
+        return edge_features_backward(gout, x, idx, ctx.cross), None, None
 
 
 def _edge_features(x: torch.Tensor, k: int, idx: Optional[torch.Tensor], x_coord: Optional[torch.Tensor],
