@@ -16,6 +16,11 @@
 
 namespace hpcs {
 
+// fast backward path (edge_bwd.cu)
+bool edge_bwd_fast_applicable(const float* gout, int N, int k);
+size_t edge_bwd_fast_workspace_bytes(int B, int N, int k);
+int edge_bwd_fast_run(const float* gout, const int64_t* idx, int B, int C, int N, int k, float* gx, void* ws, cudaStream_t st);
+
 // ------------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------------
@@ -464,7 +469,9 @@ int hpcs_edge_feat_fwd_f32(const float* x, const int64_t* idx, int B, int C, int
 
 size_t hpcs_edge_feat_bwd_workspace_bytes(int B, int N, int k) {
     if (B <= 0 || N <= 0 || k <= 0) return 0;
-    return hpcs::align_up((size_t)B * hpcs::rev_graph(nullptr, 0, N, k).ints_per_cloud * sizeof(int), 256);
+    const size_t general = hpcs::align_up((size_t)B * hpcs::rev_graph(nullptr, 0, N, k).ints_per_cloud * sizeof(int), 256);
+    const size_t fast = hpcs::align_up(hpcs::edge_bwd_fast_workspace_bytes(B, N, k), 256);
+    return general > fast ? general : fast;
 }
 
 int hpcs_edge_feat_bwd_f32(const float* gout, const float* x, const int64_t* idx, int B, int C, int N, int k,
@@ -476,6 +483,7 @@ int hpcs_edge_feat_bwd_f32(const float* gout, const float* x, const int64_t* idx
     if (B > 65535) return fail(HPCS_ERR_ARG, "edge_feat_bwd: B > 65535");
     cudaStream_t st = as_stream(stream);
     const size_t E = (size_t)N * k;
+    if (!cross && edge_bwd_fast_applicable(gout, N, k)) return edge_bwd_fast_run(gout, idx, B, C, N, k, gx, ws, st);
     int* wsi = static_cast<int*>(ws);
     {
         // warps per CTA: as many private histogram rows as fit in ~128 KB of shared memory

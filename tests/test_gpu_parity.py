@@ -153,6 +153,41 @@ def test_edge_features_fwd_bwd_vs_oracle(hb, B, C, N, k, cross):
     assert torch.equal(fn(dev(x), k=k), got.detach())
 
 
+def _edge_bwd_reference_fp64(gout, idx, C):
+    """gx = sum_j gctr - sum_j gdiff + scatter_add(gdiff by idx), in fp64 with torch ops (independent of the kernels)."""
+    B, _, _, N, k = gout.shape
+    g = gout.double()
+    gdiff, gctr = g[:, :C], g[:, C:2 * C]
+    own = gctr.sum(-1) - gdiff.sum(-1)                                      # [B,C,3,N]
+    tgt = idx.view(B, 1, 1, N * k).expand(B, C, 3, N * k)
+    return own.scatter_add(3, tgt, gdiff.reshape(B, C, 3, N * k))
+
+
+@pytest.mark.parametrize("B,C,N,k,dups", [(32, 21, 1024, 20, False), (4, 1, 1024, 20, False), (2, 5, 2048, 20, False),
+                                          (3, 2, 300, 12, False), (2, 3, 100, 8, False), (2, 4, 512, 16, True),
+                                          (1, 2, 1024, 40, False)])
+def test_edge_backward_persistent_gather(hb, B, C, N, k, dups):
+    """The TMA-fed persistent gather (csrc/edge_bwd.cu) at BASELINE size and at the shapes that exercise its
+    slicing (N=2048: 8 slices; N=300: padded slice; N=100: one short slice), the duplicate-index escape
+    path, and a shape that must fall back to the general kernel (k=40: two planes do not fit shared memory)."""
+    gen = torch.Generator().manual_seed(N + k + C)
+    x = dev(torch.randn(B, C, 3, N, generator=gen))
+    if dups:
+        idx = torch.randint(0, N, (B, N, k), generator=gen)
+        idx[:, :, 1] = idx[:, :, 0]                                         # duplicate target inside every row
+        idx = dev(idx)
+    else:
+        idx = hb.knn(x.view(B, 3 * C, N), k)
+    from hpcs_b200 import graph as hgraph
+    gout = torch.randn(B, 2 * C, 3, N, k, device=x.device, generator=torch.Generator(device=x.device).manual_seed(1))
+    got = hgraph.edge_features_backward(gout, x, idx)
+    want = _edge_bwd_reference_fp64(gout, idx, C)
+    assert rel_err(got, want) < 1e-5
+    assert (got.double() - want).abs().max() <= 1e-4 * want.abs().max()
+    if not dups:                                                            # fixed summation order: bitwise repeatable
+        assert torch.equal(got, hgraph.edge_features_backward(gout, x, idx))
+
+
 def test_edge_features_golden(hb, golden):
     g = golden("edge_feat")
     x = dev(t(g["x"])).requires_grad_(True)

@@ -1,0 +1,51 @@
+"""Time the edge-feature backward at the bench shape for several HPCS_BWD_CHUNK values (CUDA-graph replay)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import hpcs_b200 as hb  # noqa: E402
+from hpcs_b200 import graph as hgraph  # noqa: E402
+
+
+def graph_time(fn, reps=20):
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(reps):
+        g.replay()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / reps * 1e3
+
+
+def main():
+    dev = torch.device("cuda:0")
+    B, C, N, K = 32, 21, 1024, 20
+    x = torch.randn(B, C, 3, N, device=dev)
+    idx = hb.knn(x.view(B, 3 * C, N), K)
+    g = torch.randn(B, 2 * C, 3, N, K, device=dev)
+    bytes_ = g.numel() * 4 + idx.numel() * 8 + x.numel() * 4
+    for spec in sys.argv[1:] or ["81920", "16384", "8192", "4096", "2048", "1024"]:
+        chunk, _, mode = spec.partition(":")
+        os.environ["HPCS_BWD_CHUNK"] = chunk
+        os.environ["HPCS_BWD_MODE"] = mode or "0"
+        us = graph_time(lambda: hgraph.edge_features_backward(g, x, idx))
+        print(f"chunk {chunk:>6s} mode {mode or '0'}: {us:8.1f} us   {bytes_ / us / 1e3:7.1f} GB/s", flush=True)
+
+
+if __name__ == "__main__":
+    main()
