@@ -474,6 +474,10 @@ size_t hpcs_edge_feat_bwd_workspace_bytes(int B, int N, int k) {
     return general > fast ? general : fast;
 }
 
+int hpcs_edge_feat_bwd_is_fast(const float* gout, int N, int k, int cross) {
+    return (!cross && N > 0 && k > 0 && hpcs::edge_bwd_fast_applicable(gout, N, k)) ? 1 : 0;
+}
+
 int hpcs_edge_feat_bwd_f32(const float* gout, const float* x, const int64_t* idx, int B, int C, int N, int k,
                            int cross, float* gx, void* ws, size_t ws_bytes, void* stream) {
     using namespace hpcs;

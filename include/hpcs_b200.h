@@ -69,6 +69,10 @@ int hpcs_edge_feat_fwd_f32(const float* x, const int64_t* idx, int B, int C, int
 /* backward of the above wrt x: gx[B,C,3,N] (overwritten).  Deterministic: the scatter is turned
  * into a gather through a reverse (target -> sources) CSR built in the workspace. */
 size_t hpcs_edge_feat_bwd_workspace_bytes(int B, int N, int k);
+/* 1 when hpcs_edge_feat_bwd_f32 will take the persistent TMA gather for this shape (no cross term, N <= 2048,
+ * N*k <= 65535, N*k % 4 == 0, 16-byte aligned gout, two N*k planes fit shared memory); that path sums in a fixed
+ * order (bitwise repeatable).  The general path is repeatable up to the placement of equal-degree targets. */
+int hpcs_edge_feat_bwd_is_fast(const float* gout, int N, int k, int cross);
 int hpcs_edge_feat_bwd_f32(const float* gout, const float* x, const int64_t* idx, int B, int C, int N,
                            int k, int cross, float* gx, void* ws, size_t ws_bytes, void* stream);
 

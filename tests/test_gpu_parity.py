@@ -184,7 +184,10 @@ def test_edge_backward_persistent_gather(hb, B, C, N, k, dups):
     want = _edge_bwd_reference_fp64(gout, idx, C)
     assert rel_err(got, want) < 1e-5
     assert (got.double() - want).abs().max() <= 1e-4 * want.abs().max()
-    if not dups:                                                            # fixed summation order: bitwise repeatable
+    from hpcs_b200 import _lib
+    fast = bool(_lib.load().hpcs_edge_feat_bwd_is_fast(gout.data_ptr(), N, k, 0))
+    assert fast == (N * k <= 24576)                                         # two planes must fit shared memory
+    if fast and not dups:                                                   # fixed summation order: bitwise repeatable
         assert torch.equal(got, hgraph.edge_features_backward(gout, x, idx))
 
 

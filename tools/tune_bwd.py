@@ -1,4 +1,5 @@
-"""Time the edge-feature backward at the bench shape for several HPCS_BWD_CHUNK values (CUDA-graph replay)."""
+"""Time the edge-feature backward at the bench shape (CUDA-graph replay) and print the per-phase cycle split of the
+persistent gather.  The split needs a profiling build:  add "-DHPCS_BWD_PROFILE" to NVCC_FLAGS in hpcs_b200/build.py."""
 import os
 import sys
 
@@ -39,6 +40,19 @@ def main():
     idx = hb.knn(x.view(B, 3 * C, N), K)
     g = torch.randn(B, 2 * C, 3, N, K, device=dev)
     bytes_ = g.numel() * 4 + idx.numel() * 8 + x.numel() * 4
+    os.environ["HPCS_BWD_NBUF"] = os.environ.get("NBUF", "2")
+    prof = torch.zeros(8 * 320, dtype=torch.int64, device=dev)
+    os.environ["HPCS_BWD_PROF_PTR"] = hex(prof.data_ptr())
+    hgraph.edge_features_backward(g, x, idx)
+    torch.cuda.synchronize()
+    del os.environ["HPCS_BWD_PROF_PTR"]
+    pr = prof.view(320, 8).cpu().double()
+    pr = pr[pr.sum(1) > 0]
+    names = ["meta-tail", "wait", "centre", "gather", "combine", "issue", "meta-loads", "meta-sync1"]
+    tot = pr.sum(1).mean().item()
+    print("phase cycles per CTA (mean over %d CTAs), total %.0f:" % (pr.shape[0], tot))
+    for i, nme in enumerate(names):
+        print(f"   {nme:8s} {pr[:, i].mean().item():10.0f}  {100 * pr[:, i].mean().item() / tot:5.1f}%   max {pr[:, i].max().item():10.0f}")
     for spec in sys.argv[1:] or ["81920", "16384", "8192", "4096", "2048", "1024"]:
         chunk, _, mode = spec.partition(":")
         os.environ["HPCS_BWD_CHUNK"] = chunk
