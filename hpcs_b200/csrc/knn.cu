@@ -47,8 +47,9 @@ __global__ void knn_sqnorm_kernel(const float* __restrict__ x, int D, int N, flo
 template <int DREG, int QW, int SLOTS, bool STAGED>
 __global__ void __launch_bounds__(kKnnWarps * 32)
 knn_kernel(const float* __restrict__ x, const float* __restrict__ sq, int D, int Dp, int N, int k,
-           int64_t* __restrict__ idx, float* __restrict__ val) {
+           int64_t* __restrict__ idx, float* __restrict__ val, const int* __restrict__ gate, int gate_min) {
     extern __shared__ __align__(16) float smem[];
+    if (gate && *gate <= gate_min) return;                // whole-grid early exit (tensor-core path: nothing to redo)
     const int b = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -184,8 +185,9 @@ knn_kernel(const float* __restrict__ x, const float* __restrict__ sq, int D, int
 template <int D, int K, int THREADS, int TC>
 __global__ void __launch_bounds__(THREADS)
 knn_rows_kernel(const float* __restrict__ x, const float* __restrict__ sq, int N, int k,
-                int64_t* __restrict__ idx, float* __restrict__ val) {
+                int64_t* __restrict__ idx, float* __restrict__ val, const int* __restrict__ gate, int gate_min) {
     constexpr int QCAP = kRowQueue;
+    if (gate && *gate <= gate_min) return;                // whole-grid early exit (tensor-core path: nothing to redo)
     extern __shared__ __align__(16) float smem[];
     float* cs = smem;                                  // [D][TC]
     float* sqc = cs + D * TC;                          // [TC]
@@ -257,30 +259,30 @@ knn_rows_kernel(const float* __restrict__ x, const float* __restrict__ sq, int N
 
 template <int D, int K>
 static int launch_knn_rows(const float* x, const float* sq, int B, int N, int k, int64_t* idx, float* val,
-                           cudaStream_t st) {
+                           const int* gate, int gate_min, cudaStream_t st) {
     constexpr int THREADS = 64;
     constexpr int TC = D <= 4 ? 512 : 128;
     constexpr size_t smem = ((size_t)D * TC + TC + 2 * kRowQueue * THREADS) * sizeof(float);
     auto kern = knn_rows_kernel<D, K, THREADS, TC>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<dim3((N + THREADS - 1) / THREADS, B), THREADS, smem, st>>>(x, sq, N, k, idx, val);
+    kern<<<dim3((N + THREADS - 1) / THREADS, B), THREADS, smem, st>>>(x, sq, N, k, idx, val, gate, gate_min);
     return check_launch("knn_rows_kernel");
 }
 
 template <int D>
 static int dispatch_rows(const float* x, const float* sq, int B, int N, int k, int64_t* idx, float* val,
-                         cudaStream_t st, bool* handled) {
+                         const int* gate, int gate_min, cudaStream_t st, bool* handled) {
     *handled = true;
-    if (k <= 10) return launch_knn_rows<D, 10>(x, sq, B, N, k, idx, val, st);
-    if (k <= 20) return launch_knn_rows<D, 20>(x, sq, B, N, k, idx, val, st);
-    if (k <= 40) return launch_knn_rows<D, 40>(x, sq, B, N, k, idx, val, st);
+    if (k <= 10) return launch_knn_rows<D, 10>(x, sq, B, N, k, idx, val, gate, gate_min, st);
+    if (k <= 20) return launch_knn_rows<D, 20>(x, sq, B, N, k, idx, val, gate, gate_min, st);
+    if (k <= 40) return launch_knn_rows<D, 40>(x, sq, B, N, k, idx, val, gate, gate_min, st);
     *handled = false;
     return HPCS_OK;
 }
 
 template <int DREG, int QW, int SLOTS>
 static int launch_knn(const float* x, const float* sq, int B, int D, int N, int k, int64_t* idx, float* val,
-                      cudaStream_t st) {
+                      const int* gate, int gate_min, cudaStream_t st) {
     const int Dp = (D + 3) / 4 * 4;
     constexpr int QB = kKnnWarps * QW;
     dim3 grid((N + QB - 1) / QB, B), block(kKnnWarps * 32);
@@ -289,25 +291,40 @@ static int launch_knn(const float* x, const float* sq, int B, int D, int N, int 
     if (smem_staged <= 64 * 1024) {
         auto kern = knn_kernel<DREG, QW, SLOTS, true>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        kern<<<grid, block, smem_staged, st>>>(x, sq, D, Dp, N, k, idx, val);
+        kern<<<grid, block, smem_staged, st>>>(x, sq, D, Dp, N, k, idx, val, gate, gate_min);
     } else {
         if (smem_q > 200 * 1024) return fail(HPCS_ERR_ARG, "knn: D=%d too large", D);
         auto kern = knn_kernel<DREG, QW, SLOTS, false>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_q);
-        kern<<<grid, block, smem_q, st>>>(x, sq, D, Dp, N, k, idx, val);
+        kern<<<grid, block, smem_q, st>>>(x, sq, D, Dp, N, k, idx, val, gate, gate_min);
     }
     return check_launch("knn_kernel");
 }
 
 template <int DREG, int QW>
 static int dispatch_slots(const float* x, const float* sq, int B, int D, int N, int k, int64_t* idx, float* val,
-                          cudaStream_t st) {
-    if (k <= 32) return launch_knn<DREG, QW, 1>(x, sq, B, D, N, k, idx, val, st);
-    if (k <= 64) return launch_knn<DREG, QW, 2>(x, sq, B, D, N, k, idx, val, st);
-    if (k <= 128) return launch_knn<DREG, QW, 4>(x, sq, B, D, N, k, idx, val, st);
+                          const int* gate, int gate_min, cudaStream_t st) {
+    if (k <= 32) return launch_knn<DREG, QW, 1>(x, sq, B, D, N, k, idx, val, gate, gate_min, st);
+    if (k <= 64) return launch_knn<DREG, QW, 2>(x, sq, B, D, N, k, idx, val, gate, gate_min, st);
+    if (k <= 128) return launch_knn<DREG, QW, 4>(x, sq, B, D, N, k, idx, val, gate, gate_min, st);
     return fail(HPCS_ERR_ARG, "knn: k=%d > 128 not supported", k);
 }
 
+}  // namespace hpcs
+
+namespace hpcs {
+// the exact kernels on precomputed norms; gate == nullptr: unconditional
+int knn_ffma_gated(const float* x, const float* sq, int B, int D, int N, int k, int64_t* idx, float* val, const int* gate,
+                   int gate_min, cudaStream_t st) {
+    int rc = HPCS_OK;
+    bool handled = false;
+    if (D == 3) rc = dispatch_rows<3>(x, sq, B, N, k, idx, val, gate, gate_min, st, &handled);
+    else if (D == 63) rc = dispatch_rows<63>(x, sq, B, N, k, idx, val, gate, gate_min, st, &handled);
+    if (handled) return rc;
+    if (D <= 4) return dispatch_slots<4, 4>(x, sq, B, D, N, k, idx, val, gate, gate_min, st);
+    if (D <= 32) return dispatch_slots<32, 4>(x, sq, B, D, N, k, idx, val, gate, gate_min, st);
+    return dispatch_slots<64, 4>(x, sq, B, D, N, k, idx, val, gate, gate_min, st);
+}
 }  // namespace hpcs
 
 static int knn_ffma(const float* x, int B, int D, int N, int k, int64_t* idx, float* val, void* ws, cudaStream_t st) {
@@ -316,13 +333,7 @@ static int knn_ffma(const float* x, int B, int D, int N, int k, int64_t* idx, fl
     knn_sqnorm_kernel<<<dim3((N + 255) / 256, B), 256, 0, st>>>(x, D, N, sq);
     int rc = check_launch("knn_sqnorm_kernel");
     if (rc) return rc;
-    bool handled = false;
-    if (D == 3) rc = dispatch_rows<3>(x, sq, B, N, k, idx, val, st, &handled);
-    else if (D == 63) rc = dispatch_rows<63>(x, sq, B, N, k, idx, val, st, &handled);
-    if (handled) return rc;
-    if (D <= 4) return dispatch_slots<4, 4>(x, sq, B, D, N, k, idx, val, st);
-    if (D <= 32) return dispatch_slots<32, 4>(x, sq, B, D, N, k, idx, val, st);
-    return dispatch_slots<64, 4>(x, sq, B, D, N, k, idx, val, st);
+    return knn_ffma_gated(x, sq, B, D, N, k, idx, val, nullptr, 0, st);
 }
 
 static int knn_check(const float* x, int B, int D, int N, int k, int64_t* idx, void* ws, size_t ws_bytes) {

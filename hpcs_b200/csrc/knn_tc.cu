@@ -30,9 +30,13 @@
 
 namespace hpcs {
 
+// all-FFMA exact path (knn.cu); runs only when *gate > gate_min (device-side check at kernel entry)
+int knn_ffma_gated(const float* x, const float* sq, int B, int D, int N, int k, int64_t* idx, float* val, const int* gate,
+                   int gate_min, cudaStream_t st);
+
 constexpr int kKP = 64;                 // padded row length (fp32) of xa / xb
 constexpr int kTM = 128;                // query rows per CTA  (UMMA M)
-constexpr int kTN = 128;                // candidates per tile  (UMMA N)
+constexpr int kTN = 64;                 // candidates per tile  (UMMA N)
 constexpr int kTcQueue = 48;            // per-row FIFO depth in the epilogue
 constexpr int kAtomBytes = kTM * 128;   // one 32-fp32 K-atom of a 128-row tile
 
@@ -119,31 +123,67 @@ struct KeyTopK {
 };
 
 // ---- 2. tensor-core candidate kernel --------------------------------------------------------------------------
-template <int KL>
-__global__ void __launch_bounds__(160, 2)
-knn_tc_kernel(const __grid_constant__ CUtensorMap map_c, const float* __restrict__ sqc, int N, unsigned keep_mask,
-              float* __restrict__ cand /*[B*N][KL] keys*/) {
+// Warp roles (192 threads): warps 0-3 epilogue (thread = query row = TMEM lane), warp 4 TMA producer, warp 5 MMA issuer.
+// B tiles of kTN = 64 candidates go through a kStages-deep shared-memory ring; the accumulator (128 x 64 fp32) is
+// double-buffered in TMEM, so TMA, tcgen05.mma and the selection epilogue of three different tiles overlap.
+//
+// TWO_PASS (lists of 32, N >= 768): the epilogue is bound by the ALU pipe (min/max of the sorted insert), and a
+// running threshold admits ~5x more candidates than end up in the list.  The Gram tiles are so cheap on the tensor
+// cores that they are simply computed twice: pass 1 only takes the maximum of every chunk of columns (1 op per
+// score) and sets the row threshold to the 24th largest chunk maximum -- at least 24 scores reach it, ~40 on
+// average -- and pass 2 inserts just those.  Scores below the threshold are bounded by it in the safety test.
+constexpr int kStages = 3;
+constexpr int kTcThreads = 192;
+constexpr int kChunkMax = 48;            // chunk maxima per row (pass 1), == kTcQueue rows of the shared FIFO
+constexpr int kThrRank = 24;             // threshold = kThrRank-th largest chunk maximum (>= k for lists of 32)
+constexpr int kAtomB = kTN * 128;        // one 32-fp32 K-atom of a B tile
+
+template <int NV>
+__device__ __forceinline__ void sort_desc(float (&c)[NV]) {           // bitonic network, fully unrolled: static indices
+#pragma unroll
+    for (int size = 2; size <= NV; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int j = i ^ stride;
+                if (j > i) {
+                    const bool desc = (i & size) == 0;
+                    const float hi = fmaxf(c[i], c[j]), lo = fminf(c[i], c[j]);
+                    c[i] = desc ? hi : lo;
+                    c[j] = desc ? lo : hi;
+                }
+            }
+        }
+    }
+}
+
+template <int KL, bool TWO_PASS>
+__global__ void __launch_bounds__(kTcThreads, 2)
+knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const float* __restrict__ sqc,
+              int N, unsigned keep_mask, float* __restrict__ cand /*[B*N][KL] keys*/, float* __restrict__ tau_out /*[B*N]*/) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // the 128B-swizzle atoms must start on 1024-byte boundaries of the shared window
     unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
     unsigned char* sA = smem;                                          // 2 K-atoms x 16 KB
-    unsigned char* sB = smem + 2 * kAtomBytes;                         // 2 K-atoms x 16 KB
-    float* qk = reinterpret_cast<float*>(smem + 4 * kAtomBytes);       // [kTcQueue][128] pending keys
-    uint64_t* bars = reinterpret_cast<uint64_t*>(qk + kTcQueue * kTM); // full_a, full_b, mma[2], epi[2], a_ready
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
-    uint64_t* full_a = bars, *full_b = bars + 1, *mma_done = bars + 2, *epi_done = bars + 4, *a_ready = bars + 6;
+    unsigned char* sB = smem + 2 * kAtomBytes;                         // kStages x 2 K-atoms x 8 KB
+    float* qk = reinterpret_cast<float*>(sB + kStages * 2 * kAtomB);   // [kTcQueue][128] pending keys / chunk maxima
+    uint64_t* bars = reinterpret_cast<uint64_t*>(qk + kTcQueue * kTM);
+    uint64_t* full_a = bars, *a_ready = bars + 1, *full_b = bars + 2, *slot_free = full_b + kStages,
+              *acc_full = slot_free + kStages, *epi_done = acc_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(epi_done + 2);
 
     const int b = blockIdx.y;
     const int m0 = blockIdx.x * kTM;                                   // first query row of this CTA (in the cloud)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int T = (N + kTN - 1) / kTN;
+    const int TV = (N + kTN - 1) / kTN;                                // tiles of the cloud
+    const int V = TWO_PASS ? 2 * TV : TV;                              // tile visits
 
     if (threadIdx.x == 0) {
         ptx::mbar_init(full_a, 1);
-        ptx::mbar_init(full_b, 1);
-        ptx::mbar_init(mma_done, 1); ptx::mbar_init(mma_done + 1, 1);
-        ptx::mbar_init(epi_done, 4); ptx::mbar_init(epi_done + 1, 4);
         ptx::mbar_init(a_ready, 4);
+        for (int s = 0; s < kStages; ++s) { ptx::mbar_init(full_b + s, 1); ptx::mbar_init(slot_free + s, 1); }
+        for (int s = 0; s < 2; ++s) { ptx::mbar_init(acc_full + s, 1); ptx::mbar_init(epi_done + s, 4); }
         ptx::fence_barrier_init();
     }
     if (warp == 4) ptx::tmem_alloc<2 * kTN>(tmem_slot);
@@ -153,36 +193,48 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_c, const float* __restrict
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 4) {
-        // ===== producer: TMA + MMA issue (one elected lane) =====
+        // ===== TMA producer (one elected lane) =====
         if (lane == 0) {
-            ptx::tma_prefetch_desc(&map_c);
+            ptx::tma_prefetch_desc(&map_a);
+            ptx::tma_prefetch_desc(&map_b);
             const int rowA = b * N + m0;
             ptx::mbar_arrive_expect_tx(full_a, 2 * kAtomBytes);
-            ptx::tma_load_2d(sA, &map_c, full_a, 0, rowA);
-            ptx::tma_load_2d(sA + kAtomBytes, &map_c, full_a, 32, rowA);
+            ptx::tma_load_2d(sA, &map_a, full_a, 0, rowA);
+            ptx::tma_load_2d(sA + kAtomBytes, &map_a, full_a, 32, rowA);
+            for (int v = 0; v < V; ++v) {
+                const int s = v % kStages, use = v / kStages;
+                if (use >= 1) ptx::mbar_wait(slot_free + s, (use - 1) & 1);                 // its previous MMA has retired
+                const int rowB = b * N + (v % TV) * kTN;
+                unsigned char* dst = sB + s * 2 * kAtomB;
+                ptx::mbar_arrive_expect_tx(full_b + s, 2 * kAtomB);
+                ptx::tma_load_2d(dst, &map_b, full_b + s, 0, rowB);
+                ptx::tma_load_2d(dst + kAtomB, &map_b, full_b + s, 32, rowB);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 5) {
+        // ===== MMA issuer (one elected lane) =====
+        if (lane == 0) {
             const uint32_t idesc = ptx::umma_idesc_tf32(kTM, kTN);
             const uint32_t a_addr = ptx::smem_u32(sA), b_addr = ptx::smem_u32(sB);
-            for (int t = 0; t < T; ++t) {
-                if (t >= 1) ptx::mbar_wait(mma_done + ((t - 1) & 1), ((t - 1) >> 1) & 1);   // B buffer free
-                const int rowB = b * N + t * kTN;
-                ptx::mbar_arrive_expect_tx(full_b, 2 * kAtomBytes);
-                ptx::tma_load_2d(sB, &map_c, full_b, 0, rowB);
-                ptx::tma_load_2d(sB + kAtomBytes, &map_c, full_b, 32, rowB);
-                if (t == 0) ptx::mbar_wait(a_ready, 0);                                     // A landed and patched
-                ptx::mbar_wait(full_b, t & 1);
-                if (t >= 2) ptx::mbar_wait(epi_done + (t & 1), ((t >> 1) - 1) & 1);         // accumulator drained
+            ptx::mbar_wait(a_ready, 0);                                                     // A landed and patched
+            for (int v = 0; v < V; ++v) {
+                const int s = v % kStages, use = v / kStages, a = v & 1;
+                ptx::mbar_wait(full_b + s, use & 1);
+                if (v >= 2) ptx::mbar_wait(epi_done + a, ((v >> 1) - 1) & 1);               // accumulator drained
                 ptx::tc_fence_after_sync();
-                const uint32_t acc = tmem_base + (t & 1) * kTN;
+                const uint32_t acc = tmem_base + a * kTN;
 #pragma unroll
                 for (int ka = 0; ka < 2; ++ka) {
 #pragma unroll
                     for (int kk = 0; kk < 4; ++kk) {                                       // 8 tf32 = 32 bytes per MMA
                         const uint64_t da = ptx::umma_desc_k_sw128(a_addr + ka * kAtomBytes + kk * 32);
-                        const uint64_t db = ptx::umma_desc_k_sw128(b_addr + ka * kAtomBytes + kk * 32);
+                        const uint64_t db = ptx::umma_desc_k_sw128(b_addr + (s * 2 + ka) * kAtomB + kk * 32);
                         ptx::umma_tf32(acc, da, db, idesc, (ka | kk) != 0);
                     }
                 }
-                ptx::umma_commit(mma_done + (t & 1));
+                ptx::umma_commit(slot_free + s);
+                ptx::umma_commit(acc_full + a);
             }
         }
         __syncwarp();
@@ -198,11 +250,59 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_c, const float* __restrict
         ptx::fence_proxy_async_smem();                                 // generic-proxy write -> visible to the MMA
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(a_ready);
+        float* myq = qk + row;
+        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+        int v0 = 0;                                                    // first tile visit of the selection pass
+        float thr = -INFINITY;                                         // raw-score threshold (TWO_PASS)
+        if (TWO_PASS) {
+            // ---- pass 1: chunk maxima -> threshold ----
+            const int cw = (N + 32 * kChunkMax - 1) / (32 * kChunkMax);   // 32-column loads per chunk: 24..48 chunks for N >= 768
+            float cur = -INFINITY;
+            int filled = 0, nch = 0;
+            for (int v = 0; v < TV; ++v) {
+                ptx::mbar_wait(acc_full + (v & 1), (v >> 1) & 1);
+                ptx::tc_fence_after_sync();
+#pragma unroll 1
+                for (int c0 = 0; c0 < kTN; c0 += 32) {
+                    const int jbase = v * kTN + c0;
+                    if (jbase >= N) break;                             // warp-uniform
+                    float x[32];
+                    ptx::tmem_ld_32x32(trow + (v & 1) * kTN + c0, x);
+                    if (jbase + 32 > N) {
+#pragma unroll
+                        for (int c = 0; c < 32; ++c) if (jbase + c >= N) x[c] = -INFINITY;
+                    }
+                    float m = x[0];
+#pragma unroll
+                    for (int c = 1; c < 32; ++c) m = fmaxf(m, x[c]);
+                    cur = fmaxf(cur, m);
+                    if (++filled == cw || jbase + 32 >= N) { myq[nch * kTM] = cur; ++nch; cur = -INFINITY; filled = 0; }
+                }
+                ptx::tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(epi_done + (v & 1));
+            }
+            if (nch <= 32) {                                           // warp-uniform (depends on N only)
+                float c[32];
+#pragma unroll
+                for (int u = 0; u < 32; ++u) c[u] = u < nch ? myq[u * kTM] : -INFINITY;
+                sort_desc<32>(c);
+                thr = c[kThrRank - 1];
+            } else {
+                float c[64];
+#pragma unroll
+                for (int u = 0; u < 64; ++u) c[u] = u < nch ? myq[u * kTM] : -INFINITY;
+                sort_desc<64>(c);
+                thr = c[kThrRank - 1];
+            }
+            __syncwarp();                                              // the FIFO reuses the chunk-maxima rows
+            v0 = TV;
+        }
+        // ---- selection pass: sorted insert of the scores that pass the threshold(s) ----
         KeyTopK<KL> top;
         top.init();
         float tau = -INFINITY;
         int qlen = 0;
-        float* myq = qk + row;
         auto flush = [&]() {
             int rounds = qlen;
 #pragma unroll
@@ -211,26 +311,43 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_c, const float* __restrict
             qlen = 0;
             tau = top.key[KL - 1];
         };
-        for (int t = 0; t < T; ++t) {
-            ptx::mbar_wait(mma_done + (t & 1), (t >> 1) & 1);
+        for (int v = v0; v < V; ++v) {
+            const int tile = v - v0;
+            ptx::mbar_wait(acc_full + (v & 1), (v >> 1) & 1);
             ptx::tc_fence_after_sync();
-            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (t & 1) * kTN;
 #pragma unroll 1
             for (int c0 = 0; c0 < kTN; c0 += 32) {
+                const unsigned jbase = tile * kTN + c0;
+                if (jbase >= (unsigned)N) break;                       // warp-uniform
                 if (__any_sync(kFull, qlen > kTcQueue - 32)) flush();
-                float v[32];
-                ptx::tmem_ld_32x32(taddr + c0, v);
-                const unsigned jbase = t * kTN + c0;
+                float x[32];
+                ptx::tmem_ld_32x32(trow + (v & 1) * kTN + c0, x);
+                if (TWO_PASS && jbase + 32 <= (unsigned)N) {
+                    // branch-free: the key always goes to the next FIFO slot, the slot only advances for a score
+                    // that reaches the row threshold (~4 % of them); no per-element divergence
+                    float* slot = myq + qlen * kTM;
+                    const unsigned hi_bits = jbase;                    // multiple of 32: index = jbase | c
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const unsigned j = jbase + c;
-                    const float key = make_key(v[c] - h, j, keep_mask);
-                    if (j < (unsigned)N && key > tau) { myq[qlen * kTM] = key; ++qlen; }
+                    for (int c = 0; c < 32; ++c) {
+                        const unsigned bits = (__float_as_uint(x[c] - h) & keep_mask) | hi_bits;
+                        *slot = __uint_as_float(bits | (unsigned)c);
+                        slot += x[c] >= thr ? kTM : 0;
+                    }
+                    qlen = (int)(slot - myq) / kTM;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        const unsigned j = jbase + c;
+                        if (x[c] >= thr && j < (unsigned)N) {
+                            const float key = make_key(x[c] - h, j, keep_mask);
+                            if (key > tau) { myq[qlen * kTM] = key; ++qlen; }
+                        }
+                    }
                 }
             }
             ptx::tc_fence_before_sync();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(epi_done + (t & 1));
+            if (lane == 0) ptx::mbar_arrive(epi_done + (v & 1));
         }
         flush();
         if (i < N) {
@@ -238,6 +355,16 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_c, const float* __restrict
 #pragma unroll
             for (int m = 0; m < KL; m += 4)
                 *reinterpret_cast<float4*>(out + m) = make_float4(top.key[m], top.key[m + 1], top.key[m + 2], top.key[m + 3]);
+            // bound on the key of every score that is NOT in the list: pushed out of it (<= last key) or below the
+            // threshold (then shifted <= thr - h, and replacing the index bits moves a key at most to `tb`)
+            float bound = top.key[KL - 1];
+            if (TWO_PASS) {
+                const float ts = thr - h;
+                const unsigned bits = __float_as_uint(ts);
+                const float tb = __uint_as_float(ts < 0.f ? (bits & keep_mask) : (bits | ~keep_mask));
+                bound = fmaxf(bound, tb);
+            }
+            tau_out[(size_t)b * N + i] = bound;
         }
     }
     ptx::tc_fence_before_sync();
@@ -250,7 +377,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_c, const float* __restrict
 template <int KL>
 __global__ void __launch_bounds__(256)
 knn_rerank_kernel(const float* __restrict__ xb /* raw rows xr */, const float* __restrict__ sq, const float* __restrict__ sqc,
-                  const float* __restrict__ cand, const unsigned* __restrict__ cmax_bits, int D, int N, int k, unsigned keep_mask, int idx_bits,
+                  const float* __restrict__ cand, const float* __restrict__ tau_in, const unsigned* __restrict__ cmax_bits, int D, int N, int k, unsigned keep_mask, int idx_bits,
                   int64_t* __restrict__ idx, float* __restrict__ val, int* __restrict__ fb_list, int* __restrict__ fb_count) {
     constexpr int CPL = KL / 32;                                       // candidates per lane
     constexpr int RS = kKP + 4;                                        // padded smem row stride
@@ -342,8 +469,7 @@ knn_rerank_kernel(const float* __restrict__ xb /* raw rows xr */, const float* _
     }
     // safety: best possible exact value of any non-candidate < k-th exact value of the candidates
     const float kth = __shfl_sync(kFull, pd[(k - 1) >> 5], (k - 1) & 31);
-    float tau = key[CPL - 1];                                          // keys arrive sorted: last one is the KL-th
-    tau = __shfl_sync(kFull, tau, 31);
+    const float tau = __ldg(tau_in + gi);                              // bound on the key of every score outside the list
     const float cmax2 = __uint_as_float(__ldg(cmax_bits + b));         // max_j |x_j - mu|^2
     const float rmax2 = __uint_as_float(__ldg(cmax_bits + gridDim.y + b));   // max_j |x_j|^2
     const float ni = sqrtf(__ldg(sqc + gi)), nmax = sqrtf(cmax2);
@@ -374,68 +500,81 @@ knn_rerank_kernel(const float* __restrict__ xb /* raw rows xr */, const float* _
     }
 }
 
-// ---- 4. exact fallback for flagged rows ----------------------------------------------------------------------------
-// One warp per flagged row (grid-stride over the device-side list): lane-distributed sorted list over all N.
-template <int SLOTS>
-__global__ void __launch_bounds__(256)
+// ---- 4. exact redo of flagged rows ------------------------------------------------------------------------------
+// One CTA per flagged row (grid-stride over the device-side list): all N canonical distances into shared memory
+// (candidate features read coalesced, the fma chain unrolled so its loads overlap), then k rounds of a block-wide
+// arg-max with the canonical order (larger value first, ties -> lower index).  Runs only when the list is short
+// (<= gate_max rows); a cloud that fails wholesale -- far from the origin relative to its extent, so that fp32
+// rounding decides the canonical order -- is instead redone by the all-FFMA kernels (knn.cu), gated the other way.
+constexpr int kFbThreads = 256;
+
+__global__ void __launch_bounds__(kFbThreads)
 knn_fallback_kernel(const float* __restrict__ x, const float* __restrict__ sq, int D, int N, int k,
-                    const int* __restrict__ fb_list, const int* __restrict__ fb_count,
+                    const int* __restrict__ fb_list, const int* __restrict__ fb_count, int gate_max,
                     int64_t* __restrict__ idx, float* __restrict__ val) {
-    const int lane = threadIdx.x & 31;
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    extern __shared__ __align__(16) float fsm[];
+    float* qs = fsm;                       // [64] query features
+    float* pd = fsm + 64;                  // [N]
+    __shared__ float wv[kFbThreads / 32];
+    __shared__ int wj[kFbThreads / 32];
     const int count = *fb_count;
-    const int tau_slot = (k - 1) >> 5, tau_lane = (k - 1) & 31;
-    for (int f = gw; f < count; f += nw) {
+    if (count > gate_max) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int f = blockIdx.x; f < count; f += gridDim.x) {
         const int gi = fb_list[f];
         const int b = gi / N, i = gi - b * N;
         const float* xb = x + (size_t)b * D * N;
         const float* sqb = sq + (size_t)b * N;
-        const float sq_i = __ldg(sqb + i);
-        float lv[SLOTS]; int li[SLOTS];
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) { lv[s] = -INFINITY; li[s] = 0x7fffffff; }
-        float tau = -INFINITY;
-        for (int j0 = 0; j0 < N; j0 += 32) {
-            const int j = j0 + lane;
+        __syncthreads();                                               // previous row fully written out
+        if (threadIdx.x < 64) qs[threadIdx.x] = threadIdx.x < D ? __ldg(xb + (size_t)threadIdx.x * N + i) : 0.f;
+        __syncthreads();
+        const float nsq_i = -__ldg(sqb + i);
+        for (int j = threadIdx.x; j < N; j += kFbThreads) {
             float acc = 0.f;
-            if (j < N) for (int d = 0; d < D; ++d) acc = __fmaf_rn(__ldg(xb + (size_t)d * N + i), __ldg(xb + (size_t)d * N + j), acc);
-            const float pd = j < N ? __fsub_rn(__fmaf_rn(2.f, acc, -sq_i), __ldg(sqb + j)) : -INFINITY;
-            unsigned bm = __ballot_sync(kFull, pd > tau);
-            while (bm) {
-                const int src = __ffs(bm) - 1;
-                bm &= bm - 1;
-                const float v = __shfl_sync(kFull, pd, src);
-                if (v > tau) {
-                    int pos = 0;
+            int d = 0;
+            for (; d + 8 <= D; d += 8) {
+                float c[8];
 #pragma unroll
-                    for (int s = 0; s < SLOTS; ++s) pos += __popc(__ballot_sync(kFull, lv[s] >= v));
+                for (int u = 0; u < 8; ++u) c[u] = __ldg(xb + (size_t)(d + u) * N + j);
 #pragma unroll
-                    for (int s = SLOTS - 1; s >= 0; --s) {
-                        float pv = __shfl_up_sync(kFull, lv[s], 1);
-                        int pi = __shfl_up_sync(kFull, li[s], 1);
-                        if (s > 0) {
-                            const float cv = __shfl_sync(kFull, lv[s - 1], 31);
-                            const int ci = __shfl_sync(kFull, li[s - 1], 31);
-                            if (lane == 0) { pv = cv; pi = ci; }
-                        }
-                        const int r = s * 32 + lane;
-                        if (r > pos) { lv[s] = pv; li[s] = pi; }
-                        else if (r == pos) { lv[s] = v; li[s] = j0 + src; }
-                    }
-                    float tv = lv[0];
+                for (int u = 0; u < 8; ++u) acc = __fmaf_rn(qs[d + u], c[u], acc);
+            }
+            for (; d < D; ++d) acc = __fmaf_rn(qs[d], __ldg(xb + (size_t)d * N + j), acc);
+            pd[j] = __fsub_rn(__fmaf_rn(2.f, acc, nsq_i), __ldg(sqb + j));
+        }
+        __syncthreads();
+        for (int r = 0; r < k; ++r) {
+            float bv = -INFINITY;
+            int bj = 0x7fffffff;
+            for (int j = threadIdx.x; j < N; j += kFbThreads) {        // ascending j: strict '>' keeps the lower index
+                const float v = pd[j];
+                if (v > bv) { bv = v; bj = j; }
+            }
 #pragma unroll
-                    for (int s = 1; s < SLOTS; ++s) if (s == tau_slot) tv = lv[s];
-                    tau = __shfl_sync(kFull, tv, tau_lane);
+            for (int o = 16; o > 0; o >>= 1) {
+                const float ov = __shfl_xor_sync(kFull, bv, o);
+                const int oj = __shfl_xor_sync(kFull, bj, o);
+                if (ov > bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
+            }
+            if (lane == 0) { wv[warp] = bv; wj[warp] = bj; }
+            __syncthreads();
+            if (warp == 0) {
+                bv = lane < kFbThreads / 32 ? wv[lane] : -INFINITY;
+                bj = lane < kFbThreads / 32 ? wj[lane] : 0x7fffffff;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(kFull, bv, o);
+                    const int oj = __shfl_xor_sync(kFull, bj, o);
+                    if (ov > bv || (ov == bv && oj < bj)) { bv = ov; bj = oj; }
+                }
+                if (lane == 0) {
+                    const int jj = bj < N ? bj : i;
+                    idx[(size_t)gi * k + r] = jj;
+                    if (val) val[(size_t)gi * k + r] = bv;
+                    if (bj < N) pd[bj] = -INFINITY;
                 }
             }
-        }
-#pragma unroll
-        for (int s = 0; s < SLOTS; ++s) {
-            const int r = s * 32 + lane;
-            if (r < k) {
-                idx[(size_t)gi * k + r] = li[s] < N ? li[s] : i;
-                if (val) val[(size_t)gi * k + r] = lv[s];
-            }
+            __syncthreads();
         }
     }
 }
@@ -457,12 +596,12 @@ static EncodeTiledFn encode_tiled() {
 }
 
 // rows x 64 fp32, row-major; box = 32 fp32 (128 B) x 128 rows, 128B swizzle
-static bool make_row_map(CUtensorMap* map, const float* base, size_t rows) {
+static bool make_row_map(CUtensorMap* map, const float* base, size_t rows, int box_rows) {
     EncodeTiledFn enc = encode_tiled();
     if (!enc) return false;
     const cuuint64_t gdim[2] = {kKP, rows};
     const cuuint64_t gstride[1] = {kKP * sizeof(float)};
-    const cuuint32_t box[2] = {32, kTM};
+    const cuuint32_t box[2] = {32, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -470,7 +609,7 @@ static bool make_row_map(CUtensorMap* map, const float* base, size_t rows) {
 }
 
 struct TcLayout {
-    float *xc, *xr, *sq, *sqc, *cand, *mu;
+    float *xc, *xr, *sq, *sqc, *cand, *tau, *mu;
     unsigned* cmax;
     int *fb_count, *fb_list;
     int n_zero;
@@ -487,6 +626,7 @@ static TcLayout tc_layout(void* ws, int B, int D, int N, int KL) {
     L.sq = reinterpret_cast<float*>(p + off);   off += align_up(rows * sizeof(float), 256);
     L.sqc = reinterpret_cast<float*>(p + off);  off += align_up(rows * sizeof(float), 256);
     L.cand = reinterpret_cast<float*>(p + off); off += align_up(rows * KL * sizeof(float), 256);
+    L.tau = reinterpret_cast<float*>(p + off);  off += align_up(rows * sizeof(float), 256);
     L.mu = reinterpret_cast<float*>(p + off);   off += align_up((size_t)B * D * sizeof(float), 256);
     L.cmax = reinterpret_cast<unsigned*>(p + off);  off += align_up((size_t)(2 * B + 1) * sizeof(unsigned), 256);
     L.fb_count = reinterpret_cast<int*>(L.cmax + 2 * B);              // [B] centred max, [B] raw max, counter
@@ -496,7 +636,7 @@ static TcLayout tc_layout(void* ws, int B, int D, int N, int KL) {
     return L;
 }
 
-bool knn_tc_applicable(int D, int N, int k) { return D >= 16 && D <= kKP - 1 && N >= kTN && N <= 4096 && k <= 48; }
+bool knn_tc_applicable(int D, int N, int k) { return D >= 16 && D <= kKP - 1 && N >= 128 && N <= 4096 && k <= 48; }
 
 static int tc_list_len(int k) { return k <= 24 ? 32 : 64; }
 
@@ -516,13 +656,22 @@ static int run_tc(const float* x, int B, int D, int N, int k, int64_t* idx, floa
     knn_pack_kernel<<<dim3((N + 31) / 32, B), 256, 0, st>>>(x, L.mu, D, N, L.xc, L.xr, L.sq, L.sqc, L.cmax);
     rc = check_launch("knn_pack_kernel");
     if (rc) return rc;
-    CUtensorMap map_c;
-    if (!make_row_map(&map_c, L.xc, rows)) return fail(HPCS_ERR_CUDA, "knn_tc: cuTensorMapEncodeTiled failed");
+    CUtensorMap map_a, map_b;                                          // same array: 128-row boxes for A, 64-row boxes for B
+    if (!make_row_map(&map_a, L.xc, rows, kTM) || !make_row_map(&map_b, L.xc, rows, kTN))
+        return fail(HPCS_ERR_CUDA, "knn_tc: cuTensorMapEncodeTiled failed");
     {
-        const size_t smem = 4 * (size_t)kAtomBytes + (size_t)kTcQueue * kTM * sizeof(float) + 7 * sizeof(uint64_t) + 16 + 1024;
-        auto kern = knn_tc_kernel<KL>;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<dim3((N + kTM - 1) / kTM, B), 160, smem, st>>>(map_c, L.sqc, N, keep_mask, L.cand);
+        const size_t smem = 2 * (size_t)kAtomBytes + (size_t)kStages * 2 * kAtomB + (size_t)kTcQueue * kTM * sizeof(float) +
+                            (6 + 2 * kStages) * sizeof(uint64_t) + 16 + 1024;
+        const dim3 grid((N + kTM - 1) / kTM, B);
+        if (KL == 32 && N >= 32 * kThrRank) {
+            auto kern = knn_tc_kernel<KL, true>;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            kern<<<grid, kTcThreads, smem, st>>>(map_a, map_b, L.sqc, N, keep_mask, L.cand, L.tau);
+        } else {
+            auto kern = knn_tc_kernel<KL, false>;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            kern<<<grid, kTcThreads, smem, st>>>(map_a, map_b, L.sqc, N, keep_mask, L.cand, L.tau);
+        }
         rc = check_launch("knn_tc_kernel");
         if (rc) return rc;
     }
@@ -530,18 +679,23 @@ static int run_tc(const float* x, int B, int D, int N, int k, int64_t* idx, floa
         const size_t smem = 8 * ((size_t)KL * (kKP + 4) + kKP) * sizeof(float);
         auto kern = knn_rerank_kernel<KL>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<dim3((N + 7) / 8, B), 256, smem, st>>>(L.xr, L.sq, L.sqc, L.cand, L.cmax, D, N, k, keep_mask, idx_bits, idx, val,
+        kern<<<dim3((N + 7) / 8, B), 256, smem, st>>>(L.xr, L.sq, L.sqc, L.cand, L.tau, L.cmax, D, N, k, keep_mask, idx_bits, idx, val,
                                                       L.fb_list, L.fb_count);
         rc = check_launch("knn_rerank_kernel");
         if (rc) return rc;
     }
-    const int blocks = 2 * sm_count();
-    if (k <= 32) knn_fallback_kernel<1><<<blocks, 256, 0, st>>>(x, L.sq, D, N, k, L.fb_list, L.fb_count, idx, val);
-    else knn_fallback_kernel<2><<<blocks, 256, 0, st>>>(x, L.sq, D, N, k, L.fb_list, L.fb_count, idx, val);
-    return check_launch("knn_fallback_kernel");
+    // rows that failed the safety test: a short list is redone row by row; a long one (> 1/16 of all rows) means the
+    // canonical order of whole clouds is decided by fp32 rounding, and the all-FFMA path redoes everything instead
+    const int gate = (int)(rows / 16);
+    {
+        const size_t smem = (64 + (size_t)N) * sizeof(float);
+        knn_fallback_kernel<<<4 * sm_count(), kFbThreads, smem, st>>>(x, L.sq, D, N, k, L.fb_list, L.fb_count, gate, idx, val);
+        rc = check_launch("knn_fallback_kernel");
+        if (rc) return rc;
+    }
+    return knn_ffma_gated(x, L.sq, B, D, N, k, idx, val, L.fb_count, gate, st);
 }
 
-// rows redone by the exact fallback in the last call that used this workspace (synchronises the stream)
 int knn_tc_fallback_rows(const void* ws, int B, int D, int N, int k, cudaStream_t st, int* out_host) {
     const TcLayout L = tc_layout(const_cast<void*>(ws), B, D, N, tc_list_len(k));
     cudaError_t e = cudaMemcpyAsync(out_host, L.fb_count, sizeof(int), cudaMemcpyDeviceToHost, st);
