@@ -138,13 +138,18 @@ hyp_triplet_kernel(const float* __restrict__ u, float* __restrict__ G, HypHeader
             in_ = (unsigned)min((unsigned long long)__ldg(ng + t), (unsigned long long)(n - 1));
         }
         float c_ap = 0.f, c_an = 0.f, c_pn = 0.f;
+        // the sampler emits all triplets of an anchor back to back (t_per_anchor of them), so consecutive slots
+        // usually share the anchor row: it is loaded once per run, and (below) its gradient is summed in registers
+        // and sent as ONE vector reduction per run instead of one per triplet
+        unsigned held_a = 0xffffffffu;
+        float4 va = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int r = 0; r < LPT; ++r) {
             const int slot = grp * LPT + r;       // triplet grp*LPT+r: its owner lane sits in this group
             const unsigned ra = __shfl_sync(kFull, ia, slot);
             const unsigned rp = __shfl_sync(kFull, ip, slot);
             const unsigned rn = __shfl_sync(kFull, in_, slot);
-            const float4 va = __ldg(u4 + (size_t)ra * LPT + sub);
+            if (ra != held_a) { va = __ldg(u4 + (size_t)ra * LPT + sub); held_a = ra; }
             const float4 vp = __ldg(u4 + (size_t)rp * LPT + sub);
             const float4 vn = __ldg(u4 + (size_t)rn * LPT + sub);
             float dap = dot4(va, vp), dan = dot4(va, vn), dpn = dot4(vp, vn);
@@ -166,6 +171,9 @@ hyp_triplet_kernel(const float* __restrict__ u, float* __restrict__ G, HypHeader
         if (keep) { loss_acc += tt.total; gs_acc += tt.g_s; kept_acc += 1; }
         if (MODE == 1) {
             const unsigned keep_mask = __ballot_sync(kFull, keep);
+            unsigned run_a = 0xffffffffu;             // anchor whose gradient is being summed in acc_a
+            float4 acc_a = make_float4(0.f, 0.f, 0.f, 0.f);
+            held_a = 0xffffffffu;
 #pragma unroll
             for (int r = 0; r < LPT; ++r) {
                 const int slot = grp * LPT + r;       // triplet grp*LPT+r: its owner lane sits in this group
@@ -176,14 +184,22 @@ hyp_triplet_kernel(const float* __restrict__ u, float* __restrict__ G, HypHeader
                 const float g_an = __shfl_sync(kFull, tt.g_an, slot);
                 const float g_pn = __shfl_sync(kFull, tt.g_pn, slot);
                 if ((keep_mask >> slot) & 1u) {
-                    const float4 va = __ldg(u4 + (size_t)ra * LPT + sub);
+                    if (ra != held_a) { va = __ldg(u4 + (size_t)ra * LPT + sub); held_a = ra; }
                     const float4 vp = __ldg(u4 + (size_t)rp * LPT + sub);
                     const float4 vn = __ldg(u4 + (size_t)rn * LPT + sub);
-                    atomicAdd(G4 + (size_t)ra * LPT + sub, axpby(g_ap, vp, g_an, vn));
+                    const float4 ga = axpby(g_ap, vp, g_an, vn);
+                    if (ra != run_a) {
+                        if (run_a != 0xffffffffu) atomicAdd(G4 + (size_t)run_a * LPT + sub, acc_a);
+                        run_a = ra;
+                        acc_a = ga;
+                    } else {
+                        acc_a.x += ga.x; acc_a.y += ga.y; acc_a.z += ga.z; acc_a.w += ga.w;
+                    }
                     atomicAdd(G4 + (size_t)rp * LPT + sub, axpby(g_ap, va, g_pn, vn));
                     atomicAdd(G4 + (size_t)rn * LPT + sub, axpby(g_an, va, g_pn, vp));
                 }
             }
+            if (run_a != 0xffffffffu) atomicAdd(G4 + (size_t)run_a * LPT + sub, acc_a);
         }
     }
     if (MODE != 2) {

@@ -500,6 +500,127 @@ knn_rerank_kernel(const float* __restrict__ xb /* raw rows xr */, const float* _
     }
 }
 
+// ---- 3b. exact re-rank, lists of 32 ---------------------------------------------------------------------------
+// The list arrives sorted by approximate key, and the TF32 error is about one neighbour spacing, so the exact
+// top k is almost always inside the first k + kExtra entries: only those rows are gathered (the gather is the
+// cost of this kernel: 256 bytes per candidate from L2).  The entries not evaluated are then bounded by the key of
+// the best one of them; if that bound is not safe the remaining entries are evaluated too, and only if the bound
+// of everything outside the list still fails does the row go to the exact redo.
+constexpr int kExtra = 6;
+
+__global__ void __launch_bounds__(256)
+knn_rerank32_kernel(const float* __restrict__ xr, const float* __restrict__ sq, const float* __restrict__ sqc,
+                    const float* __restrict__ cand, const float* __restrict__ tau_in, const unsigned* __restrict__ cmax_bits, int D, int N,
+                    int k, unsigned keep_mask, int idx_bits, int64_t* __restrict__ idx, float* __restrict__ val,
+                    int* __restrict__ fb_list, int* __restrict__ fb_count) {
+    constexpr int RS = kKP + 4;                                        // padded smem row stride
+    extern __shared__ __align__(16) float sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* rows = sm + (size_t)warp * (32 * RS + kKP);                 // [32][RS] candidate rows
+    float* qrow = rows + 32 * RS;                                      // [64] query row
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * 8 + warp;
+    if (i >= N) return;
+    const size_t gi = (size_t)b * N + i;
+    const float sq_i = __ldg(sq + gi);
+    const float key = __ldg(cand + gi * 32 + lane);
+    const unsigned jj = __float_as_uint(key) & ~keep_mask;
+    const int cj0 = (key == -INFINITY || jj >= (unsigned)N) ? -1 : (int)jj;
+    *reinterpret_cast<float2*>(qrow + 2 * lane) = __ldg(reinterpret_cast<const float2*>(xr + gi * kKP) + lane);
+    const int half = lane >> 4, q4 = lane & 15;
+
+    float pd0 = -INFINITY;                                             // exact value of this lane's candidate, once evaluated
+    auto evaluate = [&](int lo, int hi) {                              // candidates [lo, hi): gather rows, canonical chains
+        for (int r0 = lo; r0 < hi; r0 += 8) {                          // two rows per warp instruction (16 lanes x float4
+            float4 v[4];                                               // each), four such loads in flight
+            int rr[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                rr[u] = r0 + 2 * u + half;
+                const int src = __shfl_sync(kFull, cj0, min(rr[u], 31));
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (rr[u] < hi && src >= 0) v[u] = __ldg(reinterpret_cast<const float4*>(xr + ((size_t)b * N + src) * kKP) + q4);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (rr[u] < hi) *reinterpret_cast<float4*>(rows + (size_t)rr[u] * RS + 4 * q4) = v[u];
+        }
+        __syncwarp();
+        if (lane >= lo && lane < hi && cj0 >= 0) {
+            const float* cr = rows + (size_t)lane * RS;
+            float acc = 0.f;
+            for (int d = 0; d < D; d += 4) {                           // fma chain over d ascending
+                const float4 c4 = *reinterpret_cast<const float4*>(cr + d);
+                const float4 a4 = *reinterpret_cast<const float4*>(qrow + d);
+                acc = __fmaf_rn(a4.x, c4.x, acc);
+                if (d + 1 < D) acc = __fmaf_rn(a4.y, c4.y, acc);
+                if (d + 2 < D) acc = __fmaf_rn(a4.z, c4.z, acc);
+                if (d + 3 < D) acc = __fmaf_rn(a4.w, c4.w, acc);
+            }
+            const float sq_j = -2.f * cr[kKP - 1];                     // column 63 holds -|x_j|^2 / 2 exactly
+            pd0 = __fsub_rn(__fmaf_rn(2.f, acc, -sq_i), sq_j);
+        }
+        __syncwarp();
+    };
+    float ps;                                                          // sorted copies
+    int js;
+    auto sort32 = [&]() {                                              // descending value, ascending index on ties
+        ps = pd0;
+        js = (cj0 >= 0 && pd0 > -INFINITY) ? cj0 : 0x7fffffff;
+#pragma unroll
+        for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                const float ov = __shfl_xor_sync(kFull, ps, stride);
+                const int oj = __shfl_xor_sync(kFull, js, stride);
+                const bool lower = (lane & stride) == 0;
+                const bool desc = (lane & size) == 0;
+                const bool mine_first = ps > ov || (ps == ov && js < oj);
+                const bool keep = (lower == desc) ? mine_first : !mine_first;
+                if (!keep) { ps = ov; js = oj; }
+            }
+        }
+    };
+    const float tau = __ldg(tau_in + gi);                              // bound on the key of every score outside the list
+    const float cmax2 = __uint_as_float(__ldg(cmax_bits + b));         // max_j |x_j - mu|^2
+    const float rmax2 = __uint_as_float(__ldg(cmax_bits + gridDim.y + b));   // max_j |x_j|^2
+    const float ni = sqrtf(__ldg(sqc + gi)), nmax = sqrtf(cmax2);
+    const float rsum = sqrtf(sq_i) + sqrtf(rmax2);
+    // error bound: see knn_rerank_kernel
+    const float eps = 1.01f * (ni * nmax * (1.f / 512.f + 1.f / 65536.f) + cmax2 * (1.f / 2048.f) +
+                               (ni + nmax) * (ni + nmax) * (1.f / 1048576.f) +
+                               (float)(D + 8) * rsum * rsum * (1.f / 16777216.f));
+    const float qscale = exp2f((float)(idx_bits - 22));
+    auto safe_against = [&](float bound) {                             // bound: largest key of anything not evaluated
+        const float kth = __shfl_sync(kFull, ps, k - 1);
+        return bound == -INFINITY ? kth > -INFINITY : 0.5f * kth > bound + fabsf(bound) * qscale + eps;
+    };
+
+    const int ne = min(32, k + kExtra);
+    evaluate(0, ne);
+    sort32();
+    bool ok = true;
+    if (ne < 32) {
+        const float next_key = __shfl_sync(kFull, key, ne);            // keys are sorted: the best entry not evaluated
+        ok = safe_against(fmaxf(next_key, tau));
+        if (!ok) {                                                     // warp-uniform
+            evaluate(ne, 32);
+            sort32();
+            ok = safe_against(tau);
+        }
+    } else {
+        ok = safe_against(tau);
+    }
+    if (!ok) {
+        if (lane == 0) fb_list[atomicAdd(fb_count, 1)] = (int)gi;
+        return;
+    }
+    if (lane < k) {
+        idx[gi * k + lane] = js;
+        if (val) val[gi * k + lane] = ps;
+    }
+}
+
 // ---- 4. exact redo of flagged rows ------------------------------------------------------------------------------
 // One CTA per flagged row (grid-stride over the device-side list): all N canonical distances into shared memory
 // (candidate features read coalesced, the fma chain unrolled so its loads overlap), then k rounds of a block-wide
@@ -677,10 +798,16 @@ static int run_tc(const float* x, int B, int D, int N, int k, int64_t* idx, floa
     }
     {
         const size_t smem = 8 * ((size_t)KL * (kKP + 4) + kKP) * sizeof(float);
-        auto kern = knn_rerank_kernel<KL>;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<dim3((N + 7) / 8, B), 256, smem, st>>>(L.xr, L.sq, L.sqc, L.cand, L.tau, L.cmax, D, N, k, keep_mask, idx_bits, idx, val,
-                                                      L.fb_list, L.fb_count);
+        if (KL == 32) {
+            cudaFuncSetAttribute(knn_rerank32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            knn_rerank32_kernel<<<dim3((N + 7) / 8, B), 256, smem, st>>>(L.xr, L.sq, L.sqc, L.cand, L.tau, L.cmax, D, N, k, keep_mask, idx_bits,
+                                                                         idx, val, L.fb_list, L.fb_count);
+        } else {
+            auto kern = knn_rerank_kernel<KL>;
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            kern<<<dim3((N + 7) / 8, B), 256, smem, st>>>(L.xr, L.sq, L.sqc, L.cand, L.tau, L.cmax, D, N, k, keep_mask, idx_bits, idx, val,
+                                                          L.fb_list, L.fb_count);
+        }
         rc = check_launch("knn_rerank_kernel");
         if (rc) return rc;
     }
