@@ -38,6 +38,8 @@ SIGNATURES = {
     "hpcs_edge_feat_bwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _Z, _P]),
     "hpcs_hyp_triplet_workspace_bytes": (_Z, [_L, _I]),
     "hpcs_hyp_triplet_fwd_f32": (_I, [_P, _L, _I, _P, _P, _P, _L, _P, _F, _I, _F, _I, _P, _P, _P, _Z, _P]),
+    "hpcs_hyp_triplet_fwd_i32_f32": (_I, [_P, _L, _I, _P, _P, _P, _L, _P, _F, _I, _F, _I, _P, _P, _P, _Z, _P]),
+    "hpcs_triplet_filter_i32_f32": (_I, [_P, _L, _I, _P, _P, _P, _L, _I, _F, _P, _P, _Z, _P]),
     "hpcs_hyp_triplet_bwd_f32": (_I, [_P, _P, _L, _I, _P, _P, _Z, _P, _P, _P]),
     "hpcs_triplet_filter_f32": (_I, [_P, _L, _I, _P, _P, _P, _L, _I, _F, _P, _P, _Z, _P]),
     "hpcs_hyp_lca_fwd_f32": (_I, [_P, _P, _L, _I, _I, _P, _P]),

@@ -72,7 +72,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 if proc.returncode != 0:
                     raise RuntimeError(f"nvcc failed on {cmd[-3]}")
     if jobs or not os.path.exists(LIB_PATH):
-        proc = subprocess.run([_nvcc(), "-shared", *objs, "-o", LIB_PATH], capture_output=True, text=True)
+        proc = subprocess.run([_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", *objs, "-o", LIB_PATH],
+                              capture_output=True, text=True)
         if proc.returncode != 0:
             sys.stderr.write(proc.stdout + proc.stderr)
             raise RuntimeError("link of libhpcs_b200.so failed")

@@ -110,10 +110,10 @@ __device__ __forceinline__ float4 axpby(float s, const float4 a, float t, const 
 
 // ---- main pass ---------------------------------------------------------------------------------------
 // MODE 0: loss only, 1: loss + gradient accumulation, 2: filter flags only.
-template <int LPT, int MODE>
+template <int LPT, int MODE, typename IdxT>
 __global__ void __launch_bounds__(256)
 hyp_triplet_kernel(const float* __restrict__ u, float* __restrict__ G, HypHeader* __restrict__ hdr,
-                   const int64_t* __restrict__ a, const int64_t* __restrict__ p, const int64_t* __restrict__ ng,
+                   const IdxT* __restrict__ a, const IdxT* __restrict__ p, const IdxT* __restrict__ ng,
                    int64_t T0, int64_t n, float inv_temp, int filter_mode, float margin,
                    uint8_t* __restrict__ keep_out) {
     const int lane = threadIdx.x & 31;
@@ -133,9 +133,9 @@ hyp_triplet_kernel(const float* __restrict__ u, float* __restrict__ G, HypHeader
         // indices are clamped so a bad triplet cannot fault; the reference would raise instead
         unsigned ia = 0, ip = 0, in_ = 0;
         if (valid) {
-            ia = (unsigned)min((unsigned long long)__ldg(a + t), (unsigned long long)(n - 1));
-            ip = (unsigned)min((unsigned long long)__ldg(p + t), (unsigned long long)(n - 1));
-            in_ = (unsigned)min((unsigned long long)__ldg(ng + t), (unsigned long long)(n - 1));
+            ia = (unsigned)min((unsigned long long)(long long)__ldg(a + t), (unsigned long long)(n - 1));
+            ip = (unsigned)min((unsigned long long)(long long)__ldg(p + t), (unsigned long long)(n - 1));
+            in_ = (unsigned)min((unsigned long long)(long long)__ldg(ng + t), (unsigned long long)(n - 1));
         }
         float c_ap = 0.f, c_an = 0.f, c_pn = 0.f;
         // the sampler emits all triplets of an anchor back to back (t_per_anchor of them), so consecutive slots
@@ -280,8 +280,8 @@ static int run_prep(const float* x, int64_t n, int D, const float* scale, const 
     return check_launch("hyp_prep_kernel");
 }
 
-template <int LPT>
-static int run_triplets(int mode, const HypLayout& L, const int64_t* a, const int64_t* p, const int64_t* ng,
+template <int LPT, typename IdxT>
+static int run_triplets(int mode, const HypLayout& L, const IdxT* a, const IdxT* p, const IdxT* ng,
                         int64_t T0, int64_t n, float temperature, int filter_mode, float margin, uint8_t* keep,
                         cudaStream_t st) {
     if (T0 <= 0) return HPCS_OK;
@@ -290,9 +290,9 @@ static int run_triplets(int mode, const HypLayout& L, const int64_t* a, const in
     const int64_t cap = (int64_t)8 * sm_count();
     if (blocks > cap) blocks = cap;
     const float inv_temp = 1.f / temperature;
-    if (mode == 0) hyp_triplet_kernel<LPT, 0><<<(int)blocks, 256, 0, st>>>(L.u, L.G, L.hdr, a, p, ng, T0, n, inv_temp, filter_mode, margin, keep);
-    else if (mode == 1) hyp_triplet_kernel<LPT, 1><<<(int)blocks, 256, 0, st>>>(L.u, L.G, L.hdr, a, p, ng, T0, n, inv_temp, filter_mode, margin, keep);
-    else hyp_triplet_kernel<LPT, 2><<<(int)blocks, 256, 0, st>>>(L.u, L.G, L.hdr, a, p, ng, T0, n, inv_temp, filter_mode, margin, keep);
+    if (mode == 0) hyp_triplet_kernel<LPT, 0, IdxT><<<(int)blocks, 256, 0, st>>>(L.u, L.G, L.hdr, a, p, ng, T0, n, inv_temp, filter_mode, margin, keep);
+    else if (mode == 1) hyp_triplet_kernel<LPT, 1, IdxT><<<(int)blocks, 256, 0, st>>>(L.u, L.G, L.hdr, a, p, ng, T0, n, inv_temp, filter_mode, margin, keep);
+    else hyp_triplet_kernel<LPT, 2, IdxT><<<(int)blocks, 256, 0, st>>>(L.u, L.G, L.hdr, a, p, ng, T0, n, inv_temp, filter_mode, margin, keep);
     return check_launch("hyp_triplet_kernel");
 }
 
@@ -315,11 +315,13 @@ size_t hpcs_hyp_triplet_workspace_bytes(int64_t n, int D) {
     return hpcs::hyp_layout(nullptr, n, D).bytes;
 }
 
-int hpcs_hyp_triplet_fwd_f32(const float* x, int64_t n, int D, const int64_t* a, const int64_t* p,
-                             const int64_t* ng, int64_t T0, const float* scale, float temperature,
-                             int filter_mode, float margin, int need_grad, float* loss, int64_t* kept,
-                             void* ws, size_t ws_bytes, void* stream) {
-    using namespace hpcs;
+}  // extern "C"
+
+namespace hpcs {
+template <typename IdxT>
+static int triplet_fwd(const float* x, int64_t n, int D, const IdxT* a, const IdxT* p, const IdxT* ng, int64_t T0,
+                       const float* scale, float temperature, int filter_mode, float margin, int need_grad, float* loss,
+                       int64_t* kept, void* ws, size_t ws_bytes, void* stream) {
     if (!x || !scale || !loss || !kept || !ws || (T0 > 0 && (!a || !p || !ng))) return fail(HPCS_ERR_ARG, "hyp_triplet_fwd: null pointer");
     if (n <= 0 || D <= 0 || D > 128 || T0 < 0 || n > 0x7fffffffLL) return fail(HPCS_ERR_ARG, "hyp_triplet_fwd: bad shape n=%lld D=%d", (long long)n, D);
     if (!(temperature > 0.f)) return fail(HPCS_ERR_ARG, "hyp_triplet_fwd: temperature must be > 0");
@@ -331,10 +333,45 @@ int hpcs_hyp_triplet_fwd_f32(const float* x, int64_t n, int D, const int64_t* a,
     HPCS_LPT_SWITCH(DP, rc = run_prep<LPT>(x, n, D, scale, L, st));
     if (rc) return rc;
     if (need_grad) cudaMemsetAsync(L.G, 0, (size_t)n * DP * sizeof(float), st);
-    HPCS_LPT_SWITCH(DP, rc = run_triplets<LPT>(need_grad ? 1 : 0, L, a, p, ng, T0, n, temperature, filter_mode, margin, nullptr, st));
+    HPCS_LPT_SWITCH(DP, rc = (run_triplets<LPT, IdxT>(need_grad ? 1 : 0, L, a, p, ng, T0, n, temperature, filter_mode, margin, nullptr, st)));
     if (rc) return rc;
     hyp_finalize_kernel<<<1, 32, 0, st>>>(L.hdr, n, loss, kept);
     return check_launch("hyp_finalize_kernel");
+}
+
+template <typename IdxT>
+static int triplet_filter(const float* x, int64_t n, int D, const IdxT* a, const IdxT* p, const IdxT* ng, int64_t T0,
+                          int filter_mode, float margin, uint8_t* keep, void* ws, size_t ws_bytes, void* stream) {
+    if (!x || !ws || (T0 > 0 && (!a || !p || !ng || !keep))) return fail(HPCS_ERR_ARG, "triplet_filter: null pointer");
+    if (n <= 0 || D <= 0 || D > 128 || T0 < 0 || n > 0x7fffffffLL) return fail(HPCS_ERR_ARG, "triplet_filter: bad shape");
+    const HypLayout L = hyp_layout(ws, n, D);
+    if (ws_bytes < L.bytes) return fail(HPCS_ERR_WORKSPACE, "triplet_filter: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    const int DP = padded_dim(D);
+    int rc = HPCS_OK;
+    HPCS_LPT_SWITCH(DP, rc = run_prep<LPT>(x, n, D, nullptr /* the filter does not depend on the scale */, L, st));
+    if (rc) return rc;
+    HPCS_LPT_SWITCH(DP, rc = (run_triplets<LPT, IdxT>(2, L, a, p, ng, T0, n, 1.0f, filter_mode, margin, keep, st)));
+    return rc;
+}
+}  // namespace hpcs
+
+extern "C" {
+
+int hpcs_hyp_triplet_fwd_f32(const float* x, int64_t n, int D, const int64_t* a, const int64_t* p,
+                             const int64_t* ng, int64_t T0, const float* scale, float temperature,
+                             int filter_mode, float margin, int need_grad, float* loss, int64_t* kept,
+                             void* ws, size_t ws_bytes, void* stream) {
+    return hpcs::triplet_fwd<int64_t>(x, n, D, a, p, ng, T0, scale, temperature, filter_mode, margin, need_grad, loss, kept, ws,
+                                      ws_bytes, stream);
+}
+
+int hpcs_hyp_triplet_fwd_i32_f32(const float* x, int64_t n, int D, const int32_t* a, const int32_t* p,
+                                 const int32_t* ng, int64_t T0, const float* scale, float temperature,
+                                 int filter_mode, float margin, int need_grad, float* loss, int64_t* kept,
+                                 void* ws, size_t ws_bytes, void* stream) {
+    return hpcs::triplet_fwd<int32_t>(x, n, D, a, p, ng, T0, scale, temperature, filter_mode, margin, need_grad, loss, kept, ws,
+                                      ws_bytes, stream);
 }
 
 int hpcs_hyp_triplet_bwd_f32(const float* gloss, const float* x, int64_t n, int D, const float* scale,
@@ -362,18 +399,13 @@ int hpcs_hyp_triplet_bwd_f32(const float* gloss, const float* x, int64_t n, int 
 int hpcs_triplet_filter_f32(const float* x, int64_t n, int D, const int64_t* a, const int64_t* p,
                             const int64_t* ng, int64_t T0, int filter_mode, float margin, uint8_t* keep,
                             void* ws, size_t ws_bytes, void* stream) {
-    using namespace hpcs;
-    if (!x || !ws || (T0 > 0 && (!a || !p || !ng || !keep))) return fail(HPCS_ERR_ARG, "triplet_filter: null pointer");
-    if (n <= 0 || D <= 0 || D > 128 || T0 < 0 || n > 0x7fffffffLL) return fail(HPCS_ERR_ARG, "triplet_filter: bad shape");
-    const HypLayout L = hyp_layout(ws, n, D);
-    if (ws_bytes < L.bytes) return fail(HPCS_ERR_WORKSPACE, "triplet_filter: workspace too small");
-    cudaStream_t st = as_stream(stream);
-    const int DP = padded_dim(D);
-    int rc = HPCS_OK;
-    HPCS_LPT_SWITCH(DP, rc = run_prep<LPT>(x, n, D, nullptr /* the filter does not depend on the scale */, L, st));
-    if (rc) return rc;
-    HPCS_LPT_SWITCH(DP, rc = run_triplets<LPT>(2, L, a, p, ng, T0, n, 1.0f, filter_mode, margin, keep, st));
-    return rc;
+    return hpcs::triplet_filter<int64_t>(x, n, D, a, p, ng, T0, filter_mode, margin, keep, ws, ws_bytes, stream);
+}
+
+int hpcs_triplet_filter_i32_f32(const float* x, int64_t n, int D, const int32_t* a, const int32_t* p,
+                                const int32_t* ng, int64_t T0, int filter_mode, float margin, uint8_t* keep,
+                                void* ws, size_t ws_bytes, void* stream) {
+    return hpcs::triplet_filter<int32_t>(x, n, D, a, p, ng, T0, filter_mode, margin, keep, ws, ws_bytes, stream);
 }
 
 }  // extern "C"

@@ -95,7 +95,15 @@ class CosineSimilarity(torch.nn.Module):
 # fused objective
 # ------------------------------------------------------------------------------------------------
 def _as_index(t: torch.Tensor, dev: torch.device) -> torch.Tensor:
-    return t.to(device=dev, dtype=torch.int64).contiguous()
+    """int64 (what the reference sampler produces) or int32 (half the upload) index tensor on `dev`."""
+    dtype = torch.int32 if t.dtype == torch.int32 else torch.int64
+    return t.to(device=dev, dtype=dtype).contiguous()
+
+
+def _same_index_dtype(a, p, n):
+    if a.dtype != p.dtype or a.dtype != n.dtype:
+        a, p, n = a.long(), p.long(), n.long()
+    return a, p, n
 
 
 def filter_triplets(x: torch.Tensor, a: torch.Tensor, p: torch.Tensor, n: torch.Tensor, margin: float = 0.0,
@@ -105,15 +113,16 @@ def filter_triplets(x: torch.Tensor, a: torch.Tensor, p: torch.Tensor, n: torch.
     lib = _lib.load()
     xc = x.detach().contiguous().float()
     nrow, D = xc.shape
-    a, p, n = _as_index(a, dev), _as_index(p, dev), _as_index(n, dev)
+    a, p, n = _same_index_dtype(_as_index(a, dev), _as_index(p, dev), _as_index(n, dev))
     T0 = a.numel()
     keep = torch.empty(T0, dtype=torch.uint8, device=dev)
+    entry = lib.hpcs_triplet_filter_i32_f32 if a.dtype == torch.int32 else lib.hpcs_triplet_filter_f32
     ws = _lib.workspace(lib.hpcs_hyp_triplet_workspace_bytes(nrow, D), dev)
     mode = FILTER_MODES.get(type_of_triplets, _BELOW_MARGIN)
     with torch.cuda.device(dev):
-        _lib.check(lib.hpcs_triplet_filter_f32(xc.data_ptr(), nrow, D, a.data_ptr(), p.data_ptr(), n.data_ptr(), T0,
-                                               mode, float(margin), keep.data_ptr(), ws.data_ptr(), ws.numel(),
-                                               _lib.stream_ptr(dev)), "hpcs_triplet_filter_f32")
+        _lib.check(entry(xc.data_ptr(), nrow, D, a.data_ptr(), p.data_ptr(), n.data_ptr(), T0,
+                         mode, float(margin), keep.data_ptr(), ws.data_ptr(), ws.numel(),
+                         _lib.stream_ptr(dev)), "hpcs_triplet_filter_f32")
     return keep.bool()
 
 
@@ -147,11 +156,12 @@ class _HypTripletLoss(torch.autograd.Function):
         loss = torch.empty(1, dtype=torch.float32, device=dev)
         kept = torch.empty(1, dtype=torch.int64, device=dev)
         ws = _lib.workspace(lib.hpcs_hyp_triplet_workspace_bytes(nrow, D), dev)
+        entry = lib.hpcs_hyp_triplet_fwd_i32_f32 if a.dtype == torch.int32 else lib.hpcs_hyp_triplet_fwd_f32
         with torch.cuda.device(dev):
-            _lib.check(lib.hpcs_hyp_triplet_fwd_f32(x.data_ptr(), nrow, D, a.data_ptr(), p.data_ptr(), n.data_ptr(), T0,
-                                                    scale.data_ptr(), float(temperature), int(filter_mode),
-                                                    float(margin), int(need_grad), loss.data_ptr(), kept.data_ptr(),
-                                                    ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev)),
+            _lib.check(entry(x.data_ptr(), nrow, D, a.data_ptr(), p.data_ptr(), n.data_ptr(), T0,
+                             scale.data_ptr(), float(temperature), int(filter_mode),
+                             float(margin), int(need_grad), loss.data_ptr(), kept.data_ptr(),
+                             ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev)),
                        "hpcs_hyp_triplet_fwd_f32")
         ctx.save_for_backward(x, scale, ws)
         ctx.mark_non_differentiable(kept)
@@ -180,7 +190,7 @@ def hyp_triplet_loss(x: torch.Tensor, triplets, scale: torch.Tensor, temperature
     dev = _lib.require_cuda(x, scale)
     if x.dtype != torch.float32 or x.dim() != 2:
         raise TypeError("hyp_triplet_loss expects x[n,D] float32")
-    a, p, n = (_as_index(t, dev) for t in triplets)
+    a, p, n = _same_index_dtype(*(_as_index(t, dev) for t in triplets))
     sc = scale.reshape(-1)
     if sc.numel() != 1 or sc.dtype != torch.float32:
         raise TypeError("scale must hold one float32")

@@ -92,12 +92,20 @@ int hpcs_hyp_triplet_fwd_f32(const float* x, int64_t n, int D, const int64_t* a,
                              const int64_t* ng, int64_t T0, const float* scale, float temperature,
                              int filter_mode, float margin, int need_grad, float* loss, int64_t* kept,
                              void* ws, size_t ws_bytes, void* stream);
+/* same, triplet indices as int32 (the reference samples int64 on the host; int32 halves the 39 MB/step upload) */
+int hpcs_hyp_triplet_fwd_i32_f32(const float* x, int64_t n, int D, const int32_t* a, const int32_t* p,
+                                 const int32_t* ng, int64_t T0, const float* scale, float temperature,
+                                 int filter_mode, float margin, int need_grad, float* loss, int64_t* kept,
+                                 void* ws, size_t ws_bytes, void* stream);
 int hpcs_hyp_triplet_bwd_f32(const float* gloss, const float* x, int64_t n, int D, const float* scale,
                              const void* ws, size_t ws_bytes, float* gx, float* gscale, void* stream);
 /* the miner's filter alone: keep[T0] uint8 (1 = triplet survives). */
 int hpcs_triplet_filter_f32(const float* x, int64_t n, int D, const int64_t* a, const int64_t* p,
                             const int64_t* ng, int64_t T0, int filter_mode, float margin, uint8_t* keep,
                             void* ws, size_t ws_bytes, void* stream);
+int hpcs_triplet_filter_i32_f32(const float* x, int64_t n, int D, const int32_t* a, const int32_t* p,
+                                const int32_t* ng, int64_t T0, int filter_mode, float margin, uint8_t* keep,
+                                void* ws, size_t ws_bytes, void* stream);
 
 /* hyp_lca(a, b, return_coord)         hpcs/distances/lca.py:37-52 (general, unequal norms)
  *   a,b[T,D] fp32 -> out[T,D] (return_coord) or out[T,1] = 2 artanh(|proj|); scalar chain in fp64. */

@@ -455,3 +455,27 @@ def test_linkage_full_size_valid_dendrogram(hb):
         ref = linkage(leaves[0].cpu().numpy(), method=method, metric="cosine")
         _check_Z(Zc[0], ref)
         assert np.array_equal(fcluster(Zc[0], 6, "maxclust"), fcluster(ref, 6, "maxclust"))
+
+
+def test_triplet_loss_int32_indices(hb):
+    """int32 triplet indices (half the host->device bytes) give the same bits as the reference's int64."""
+    gen = torch.Generator().manual_seed(5)
+    n, D = 4096, 32
+    emb = dev(O.expmap0(torch.randn(n, D, generator=gen)))
+    labels = torch.randint(0, 6, (n,), generator=gen)
+    torch.manual_seed(3)
+    trip = hb.get_balanced_random_triplet_indices(labels, t_per_anchor=20, fraction=0.0)
+    sc = torch.tensor([1e-3], device=emb.device)
+    outs = []
+    for cast in (torch.int64, torch.int32):
+        e = emb.clone().requires_grad_(True)
+        s_ = sc.clone().requires_grad_(True)
+        loss, kept = hb.hyp_triplet_loss(e, tuple(t.to(cast) for t in trip), s_, 0.05, "easy", 0.0, return_kept=True)
+        ge, gs = torch.autograd.grad(loss, (e, s_))
+        outs.append((loss, kept, ge, gs))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert rel_err(outs[1][2], outs[0][2]) < 1e-6 and rel_err(outs[1][3], outs[0][3]) < 1e-6    # atomics: order differs
+    from hpcs_b200.loss import filter_triplets
+    k64 = filter_triplets(emb, *trip, 0.0, "easy")
+    k32 = filter_triplets(emb, *(t.to(torch.int32) for t in trip), 0.0, "easy")
+    assert torch.equal(k64, k32)
