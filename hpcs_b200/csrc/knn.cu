@@ -182,19 +182,26 @@ knn_kernel(const float* __restrict__ x, const float* __restrict__ sq, int D, int
 // [D][TC] (+ their norms) through shared memory; a warp reads 4 consecutive candidates of one
 // feature with a single broadcast LDS.128, so the inner loop is 4 independent canonical fma chains.
 // Selection: RowSelector (knn_rows.cuh).  Same canonical arithmetic and order as knn_kernel.
-template <int D, int K, int THREADS, int TC>
-__global__ void __launch_bounds__(THREADS)
+// SPLIT > 1: SPLIT threads share one query row, each scanning every SPLIT-th 32-candidate chunk of a tile (the part
+// index is warp-uniform, so the broadcast loads stay broadcasts); their sorted lists are merged at the end with
+// the canonical order.  For D = 3 the selection, not the arithmetic, is the cost, and one thread per row leaves
+// only 7 warps per SM at B*N = 32768.  Kept as an option: each part re-fills its own top-K, and on B200 that extra
+// insertion work outweighs the added warps (see launch_knn_rows), so SPLIT = 1 is what runs.
+template <int D, int K, int ROWS, int TC, int SPLIT>
+__global__ void __launch_bounds__(ROWS * SPLIT)
 knn_rows_kernel(const float* __restrict__ x, const float* __restrict__ sq, int N, int k,
                 int64_t* __restrict__ idx, float* __restrict__ val, const int* __restrict__ gate, int gate_min) {
     constexpr int QCAP = kRowQueue;
+    constexpr int THREADS = ROWS * SPLIT;
     if (gate && *gate <= gate_min) return;                // whole-grid early exit (tensor-core path: nothing to redo)
     extern __shared__ __align__(16) float smem[];
     float* cs = smem;                                  // [D][TC]
     float* sqc = cs + D * TC;                          // [TC]
-    float* qv = sqc + TC;                              // [QCAP][THREADS]
+    float* qv = sqc + TC;                              // [QCAP][THREADS]   (after the scan: [SPLIT][K][ROWS] merge lists)
     int* qj = reinterpret_cast<int*>(qv + QCAP * THREADS);
     const int b = blockIdx.y;
-    const int i = blockIdx.x * THREADS + threadIdx.x;  // query row (may be >= N in the last CTA)
+    const int r_in = threadIdx.x % ROWS, part = threadIdx.x / ROWS;    // ROWS is a multiple of 32: part is warp-uniform
+    const int i = blockIdx.x * ROWS + r_in;            // query row (may be >= N in the last CTA)
     const float* xb = x + (size_t)b * D * N;
     const float* sqb = sq + (size_t)b * N;
     const int iq = i < N ? i : N - 1;                  // idle rows shadow the last one (keeps warps uniform)
@@ -216,7 +223,7 @@ knn_rows_kernel(const float* __restrict__ x, const float* __restrict__ sq, int N
         for (int c = threadIdx.x; c < TC; c += THREADS) sqc[c] = j0 + c < N ? __ldg(sqb + j0 + c) : 0.f;
         __syncthreads();
         const int lim = min(TC, N - j0);
-        for (int c0 = 0; c0 < lim; c0 += 32) {
+        for (int c0 = 32 * part; c0 < lim; c0 += 32 * SPLIT) {
             sel.maybe_flush(32);
 #pragma unroll
             for (int c = c0; c < c0 + 32; c += 4) {
@@ -243,6 +250,49 @@ knn_rows_kernel(const float* __restrict__ x, const float* __restrict__ sq, int N
         }
     }
     sel.flush();
+    if (SPLIT > 1) {
+        // every part publishes its sorted list; part 0 merges the SPLIT heads K times (larger value first, equal
+        // values -> lower index: the canonical order, independent of which part saw a candidate)
+        __syncthreads();                               // FIFOs are dead: reuse them
+        float* mv = qv;                                // [SPLIT][K][ROWS]
+        int* mj = qj;
+#pragma unroll
+        for (int m = 0; m < K; ++m) {
+            mv[(part * K + m) * ROWS + r_in] = sel.top.val[m];
+            mj[(part * K + m) * ROWS + r_in] = sel.top.idx[m];
+        }
+        __syncthreads();
+        if (part != 0 || i >= N) return;
+        int head[SPLIT];
+        float hv[SPLIT];
+        int hj[SPLIT];
+#pragma unroll
+        for (int s = 0; s < SPLIT; ++s) { head[s] = 0; hv[s] = mv[(s * K) * ROWS + r_in]; hj[s] = mj[(s * K) * ROWS + r_in]; }
+        int64_t* oi = idx + ((size_t)b * N + i) * k;
+        float* ov = val ? val + ((size_t)b * N + i) * k : nullptr;
+        for (int m = 0; m < k; ++m) {
+            int best = 0;
+#pragma unroll
+            for (int s = 1; s < SPLIT; ++s)
+                if (hv[s] > hv[best] || (hv[s] == hv[best] && hj[s] < hj[best])) best = s;
+            float bv = hv[0];
+            int bj = hj[0];
+#pragma unroll
+            for (int s = 1; s < SPLIT; ++s) if (s == best) { bv = hv[s]; bj = hj[s]; }
+            oi[m] = bj < N ? bj : i;
+            if (ov) ov[m] = bv;
+#pragma unroll
+            for (int s = 0; s < SPLIT; ++s) {
+                if (s == best) {
+                    ++head[s];
+                    const bool more = head[s] < K;
+                    hv[s] = more ? mv[(s * K + head[s]) * ROWS + r_in] : -INFINITY;
+                    hj[s] = more ? mj[(s * K + head[s]) * ROWS + r_in] : 0x7fffffff;
+                }
+            }
+        }
+        return;
+    }
     if (i < N) {
         int64_t* oi = idx + ((size_t)b * N + i) * k;
         float* ov = val ? val + ((size_t)b * N + i) * k : nullptr;
@@ -260,12 +310,14 @@ knn_rows_kernel(const float* __restrict__ x, const float* __restrict__ sq, int N
 template <int D, int K>
 static int launch_knn_rows(const float* x, const float* sq, int B, int N, int k, int64_t* idx, float* val,
                            const int* gate, int gate_min, cudaStream_t st) {
-    constexpr int THREADS = 64;
+    constexpr int ROWS = 64;
+    constexpr int SPLIT = 1;            // measured at B=32, N=1024, D=3: SPLIT 1 / 2 / 4 -> 68 / 81 / 116 us (the extra inserts cost more than the occupancy gains)
     constexpr int TC = D <= 4 ? 512 : 128;
-    constexpr size_t smem = ((size_t)D * TC + TC + 2 * kRowQueue * THREADS) * sizeof(float);
-    auto kern = knn_rows_kernel<D, K, THREADS, TC>;
+    constexpr size_t fifo = 2 * (size_t)kRowQueue * ROWS * SPLIT, merge = 2 * (size_t)SPLIT * K * ROWS;
+    constexpr size_t smem = ((size_t)D * TC + TC + (fifo > merge ? fifo : merge)) * sizeof(float);
+    auto kern = knn_rows_kernel<D, K, ROWS, TC, SPLIT>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<dim3((N + THREADS - 1) / THREADS, B), THREADS, smem, st>>>(x, sq, N, k, idx, val, gate, gate_min);
+    kern<<<dim3((N + ROWS - 1) / ROWS, B), ROWS * SPLIT, smem, st>>>(x, sq, N, k, idx, val, gate, gate_min);
     return check_launch("knn_rows_kernel");
 }
 
