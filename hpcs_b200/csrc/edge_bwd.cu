@@ -43,7 +43,7 @@ struct Rev2Dims {
 __host__ __device__ inline Rev2Dims rev2_dims(int N, int k) {
     Rev2Dims d;
     const size_t E = (size_t)N * k;
-    d.NS = N < kSliceTargets ? (N + 31) / 32 * 32 : kSliceTargets;
+    d.NS = N < kSliceTargets ? (N + 31) / 32 * 32 : kSliceTargets;   // (128-target slices measured slower: 143 vs 130 us)
     d.S = (N + d.NS - 1) / d.NS;
     d.GS = d.NS / 32;
     d.G = d.S * d.GS;

@@ -16,6 +16,7 @@ def main():
     ap.add_argument("--ops", default="knn3,knn63,edge,loss")
     ap.add_argument("--reps", type=int, default=3)
     ap.add_argument("--time", action="store_true", help="print CUDA-event timings per op")
+    ap.add_argument("--warm", type=int, default=2, help="untimed warm-up calls per op (0 for a compact ncu capture)")
     args = ap.parse_args()
     ops = args.ops.split(",")
     dev = torch.device("cuda:0")
@@ -24,7 +25,7 @@ def main():
     d = {k: v.to(dev) for k, v in host.items()}
 
     def timeit(name, fn):
-        for _ in range(2):
+        for _ in range(args.warm):
             fn()
         torch.cuda.synchronize()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
