@@ -42,6 +42,12 @@ METRIC = "point clouds/sec (1024 pts, k=20) fwd+bwd"
 UNIT = "clouds/s"
 
 
+# DRAM bytes per op from the committed `ncu --set full` capture (profiles/r01_b_ops_ncu_full.md): read + written,
+# summed over the op's kernels (edge bwd = reverse-graph build 5.3 MB + gather 332.9 + 9.8 MB; edge fwd 13.5 + 273.0 MB,
+# below the algorithmic 343.8 MB because the tail of the output is still in L2 when the kernel ends)
+NCU_TRAFFIC_BYTES = {"edge_bwd_c21": 348.0e6, "edge_fwd_c21": 286.5e6}
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -372,7 +378,9 @@ def run_native(args):
         ops[name] = ent
     top = max((n for n in ops if ops[n].get("peak")), key=lambda n: ops[n]["share"])
     roofline = {"kernel": top, "bound": ops[top]["bound"], "achieved": ops[top]["achieved"], "peak": ops[top]["peak"],
-                "unit": ops[top]["unit"], "frac": ops[top]["frac"], "traffic": None, "peak_source": pk["source"]}
+                "unit": ops[top]["unit"], "frac": ops[top]["frac"], "traffic": NCU_TRAFFIC_BYTES.get(top),
+                "traffic_source": "profiles/r01_b_ops_ncu_full.md (dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+                "algorithmic_bytes": work[top].get("bytes"), "peak_source": pk["source"]}
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",

@@ -530,56 +530,64 @@ knn_rerank32_kernel(const float* __restrict__ xr, const float* __restrict__ sq, 
     const int half = lane >> 4, q4 = lane & 15;
 
     float pd0 = -INFINITY;                                             // exact value of this lane's candidate, once evaluated
+    const float4* xr4 = reinterpret_cast<const float4*>(xr) + (size_t)b * N * (kKP / 4) + q4;   // this lane's 16-byte column of the cloud
+    float* my_dst = rows + 4 * q4;
     auto evaluate = [&](int lo, int hi) {                              // candidates [lo, hi): gather rows, canonical chains
-        for (int r0 = lo; r0 < hi; r0 += 8) {                          // two rows per warp instruction (16 lanes x float4
-            float4 v[4];                                               // each), four such loads in flight
-            int rr[4];
+        for (int r0 = lo; r0 < hi; r0 += 16) {                         // two rows per warp instruction (16 lanes x float4
+            float4 v[8];                                               // each), eight such loads in flight
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                rr[u] = r0 + 2 * u + half;
-                const int src = __shfl_sync(kFull, cj0, min(rr[u], 31));
+            for (int u = 0; u < 8; ++u) {
+                const int rr = r0 + 2 * u + half;
+                const int src = __shfl_sync(kFull, cj0, rr & 31);
                 v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (rr[u] < hi && src >= 0) v[u] = __ldg(reinterpret_cast<const float4*>(xr + ((size_t)b * N + src) * kKP) + q4);
+                if (rr < hi && src >= 0) v[u] = __ldg(xr4 + src * (kKP / 4));
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (rr[u] < hi) *reinterpret_cast<float4*>(rows + (size_t)rr[u] * RS + 4 * q4) = v[u];
+            for (int u = 0; u < 8; ++u) {
+                const int rr = r0 + 2 * u + half;
+                if (rr < hi) *reinterpret_cast<float4*>(my_dst + rr * RS) = v[u];
+            }
         }
         __syncwarp();
         if (lane >= lo && lane < hi && cj0 >= 0) {
-            const float* cr = rows + (size_t)lane * RS;
+            const float* cr = rows + lane * RS;
             float acc = 0.f;
-            for (int d = 0; d < D; d += 4) {                           // fma chain over d ascending
+            int d = 0;
+            for (; d + 4 <= D; d += 4) {                               // fma chain over d ascending
                 const float4 c4 = *reinterpret_cast<const float4*>(cr + d);
                 const float4 a4 = *reinterpret_cast<const float4*>(qrow + d);
                 acc = __fmaf_rn(a4.x, c4.x, acc);
-                if (d + 1 < D) acc = __fmaf_rn(a4.y, c4.y, acc);
-                if (d + 2 < D) acc = __fmaf_rn(a4.z, c4.z, acc);
-                if (d + 3 < D) acc = __fmaf_rn(a4.w, c4.w, acc);
+                acc = __fmaf_rn(a4.y, c4.y, acc);
+                acc = __fmaf_rn(a4.z, c4.z, acc);
+                acc = __fmaf_rn(a4.w, c4.w, acc);
             }
+            for (; d < D; ++d) acc = __fmaf_rn(qrow[d], cr[d], acc);
             const float sq_j = -2.f * cr[kKP - 1];                     // column 63 holds -|x_j|^2 / 2 exactly
             pd0 = __fsub_rn(__fmaf_rn(2.f, acc, -sq_i), sq_j);
         }
         __syncwarp();
     };
-    float ps;                                                          // sorted copies
-    int js;
-    auto sort32 = [&]() {                                              // descending value, ascending index on ties
-        ps = pd0;
-        js = (cj0 >= 0 && pd0 > -INFINITY) ? cj0 : 0x7fffffff;
+    // sort by one 64-bit key: order-preserving image of the value (high word) and the complemented index (low word),
+    // so "larger key first" is "larger value first, ties -> lower index"
+    unsigned long long skey;
+    auto sort32 = [&]() {
+        const unsigned fb = __float_as_uint(pd0);
+        const unsigned ord = (fb & 0x80000000u) ? ~fb : (fb | 0x80000000u);
+        const unsigned jc = (cj0 >= 0 && pd0 > -INFINITY) ? ~(unsigned)cj0 : 0u;
+        skey = ((unsigned long long)ord << 32) | jc;
 #pragma unroll
         for (int size = 2; size <= 32; size <<= 1) {
 #pragma unroll
             for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                const float ov = __shfl_xor_sync(kFull, ps, stride);
-                const int oj = __shfl_xor_sync(kFull, js, stride);
-                const bool lower = (lane & stride) == 0;
-                const bool desc = (lane & size) == 0;
-                const bool mine_first = ps > ov || (ps == ov && js < oj);
-                const bool keep = (lower == desc) ? mine_first : !mine_first;
-                if (!keep) { ps = ov; js = oj; }
+                const unsigned long long other = __shfl_xor_sync(kFull, skey, stride);
+                const bool want_max = ((lane & stride) == 0) == ((lane & size) == 0);
+                skey = want_max ? (skey > other ? skey : other) : (skey < other ? skey : other);
             }
         }
+    };
+    auto sorted_value = [&]() {
+        const unsigned ord = (unsigned)(skey >> 32);
+        return __uint_as_float((ord & 0x80000000u) ? (ord & 0x7fffffffu) : ~ord);
     };
     const float tau = __ldg(tau_in + gi);                              // bound on the key of every score outside the list
     const float cmax2 = __uint_as_float(__ldg(cmax_bits + b));         // max_j |x_j - mu|^2
@@ -592,7 +600,7 @@ knn_rerank32_kernel(const float* __restrict__ xr, const float* __restrict__ sq, 
                                (float)(D + 8) * rsum * rsum * (1.f / 16777216.f));
     const float qscale = exp2f((float)(idx_bits - 22));
     auto safe_against = [&](float bound) {                             // bound: largest key of anything not evaluated
-        const float kth = __shfl_sync(kFull, ps, k - 1);
+        const float kth = __shfl_sync(kFull, sorted_value(), k - 1);
         return bound == -INFINITY ? kth > -INFINITY : 0.5f * kth > bound + fabsf(bound) * qscale + eps;
     };
 
@@ -616,8 +624,8 @@ knn_rerank32_kernel(const float* __restrict__ xr, const float* __restrict__ sq, 
         return;
     }
     if (lane < k) {
-        idx[gi * k + lane] = js;
-        if (val) val[gi * k + lane] = ps;
+        idx[gi * k + lane] = (int64_t)(~(unsigned)skey);
+        if (val) val[gi * k + lane] = sorted_value();
     }
 }
 
