@@ -102,40 +102,55 @@ def algorithmic_work(B):
 
 
 class ClockSampler(threading.Thread):
-    """SM clock / throttle reasons during the timed region (nvml; one sample every 50 ms)."""
+    """SM clock / throttle reasons under load (nvml, one sample every 2 ms).  NVML is initialised before the
+    thread starts so the first sample lands inside even a millisecond-long timed region; samples are tagged with
+    the region they were taken in ("value" = the timed steps, "ops"/"e2e" = the later timed regions)."""
+
+    NAMES = ("HwSlowdown:hw_slowdown", "HwThermalSlowdown:hw_thermal_slowdown",
+             "SwThermalSlowdown:sw_thermal_slowdown", "SwPowerCap:sw_power_cap")
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self.index, self.samples, self.reasons, self.max_mhz = index, {}, set(), None
+        self.region = "value"
         self._stop_evt = threading.Event()
-
-    def run(self):
+        self._nv = self._h = None
         try:
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {
-                nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
-                nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
-                nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
-                nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
-            }
-            while not self._stop_evt.is_set():
-                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for bit, name in names.items():
-                    if r & bit:
-                        self.reasons.add(name)
-                self._stop_evt.wait(0.05)
+            self._nv, self._h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)
+            self._bits = {getattr(nv, "nvmlClocksThrottleReason" + n.split(":")[0]): n.split(":")[1] for n in self.NAMES}
         except Exception as exc:                                # nvml missing: report, do not fail the bench
             self.reasons.add(f"nvml_unavailable:{type(exc).__name__}")
+
+    def sample(self):
+        nv, h = self._nv, self._h
+        self.samples.setdefault(self.region, []).append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        for bit, name in self._bits.items():
+            if r & bit:
+                self.reasons.add(name)
+
+    def run(self):
+        if self._nv is None:
+            return
+        try:
+            while not self._stop_evt.is_set():
+                self.sample()
+                self._stop_evt.wait(0.002)
+        except Exception as exc:
+            self.reasons.add(f"nvml_error:{type(exc).__name__}")
 
     def stop(self):
         self._stop_evt.set()
         self.join(timeout=2)
-        s = sorted(self.samples)
-        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        med = {k: sorted(v)[len(v) // 2] for k, v in self.samples.items() if v}
+        every = sorted(x for v in self.samples.values() for x in v)
+        out = {"sm_mhz": med.get("value", every[len(every) // 2] if every else None), "sm_max_mhz": self.max_mhz,
+               "reasons": sorted(self.reasons), "samples": {k: len(v) for k, v in self.samples.items()},
+               "sm_mhz_by_region": med}
+        return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -231,16 +246,18 @@ def run_native(args):
             out = step(d, trip)
     for _ in range(max(args.warmup, 3)):
         run_step()
-    barrier()
     sampler = ClockSampler(local)
+    barrier()
     sampler.start()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
     for _ in range(args.steps):
         run_step()
     t1.record()
+    if sampler._nv is not None:
+        sampler.sample()                                    # the replays are queued: the GPU is busy right now
     barrier()
-    clocks = sampler.stop()
+    sampler.region = "ops"
     launches = launches_per_step * args.steps
     ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
     if world > 1:
@@ -346,6 +363,7 @@ def run_native(args):
 
     e2e_loop(4)
     barrier()
+    sampler.region = "e2e"
     te0, te1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     te0.record()
     e2e_loop(args.steps)
@@ -353,6 +371,7 @@ def run_native(args):
         torch.cuda.current_stream().wait_stream(s_)
     te1.record()
     barrier()
+    clocks = sampler.stop()
     ms_e = torch.tensor([te0.elapsed_time(te1)], device=dev)
     if world > 1:
         dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
@@ -404,6 +423,127 @@ def run_native(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_pass(steps=2, warmup=1)
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# decode workload (BASELINE.json configs[4]): single-/complete-linkage decode of 32-d Poincare embeddings
+# ------------------------------------------------------------------------------------------------
+def decode_inputs(B, N, seed):
+    gen = torch.Generator().manual_seed(seed)
+    u = torch.randn(B, N, D_EMB, generator=gen)
+    nrm = u.norm(dim=-1, keepdim=True)
+    return torch.tanh(nrm.clamp(max=15)) * u / nrm                    # ExpMap(N(0,1)), SURVEY 8(d)
+
+
+def decode_cpu_baseline(x, method, budget_s=12.0):
+    """The reference's decoder on host cores: normalize + project (torch CPU) then scipy linkage, cloud by cloud
+    (base_hyp_hc.py:81-86,135-137), on as many clouds of the same batch as fit the time budget."""
+    from oracle import hpcs_oracle as O
+    done, t0 = 0, time.perf_counter()
+    while done < x.shape[0] and (done == 0 or time.perf_counter() - t0 < budget_s):
+        O.decode_linkage(x[done], torch.tensor([SCALE]), method)
+        done += 1
+    dt = time.perf_counter() - t0
+    return {"value": round(done / dt, 3), "unit": "dendrograms/s", "cores": 1, "kind": "port",
+            "sample": f"{done} clouds x {x.shape[1]} pts, oracle restatement of _decode_linkage (torch CPU normalize/project + "
+                      f"scipy linkage(method='{method}', metric='cosine'), single-threaded like the reference)",
+            "s_per_cloud": round(dt / done, 4)}
+
+
+def run_decode(args):
+    import hpcs_b200 as hb
+    from hpcs_b200 import _lib, dist as hdist
+    import torch.distributed as dist
+    rank, world, local = hdist.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (native arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    B, N, method = args.decode_b, args.decode_n, args.method
+    host = decode_inputs(B, N, seed=rank)
+    x = host.to(dev)
+    scale = torch.tensor([SCALE], device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return hb.decode_linkage_batch(x, scale, method)
+
+    warm = max(args.warmup, 3)
+    for _ in range(warm):
+        Z = step()
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count()
+    Z = step()
+    launches_per_step = _lib.launch_count() - l0
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        Z = step()
+    t1.record()
+    if sampler._nv is not None:
+        sampler.sample()
+    barrier()
+    ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = ms.item() / args.steps
+
+    # end to end: embeddings from pinned host memory, Z back to pinned host memory (what fcluster consumes)
+    sampler.region = "e2e"
+    x_pin = host.pin_memory()
+    z_pin = torch.empty(Z.shape, dtype=Z.dtype).pin_memory()
+    xd = torch.empty_like(x)
+
+    def e2e_step():
+        xd.copy_(x_pin, non_blocking=True)
+        z = hb.decode_linkage_batch(xd, scale, method)
+        z_pin.copy_(z, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    te0, te1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    te0.record()
+    for _ in range(args.steps):
+        e2e_step()
+    te1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms_e = torch.tensor([te0.elapsed_time(te1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
+    if rank != 0:
+        return
+    pk = peaks()
+    alg_bytes = 2.0 * B * N * (N - 1) / 2 * 8                          # fp64 condensed matrix written once, read once
+    achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+    zc = z_pin.numpy()
+    line = {
+        "metric": f"dendrograms/sec ({method}-linkage decode, {N} pts, 32-d)", "value": round(world * B / (ms_per_step * 1e-3), 1),
+        "unit": "dendrograms/s", "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": round(ms_per_step, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"decode_{method}_b{B}_n{N}_d{D_EMB} (BASELINE.json configs[4])", "clouds_per_gpu": B,
+                   "points": N, "emb_dim": D_EMB, "method": method, "scale": SCALE, "parallelism": f"dp{world}",
+                   "l2": f"fp64 distance matrices {B * N * N * 8 / 1e6:.0f} MB per step vs 126 MB L2; no explicit flush",
+                   "launch": "eager (one C-ABI call per step)"},
+        "e2e": {"value": round(world * B / (ms_e.item() / args.steps * 1e-3), 1), "unit": "dendrograms/s",
+                "h2d_bytes_per_step": int(x_pin.numel() * 4), "d2h_bytes_per_step": int(z_pin.numel() * 8)},
+        "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks,
+        "roofline": {"kernel": "pdist_cosine + linkage", "bound": "hbm", "achieved": round(achieved, 1), "peak": pk["hbm_gbs"],
+                     "unit": "GB/s", "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": None,
+                     "algorithmic_bytes": alg_bytes, "peak_source": pk["source"]},
+        "root_count": float(zc[0, -1, 3]),
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = decode_cpu_baseline(host, method)
     print(json.dumps(line), flush=True)
 
 
@@ -477,9 +617,23 @@ def main():
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--workload", choices=["train", "decode"], default="train",
+                    help="train = the headline step (configs[1]); decode = dendrogram decode (configs[4])")
+    ap.add_argument("--decode-n", type=int, default=1024)
+    ap.add_argument("--decode-b", type=int, default=64)
+    ap.add_argument("--method", choices=["single", "complete"], default="single")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.impl == "reference" and args.workload == "decode":
+        if int(os.environ.get("RANK", "0")) == 0:
+            cb = decode_cpu_baseline(decode_inputs(args.decode_b, args.decode_n, 0), args.method)
+            print(json.dumps({"impl": "reference", "metric": f"dendrograms/sec ({args.method}-linkage decode, {args.decode_n} pts, 32-d)",
+                              "value": cb["value"], "unit": cb["unit"], "n_gpus": int(os.environ.get("WORLD_SIZE", "1")),
+                              "higher_is_better": True, "cpu_baseline": cb,
+                              "e2e": {"value": cb["value"], "unit": cb["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+    elif args.impl == "reference":
         run_reference(args)
+    elif args.workload == "decode":
+        run_decode(args)
     else:
         run_native(args)
     import torch.distributed as dist

@@ -4,10 +4,12 @@
 // of BaseSimilarityHypHC._decode_linkage (hpcs/models/base_hyp_hc.py:81-86) and the Python loop
 // over clouds at :135-137: all B clouds are decoded by one launch sequence, one CTA per cloud.
 //   1. pdist_cosine_kernel  -- fp64 cosine distance matrix, bit-identical to scipy's pdist
-//      (two running sums over even/odd elements, separate multiply/add, see oracle);
-//   2. linkage_kernel<0>    -- 'single': Prim's MST from node 0 over matrix rows (what scipy's
-//      mst_single_linkage does), block-wide (value, index) arg-min per step;
-//      linkage_kernel<1>    -- 'complete': nearest-neighbour chain with the max update
+//      (two running sums over even/odd elements, see oracle), 64x64 tiles, 4x4 outputs per thread on DFMA;
+//   2. linkage_kernel<0,.>  -- 'single': Prim's MST from node 0 over matrix rows (what scipy's
+//      mst_single_linkage does); a thread keeps the running minima of its columns in registers, loads
+//      its part of the row in one batch and the block takes a (value, index) arg-min with redux.sync
+//      and ONE barrier per step -- the N-1 steps are a serial chain, so a step's latency is the cost;
+//      linkage_kernel<1,.>  -- 'complete': nearest-neighbour chain with the max update
 //      (scipy's nn_chain), same arg-min primitive, distance matrix updated in place;
 //   3. in the same kernel: stable bitonic sort of the N-1 merges by height, then the union-find
 //      relabel pass (smaller root id first, new id N+i, subtree size) that scipy's `label` does.
@@ -20,218 +22,311 @@
 
 namespace hpcs {
 
-constexpr int kTile = 32;
+constexpr int kPT = 64;           // pdist tile edge
+constexpr int kPLD = kPT + 2;     // shared-memory row pitch in doubles (keeps 16-byte alignment, spreads banks)
 
-// grid: (T*(T+1)/2 upper tiles, B); block 256.  dm[b][i][j] full symmetric, zero diagonal.
+// fp64 cosine distance matrix, bit-identical to scipy's pdist(., 'cosine') on the same fp32 rows.
+// grid: (T*(T+1)/2 upper 64x64 tiles, B); block 256 = 16 x 16 threads, 4 x 4 outputs each: rows ty*4+ii, columns
+// tx+16*jj.  dm[b][i][j] full symmetric, zero diagonal.
+// scipy sums a dot product as two running sums (even / odd elements, separate multiply and add), added at the end,
+// an odd tail element last.  Every operand here is an fp32 value widened to fp64, so a product has at most 48
+// significant bits and is exact in fp64: fma(a, b, acc) rounds the same real number as add(mul(a, b), acc) and gives
+// the same bits.  The kernel therefore runs on DFMA (half the fp64 instructions) without changing any result.
 __global__ void __launch_bounds__(256)
 pdist_cosine_kernel(const float* __restrict__ leaves, int N, int D, double* __restrict__ dm) {
-    extern __shared__ double sm[];
-    double* ri = sm;                          // [32][D]   rows of the i-tile
-    double* rj = ri + kTile * D;              // [D][32]   rows of the j-tile, transposed
-    double* ni = rj + kTile * D;              // [32] norms
-    double* nj = ni + kTile;                  // [32]
-    double* tile = nj + kTile;                // [32][33] results
+    extern __shared__ __align__(16) double sm[];
+    double* as = sm;                          // [D][kPLD] rows of the i-tile, feature-major
+    double* bs = as + (size_t)D * kPLD;       // [D][kPLD] rows of the j-tile
+    double* na = bs + (size_t)D * kPLD;       // [64] norms
+    double* nb = na + kPT;
     const int b = blockIdx.y;
-    // linear upper-triangular tile index -> (bi, bj), bi <= bj
-    const int T = (N + kTile - 1) / kTile;
-    int bi = 0, rem = blockIdx.x;
+    const int T = (N + kPT - 1) / kPT;
+    int bi = 0, rem = blockIdx.x;             // linear upper-triangular tile index -> (bi, bj), bi <= bj
     while (rem >= T - bi) { rem -= T - bi; ++bi; }
     const int bj = bi + rem;
     const float* lb = leaves + (size_t)b * N * D;
-    for (int e = threadIdx.x; e < kTile * D; e += blockDim.x) {
-        const int r = e / D, q = e % D;
-        const int gi = bi * kTile + r, gj = bj * kTile + r;
-        ri[r * D + q] = gi < N ? (double)lb[(size_t)gi * D + q] : 0.0;
-        rj[q * kTile + r] = gj < N ? (double)lb[(size_t)gj * D + q] : 0.0;
+    for (int e = threadIdx.x; e < kPT * D; e += blockDim.x) {
+        const int r = e / D, q = e - r * D;
+        const int gi = bi * kPT + r, gj = bj * kPT + r;
+        as[q * kPLD + r] = gi < N ? (double)__ldg(lb + (size_t)gi * D + q) : 0.0;
+        bs[q * kPLD + r] = gj < N ? (double)__ldg(lb + (size_t)gj * D + q) : 0.0;
     }
     __syncthreads();
-    if (threadIdx.x < 2 * kTile) {
-        const bool second = threadIdx.x >= kTile;
-        const int r = threadIdx.x % kTile;
+    if (threadIdx.x < 2 * kPT) {
+        const double* src = (threadIdx.x >= kPT ? bs : as) + (threadIdx.x & (kPT - 1));
         double even = 0.0, odd = 0.0;
-        for (int q = 0; q + 1 < D; q += 2) {
-            const double v0 = second ? rj[q * kTile + r] : ri[r * D + q];
-            const double v1 = second ? rj[(q + 1) * kTile + r] : ri[r * D + q + 1];
-            even = __dadd_rn(even, __dmul_rn(v0, v0));
-            odd = __dadd_rn(odd, __dmul_rn(v1, v1));
+        int q = 0;
+        for (; q + 1 < D; q += 2) {
+            const double v0 = src[q * kPLD], v1 = src[(q + 1) * kPLD];
+            even = fma(v0, v0, even);
+            odd = fma(v1, v1, odd);
         }
         double s = __dadd_rn(even, odd);
-        if (D & 1) {
-            const double v = second ? rj[(D - 1) * kTile + r] : ri[r * D + D - 1];
-            s = __dadd_rn(s, __dmul_rn(v, v));
-        }
-        (second ? nj : ni)[r] = __dsqrt_rn(s);
+        if (D & 1) { const double v = src[(D - 1) * kPLD]; s = fma(v, v, s); }
+        (threadIdx.x >= kPT ? nb : na)[threadIdx.x & (kPT - 1)] = __dsqrt_rn(s);
     }
-    __syncthreads();
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    double ev[4][4], od[4][4];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int i = ty * 4 + r;
-        double even = 0.0, odd = 0.0;
-        for (int q = 0; q + 1 < D; q += 2) {
-            even = __dadd_rn(even, __dmul_rn(ri[i * D + q], rj[q * kTile + tx]));
-            odd = __dadd_rn(odd, __dmul_rn(ri[i * D + q + 1], rj[(q + 1) * kTile + tx]));
-        }
-        double s = __dadd_rn(even, odd);
-        if (D & 1) s = __dadd_rn(s, __dmul_rn(ri[i * D + D - 1], rj[(D - 1) * kTile + tx]));
-        double c = __ddiv_rn(s, __dmul_rn(ni[i], nj[tx]));
-        if (fabs(c) > 1.0) c = copysign(1.0, c);
-        const int gi = bi * kTile + i, gj = bj * kTile + tx;
-        tile[i * 33 + tx] = (gi == gj) ? 0.0 : __dsub_rn(1.0, c);
+    for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) { ev[ii][jj] = 0.0; od[ii][jj] = 0.0; }
+    const double* ap = as + ty * 4;
+    const double* bp = bs + tx;
+    int q = 0;
+    for (; q + 1 < D; q += 2) {
+        const double2 a01 = *reinterpret_cast<const double2*>(ap + q * kPLD);
+        const double2 a23 = *reinterpret_cast<const double2*>(ap + q * kPLD + 2);
+        const double2 c01 = *reinterpret_cast<const double2*>(ap + (q + 1) * kPLD);
+        const double2 c23 = *reinterpret_cast<const double2*>(ap + (q + 1) * kPLD + 2);
+        const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+        const double c[4] = {c01.x, c01.y, c23.x, c23.y};
+        double be[4], bo[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) { be[jj] = bp[q * kPLD + 16 * jj]; bo[jj] = bp[(q + 1) * kPLD + 16 * jj]; }
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                ev[ii][jj] = fma(a[ii], be[jj], ev[ii][jj]);
+                od[ii][jj] = fma(c[ii], bo[jj], od[ii][jj]);
+            }
     }
-    __syncthreads();
+    __syncthreads();                           // norms written
+    double res[4][4];
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+        const int i = ty * 4 + ii;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int j = tx + 16 * jj;
+            double s = __dadd_rn(ev[ii][jj], od[ii][jj]);
+            if (D & 1) s = fma(as[(D - 1) * kPLD + i], bs[(D - 1) * kPLD + j], s);
+            double c = __ddiv_rn(s, __dmul_rn(na[i], nb[j]));
+            if (fabs(c) > 1.0) c = copysign(1.0, c);
+            res[ii][jj] = (bi * kPT + i == bj * kPT + j) ? 0.0 : __dsub_rn(1.0, c);
+        }
+    }
     double* db = dm + (size_t)b * N * N;
+    const bool vec_ok = (N & 3) == 0;          // rows start 32-byte aligned
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        const int i = ty * 4 + r;
-        const int gi = bi * kTile + i, gj = bj * kTile + tx;
-        if (gi < N && gj < N) db[(size_t)gi * N + gj] = tile[i * 33 + tx];
-        if (bi != bj) {                       // mirrored tile, read transposed
-            const int gi2 = bj * kTile + i, gj2 = bi * kTile + tx;
-            if (gi2 < N && gj2 < N) db[(size_t)gi2 * N + gj2] = tile[tx * 33 + i];
+    for (int ii = 0; ii < 4; ++ii) {
+        const int gi = bi * kPT + ty * 4 + ii;
+        if (gi >= N) continue;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int gj = bj * kPT + tx + 16 * jj;
+            if (gj < N) db[(size_t)gi * N + gj] = res[ii][jj];          // 16 lanes x 8 B contiguous
+        }
+    }
+    if (bi != bj) {                            // mirrored tile: this thread's 4 rows are 4 consecutive columns there
+        const int gi0 = bi * kPT + ty * 4;
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int gj = bj * kPT + tx + 16 * jj;
+            if (gj >= N) continue;
+            double* dst = db + (size_t)gj * N + gi0;
+            if (vec_ok && gi0 + 3 < N) {
+                *reinterpret_cast<double2*>(dst) = make_double2(res[0][jj], res[1][jj]);
+                *reinterpret_cast<double2*>(dst + 2) = make_double2(res[2][jj], res[3][jj]);
+            } else {
+#pragma unroll
+                for (int ii = 0; ii < 4; ++ii) if (gi0 + ii < N) dst[ii] = res[ii][jj];
+            }
         }
     }
 }
 
-struct ArgMin {
-    double v;
-    int i;
-};
 __device__ __forceinline__ bool am_less(double v, int i, double ov, int oi) { return v < ov || (v == ov && i < oi); }
 
-// Block-wide lexicographic (value, index) minimum; every thread gets the result.
-__device__ __forceinline__ ArgMin block_argmin(double v, int i, ArgMin* scratch /*[32]*/, ArgMin* result) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        const double ov = __shfl_xor_sync(kFull, v, o);
-        const int oi = __shfl_xor_sync(kFull, i, o);
-        if (am_less(ov, oi, v, i)) { v = ov; i = oi; }
-    }
-    if (lane == 0) { scratch[warp].v = v; scratch[warp].i = i; }
-    __syncthreads();
-    if (warp == 0) {
-        v = lane < nwarp ? scratch[lane].v : DBL_MAX;
-        i = lane < nwarp ? scratch[lane].i : 0x7fffffff;
-        if (!(lane < nwarp)) v = INFINITY;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ov = __shfl_xor_sync(kFull, v, o);
-            const int oi = __shfl_xor_sync(kFull, i, o);
-            if (am_less(ov, oi, v, i)) { v = ov; i = oi; }
-        }
-        if (lane == 0) { result->v = v; result->i = i; }
-    }
-    __syncthreads();
-    return *result;
+// ---- block-wide lexicographic (distance, index) minimum ------------------------------------------------------
+// Distances are non-negative doubles (or +inf), so their bit patterns order like unsigned integers: the minimum is
+// three integer warp reductions (redux.sync) -- high word, low word among the lanes that tie on the high word, index
+// among the lanes that tie on both -- instead of five rounds of 64-bit shuffles.  One __syncthreads per call: the
+// per-warp results go through a double-buffered scratch array and every warp reduces them again for itself.
+struct LexKey {
+    unsigned hi, lo;
+    int idx;
+};
+constexpr int kNoIdx = 0x7fffffff;
+
+__device__ __forceinline__ void warp_lexmin(LexKey& k) {
+    const unsigned mh = __reduce_min_sync(kFull, k.hi);
+    const unsigned l2 = k.hi == mh ? k.lo : 0xffffffffu;
+    const unsigned ml = __reduce_min_sync(kFull, l2);
+    const unsigned i2 = (k.hi == mh && k.lo == ml) ? (unsigned)k.idx : (unsigned)kNoIdx;
+    k.idx = (int)__reduce_min_sync(kFull, i2);
+    k.hi = mh;
+    k.lo = ml;
 }
 
-// METHOD 0 single, 1 complete.  One CTA per cloud.
-template <int METHOD>
+__device__ __forceinline__ LexKey block_lexmin(double v, int idx, uint4* scratch /*[2][32]*/, unsigned& phase) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    LexKey k{(unsigned)(bits >> 32), (unsigned)bits, idx};
+    warp_lexmin(k);
+    uint4* buf = scratch + (phase & 1u) * 32;
+    ++phase;
+    if (lane == 0) buf[warp] = make_uint4(k.hi, k.lo, (unsigned)k.idx, 0u);
+    __syncthreads();
+    const uint4 e = lane < nwarp ? buf[lane] : make_uint4(0xffffffffu, 0xffffffffu, (unsigned)kNoIdx, 0u);
+    LexKey r{e.x, e.y, (int)e.z};
+    warp_lexmin(r);
+    return r;
+}
+__device__ __forceinline__ double key_value(const LexKey& k) {
+    return __longlong_as_double((long long)(((unsigned long long)k.hi << 32) | k.lo));
+}
+
+// METHOD 0 single, 1 complete.  One CTA per cloud; thread t owns columns t, t + T, ..., t + (CPT-1) T of the
+// distance matrix: its running minima (single) and its alive flags live in registers, and the CPT loads of a row are
+// issued back to back before any of them is used.
+// Contracted input (single linkage after Boruvka rounds, see below): the matrix is n x n with row pitch `pitch`,
+// n is read from nd_all[b*8 + nd_slot], node v stands for leaf rep[v], and the first N - n merge records are already
+// in recx/recy/rech.  Direct input: pitch = N, nd_all = nullptr, rep_all = nullptr.
+// gate (optional): per-cloud flag; the CTA returns at once unless gate[b] != 0 (exact redo of clouds with tied heights).
+template <int METHOD, int CPT>
 __global__ void __launch_bounds__(1024)
-linkage_kernel(double* dm_all, int N, int NP2, int* __restrict__ recx_all, int* __restrict__ recy_all,
-               double* __restrict__ rech_all, double* __restrict__ Z_all) {
+linkage_kernel(double* dm_all, size_t dm_stride, int pitch, const int* __restrict__ nd_all, int nd_slot,
+               const int* __restrict__ rep_all, int rep_stride, int N, int NP2, int* __restrict__ recx_all,
+               int* __restrict__ recy_all, double* __restrict__ rech_all, double* __restrict__ Z_all,
+               int* __restrict__ tie_flag, const int* __restrict__ gate) {
     extern __shared__ __align__(16) unsigned char raw[];
-    __shared__ ArgMin scratch[32];
-    __shared__ ArgMin result;
-    __shared__ int ctl[4];
+    __shared__ uint4 scratch[64];
+    __shared__ int tie_s;
     const int b = blockIdx.x;
+    if (gate && gate[b] == 0) return;
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int M = N - 1;
-    double* dm = dm_all + (size_t)b * N * N;              // mutated by METHOD 1: plain loads only
+    const int n_nodes = nd_all ? nd_all[b * 8 + nd_slot] : N;       // nodes of the (contracted) matrix
+    const int rec0 = N - n_nodes;                                   // merges already recorded
+    const int* rep = rep_all ? rep_all + (size_t)b * rep_stride : nullptr;
+    double* dm = dm_all + (size_t)b * dm_stride;          // mutated by METHOD 1: plain loads only
     int* recx = recx_all + (size_t)b * N;
     int* recy = recy_all + (size_t)b * N;
     double* rech = rech_all + (size_t)b * N;
     double* Z = Z_all + (size_t)b * M * 4;
 
-    // shared-memory regions (see header comment for the overlay plan)
-    double* A = reinterpret_cast<double*>(raw);                      // [NP2]  Dmin / sort keys
+    // shared-memory regions
+    double* A = reinterpret_cast<double*>(raw);                      // [NP2]  sort keys
     int* ordv = reinterpret_cast<int*>(raw + (size_t)8 * NP2);       // [NP2]  sort payload
-    unsigned char* regC = raw + (size_t)12 * NP2;                    // 8N bytes: flags / sizes+chain / sorted (x,y)
+    unsigned char* regC = raw + (size_t)12 * NP2;                    // 8N bytes: NN chain, later the sorted (x,y)
     int* csize = reinterpret_cast<int*>(regC + (size_t)8 * N);       // [2N]
-    int* parent = reinterpret_cast<int*>(raw);                       // [2N] overlays A+ordv after the sort
+    int* parent = reinterpret_cast<int*>(raw);                       // [N] overlays A after the sort
+
+    unsigned alive = 0u, phase = 0u;
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) if (tid + c * nthr < n_nodes) alive |= 1u << c;
+    auto drop = [&](int col) {                                       // the owner of `col` clears its flag
+        const int c = col / nthr;
+        if (col - c * nthr == tid) alive &= ~(1u << c);
+    };
+    auto first_alive = [&]() -> int {                                // lowest column still alive (block-wide)
+        int mine = kNoIdx;
+#pragma unroll
+        for (int c = CPT - 1; c >= 0; --c) if ((alive >> c) & 1u) mine = tid + c * nthr;
+        return block_lexmin(0.0, mine, scratch, phase).idx;
+    };
 
     if (METHOD == 0) {
-        unsigned char* merged = regC;
-        for (int i = tid; i < N; i += nthr) { A[i] = INFINITY; merged[i] = 0; }
-        __syncthreads();
+        // Prim from node 0 over matrix rows, what scipy's mst_single_linkage does: (distance, index) arg-min per step
+        double dmin[CPT];
+#pragma unroll
+        for (int c = 0; c < CPT; ++c) dmin[c] = INFINITY;
         int x = 0;
-        for (int k = 0; k < M; ++k) {
-            if (tid == 0) merged[x] = 1;
-            __syncthreads();
-            const double* row = dm + (size_t)x * N;
-            double bv = INFINITY;
-            int bi = 0x7fffffff;
-            for (int i = tid; i < N; i += nthr) {
-                if (merged[i]) continue;
-                const double d = row[i];
-                double cur = A[i];
-                if (cur > d) { cur = d; A[i] = d; }
-                if (cur < bv) { bv = cur; bi = i; }
+        for (int k = rec0; k < M; ++k) {
+            drop(x);
+            const double* row = dm + (size_t)x * pitch;
+            double v[CPT];
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                const int col = tid + c * nthr;
+                v[c] = col < n_nodes ? __ldcs(row + col) : INFINITY; // each row is read once: streaming
             }
-            const ArgMin r = block_argmin(bv, bi, scratch, &result);
-            if (tid == 0) { recx[k] = x; recy[k] = r.i; rech[k] = r.v; }
-            x = r.i;
+            double bv = INFINITY;
+            int bi = kNoIdx;
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                if ((alive >> c) & 1u) {
+                    if (dmin[c] > v[c]) dmin[c] = v[c];
+                    if (dmin[c] < bv) { bv = dmin[c]; bi = tid + c * nthr; }
+                }
+            }
+            LexKey r = block_lexmin(bv, bi, scratch, phase);
+            if (r.idx == kNoIdx) r.idx = first_alive();              // only NaN/inf distances left (zero-norm rows)
+            if (tid == 0) {
+                recx[k] = rep ? rep[x] : x;
+                recy[k] = rep ? rep[r.idx] : r.idx;
+                rech[k] = key_value(r);
+            }
+            x = r.idx;
         }
     } else {
-        int* size = reinterpret_cast<int*>(regC);                     // [N]
-        int* chain = size + N;                                        // [N]
-        for (int i = tid; i < N; i += nthr) size[i] = 1;
-        if (tid == 0) { ctl[0] = 0; /* chain length */ ctl[1] = 0; /* first active */ }
-        __syncthreads();
+        // nearest-neighbour chain with the 'complete' update (scipy's nn_chain), matrix updated in place
+        int* chain = reinterpret_cast<int*>(regC);                    // [N]
+        int len = 0, x = 0, prev = -1;
         for (int k = 0; k < M; ++k) {
-            if (tid == 0 && ctl[0] == 0) {
-                int f = ctl[1];
-                while (size[f] == 0) ++f;
-                ctl[1] = f;
-                chain[0] = f;
-                ctl[0] = 1;
+            if (len == 0) {
+                x = first_alive();
+                prev = -1;
+                if (tid == 0) chain[0] = x;
+                len = 1;
             }
-            __syncthreads();
-            int x, y;
+            int y;
             double cur;
             while (true) {
-                const int len = ctl[0];
-                x = chain[len - 1];
-                const int prev = len > 1 ? chain[len - 2] : -1;
                 const double* row = dm + (size_t)x * N;
+                double v[CPT];
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) {
+                    const int col = tid + c * nthr;
+                    v[c] = col < N ? row[col] : INFINITY;
+                }
+                const double dprev = prev >= 0 ? row[prev] : INFINITY;
                 double bv = INFINITY;
-                int bi = 0x7fffffff;
-                for (int i = tid; i < N; i += nthr) {
-                    if (size[i] == 0 || i == x) continue;
-                    const double d = row[i];
-                    if (d < bv) { bv = d; bi = i; }
+                int bi = kNoIdx;
+#pragma unroll
+                for (int c = 0; c < CPT; ++c) {
+                    const int col = tid + c * nthr;
+                    if (((alive >> c) & 1u) && col != x && v[c] < bv) { bv = v[c]; bi = col; }
                 }
-                const ArgMin r = block_argmin(bv, bi, scratch, &result);
-                y = r.i; cur = r.v;
-                if (prev >= 0) {
-                    const double dprev = row[prev];
-                    if (!(r.v < dprev)) { y = prev; cur = dprev; }
-                }
-                const bool done = prev >= 0 && y == prev;
-                __syncthreads();                    // everyone has read ctl/chain before they change
+                const LexKey r = block_lexmin(bv, bi, scratch, phase);
+                y = r.idx; cur = key_value(r);
+                bool done = false;
+                if (prev >= 0 && !(cur < dprev)) { y = prev; cur = dprev; done = true; }   // ties prefer the previous link
+                if (y == kNoIdx) { y = first_alive(); }               // degenerate input (NaN rows): keep going
                 if (done) break;
-                if (tid == 0) { chain[len] = y; ctl[0] = len + 1; }
-                __syncthreads();
+                if (tid == 0) chain[len] = y;
+                ++len;
+                prev = x;
+                x = y;
             }
             if (x > y) { const int t = x; x = y; y = t; }
-            const int nx = size[x], ny = size[y];
-            __syncthreads();
-            if (tid == 0) {
-                ctl[0] -= 2;
-                recx[k] = x; recy[k] = y; rech[k] = cur;
-                size[x] = 0; size[y] = nx + ny;
-            }
+            if (tid == 0) { recx[k] = x; recy[k] = y; rech[k] = cur; }
+            drop(x);                                                  // cluster x is dropped, y becomes the union
             // Lance-Williams 'complete': d(i, x u y) = max(d(i,x), d(i,y)); kept symmetric
-            double* rowx = dm + (size_t)x * N;
+            const double* rowx = dm + (size_t)x * N;
             double* rowy = dm + (size_t)y * N;
-            for (int i = tid; i < N; i += nthr) {
-                if (i == y || i == x || size[i] == 0) continue;
-                const double v = fmax(rowx[i], rowy[i]);
-                rowy[i] = v;
-                dm[(size_t)i * N + y] = v;
+            double vx[CPT], vy[CPT];
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                const int col = tid + c * nthr;
+                const bool on = ((alive >> c) & 1u) && col != y;
+                vx[c] = on ? rowx[col] : 0.0;
+                vy[c] = on ? rowy[col] : 0.0;
             }
-            __syncthreads();
+#pragma unroll
+            for (int c = 0; c < CPT; ++c) {
+                const int col = tid + c * nthr;
+                if (((alive >> c) & 1u) && col != y) {
+                    const double v = fmax(vx[c], vy[c]);
+                    rowy[col] = v;
+                    dm[(size_t)col * N + y] = v;
+                }
+            }
+            __syncthreads();                       // column y (written by other threads) is read by later row scans
+            len -= 2;
+            if (len > 0) { x = chain[len - 1]; prev = len > 1 ? chain[len - 2] : -1; }
         }
     }
     __syncthreads();
@@ -258,29 +353,251 @@ linkage_kernel(double* dm_all, int N, int NP2, int* __restrict__ recx_all, int* 
         }
     }
     int2* exy = reinterpret_cast<int2*>(regC);
+    if (tid == 0) tie_s = 0;
+    __syncthreads();
     for (int i = tid; i < M; i += nthr) {
         const int o = ordv[i];
         exy[i] = make_int2(recx[o], recy[o]);
         Z[(size_t)i * 4 + 2] = A[i];
+        if (i + 1 < M && A[i] == A[i + 1]) tie_s = 1;                // equal heights: merge order is not unique
     }
     __syncthreads();
-    // ---- union-find relabel (scipy `label`) -----------------------------------------------------
-    for (int v = tid; v < 2 * N; v += nthr) { parent[v] = v; csize[v] = v < N ? 1 : 0; }
+    if (tie_flag && tid == 0) tie_flag[b] = tie_s;
+    // ---- union-find relabel (scipy `label`): ids of the two clusters a merge joins, size of the union --------------
+    // The forest lives on the N leaves with union by size, and cid[root] carries the scipy id of the cluster (leaf id,
+    // or N + i for the cluster made by sorted merge i).  Single-linkage dendrograms are chains -- one big cluster
+    // swallowing points -- and union by size keeps the big cluster's root fixed, so a find is one or two hops instead
+    // of a walk up a chain of merge nodes.
+    int* cid = csize + N;                                             // [N] (csize is [2N]: second half)
+    for (int v = tid; v < N; v += nthr) { parent[v] = v; csize[v] = 1; cid[v] = v; }
     __syncthreads();
-    if (tid == 0) {
+    if (tid < 32) {
+        // lanes 0 and 1 chase the two roots of a merge at the same time (they are in different trees)
+        const int lane = tid;
+        int2 e = exy[0];
         for (int i = 0; i < M; ++i) {
-            const int2 e = exy[i];
-            int rx = e.x, ry = e.y;
-            while (parent[rx] != rx) { const int g = parent[parent[rx]]; parent[rx] = g; rx = g; }
-            while (parent[ry] != ry) { const int g = parent[parent[ry]]; parent[ry] = g; ry = g; }
-            const int id = N + i;
-            const int sz = csize[rx] + csize[ry];
-            parent[rx] = id; parent[ry] = id; csize[id] = sz;
-            Z[(size_t)i * 4 + 0] = (double)(rx < ry ? rx : ry);
-            Z[(size_t)i * 4 + 1] = (double)(rx < ry ? ry : rx);
-            Z[(size_t)i * 4 + 3] = (double)sz;
+            const int2 nxt = i + 1 < M ? exy[i + 1] : e;             // next record: independent of the chase below
+            int r = lane == 1 ? e.y : e.x;
+            int sz = 0, id = 0;
+            if (lane < 2) {
+                while (true) {
+                    const int p = parent[r];
+                    if (p == r) break;
+                    const int g = parent[p];
+                    parent[r] = g;
+                    r = g;
+                }
+                sz = csize[r];
+                id = cid[r];
+            }
+            const int rx = __shfl_sync(kFull, r, 0), ry = __shfl_sync(kFull, r, 1);
+            const int sx = __shfl_sync(kFull, sz, 0), sy = __shfl_sync(kFull, sz, 1);
+            const int ix = __shfl_sync(kFull, id, 0), iy = __shfl_sync(kFull, id, 1);
+            if (lane == 0) {
+                const int big = sx >= sy ? rx : ry, small = sx >= sy ? ry : rx;
+                parent[small] = big;
+                csize[big] = sx + sy;
+                cid[big] = N + i;
+                Z[(size_t)i * 4 + 0] = (double)(ix < iy ? ix : iy);
+                Z[(size_t)i * 4 + 1] = (double)(ix < iy ? iy : ix);
+                Z[(size_t)i * 4 + 3] = (double)(sx + sy);
+            }
+            __syncwarp();
+            e = nxt;
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Boruvka rounds for single linkage
+// ------------------------------------------------------------------------------------------------
+// Prim's N - 1 steps are a serial chain of row fetches; a Boruvka round is fully parallel: every node takes its
+// nearest other node ((distance, index) arg-min of its matrix row), these edges are MST edges, the nodes they join
+// become one super-node, and the matrix is contracted to component-to-component minima.  A round leaves at most half
+// the nodes (about a third on embeddings), so after R rounds Prim runs on N/3^R nodes.  The dendrogram of single
+// linkage is the same for every MST as long as the N - 1 merge heights are distinct (clusters at a threshold are the
+// connected components of the threshold graph); when two heights tie, scipy's order depends on its Prim visiting
+// order, so such a cloud raises tie_flag and is redone by the exact Prim emulation on the untouched full matrix.
+//
+// Per cloud: nd[8] ints: nd[r] = nodes after r rounds (nd[0] = N).
+
+__device__ __forceinline__ int node_count(const int* nd_all, int b, int slot, int N) {
+    return slot == 0 ? N : nd_all[b * 8 + slot];
+}
+
+// Row arg-min of the n x n matrix (n = nd[slot]).  grid (rows, B), one CTA per row.
+__global__ void __launch_bounds__(256)
+boruvka_rowmin_kernel(const double* __restrict__ dm_all, size_t dm_stride, int pitch, const int* __restrict__ nd_all,
+                      int slot, double* __restrict__ rmw_all, int* __restrict__ rmj_all, int N) {
+    __shared__ uint4 scratch[64];
+    const int b = blockIdx.y, i = blockIdx.x;
+    const int n = node_count(nd_all, b, slot, N);
+    if (i >= n) return;
+    const double* row = dm_all + (size_t)b * dm_stride + (size_t)i * pitch;
+    double bv = INFINITY;
+    int bi = kNoIdx;
+    for (int j0 = threadIdx.x; j0 < n; j0 += 4 * blockDim.x) {
+        double v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int j = j0 + u * blockDim.x; v[u] = j < n ? __ldcs(row + j) : INFINITY; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int j = j0 + u * blockDim.x; if (j != i && v[u] < bv) { bv = v[u]; bi = j; } }
+    }
+    unsigned phase = 0u;
+    const LexKey r = block_lexmin(bv, bi, scratch, phase);
+    if (threadIdx.x == 0) { rmw_all[(size_t)b * N + i] = key_value(r); rmj_all[(size_t)b * N + i] = r.idx; }
+}
+
+// exclusive prefix sum over vals[0..n) (ints in shared memory), in place; returns the total.  Every thread calls it.
+__device__ int block_exclusive_scan(int* vals, int n, int* wsum /*[32]*/) {
+    const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
+    const int per = (n + nthr - 1) / nthr;
+    const int lo = min(n, tid * per), hi = min(n, lo + per);
+    int sum = 0;
+    for (int i = lo; i < hi; ++i) sum += vals[i];
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(kFull, inc, o); if (lane >= o) inc += v; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const int w = lane < nwarp ? wsum[lane] : 0;
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(kFull, winc, o); if (lane >= o) winc += v; }
+        wsum[lane] = winc - w;                                   // exclusive warp offsets; lane 31's inclusive = total
+        if (lane == 31) wsum[32] = winc;
+    }
+    __syncthreads();
+    int run = wsum[warp] + inc - sum;
+    for (int i = lo; i < hi; ++i) { const int v = vals[i]; vals[i] = run; run += v; }
+    const int total = wsum[32];
+    __syncthreads();
+    return total;
+}
+
+// Hook + label one round.  One CTA per cloud.  In: row arg-mins (rmw, rmj) of the n = nd[slot] nodes, rep_in (leaf
+// standing for a node; nullptr = identity).  Out: merge records appended at rec[N - n ...], nd[slot + 1] = n',
+// label-sorted member lists (moff[n' + 1], memb[n]) for the contraction, rep_out[n'].
+__global__ void __launch_bounds__(1024)
+boruvka_hook_kernel(const double* __restrict__ rmw_all, const int* __restrict__ rmj_all, int* __restrict__ nd_all, int slot,
+                    const int* __restrict__ rep_in_all, int rep_in_stride, int* __restrict__ rep_out_all, int rep_out_stride,
+                    int* __restrict__ memb_all, int* __restrict__ moff_all, int* __restrict__ recx_all,
+                    int* __restrict__ recy_all, double* __restrict__ rech_all, int N) {
+    extern __shared__ __align__(16) int hs[];
+    __shared__ int wsum[33];
+    const int b = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
+    int* nd = nd_all + b * 8;
+    const int n = node_count(nd_all, b, slot, N);
+    if (n <= 1) { if (tid == 0) nd[slot + 1] = n; return; }       // nothing left to join (moff/memb/rep_out unused)
+    int* par = hs;              // [n] nearest node, then root
+    int* aux = par + n;         // [n] emit flags -> record positions; then root flags -> new ids
+    int* cnt = aux + n;         // [n] member counts -> offsets -> cursors
+    const double* rmw = rmw_all + (size_t)b * N;
+    const int* rmj = rmj_all + (size_t)b * N;
+    const int* rep_in = rep_in_all ? rep_in_all + (size_t)b * rep_in_stride : nullptr;
+    int* rep_out = rep_out_all + (size_t)b * rep_out_stride;
+    int* memb = memb_all + (size_t)b * N;
+    int* moff = moff_all + (size_t)b * (N + 1);
+    int* recx = recx_all + (size_t)b * N;
+    int* recy = recy_all + (size_t)b * N;
+    double* rech = rech_all + (size_t)b * N;
+
+    for (int i = tid; i < n; i += nthr) {
+        const int j = rmj[i];
+        par[i] = (unsigned)j < (unsigned)n ? j : (i + 1 < n ? i + 1 : 0);   // no finite distance in the row (NaN input): any other node
+    }
+    __syncthreads();
+    // a mutual pair keeps its lower node as root; every other node emits its edge
+    for (int i = tid; i < n; i += nthr) { const int j = par[i]; aux[i] = (par[j] == i && i < j) ? 0 : 1; }
+    __syncthreads();
+    const int rec0 = N - n;
+    {
+        // positions of the emitted records (scan of the emit flags), written before par is modified
+        for (int i = tid; i < n; i += nthr) cnt[i] = aux[i];
+        __syncthreads();
+        block_exclusive_scan(cnt, n, wsum);
+        for (int i = tid; i < n; i += nthr) {
+            if (aux[i]) {
+                const int j = par[i], pos = rec0 + cnt[i];
+                recx[pos] = rep_in ? rep_in[i] : i;
+                recy[pos] = rep_in ? rep_in[j] : j;
+                rech[pos] = rmw[i];
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < n; i += nthr) if (!aux[i]) par[i] = i;
+    __syncthreads();
+    // pointer jumping to the roots (in place: a value read mid-update is still an ancestor)
+    for (int it = 0; it < 14; ++it) {
+        int changed = 0;
+        for (int i = tid; i < n; i += nthr) {
+            const int p = par[i], g = par[p];
+            if (g != p) changed = 1;
+            par[i] = g;
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+    // new ids of the roots, ascending
+    for (int i = tid; i < n; i += nthr) { aux[i] = par[i] == i ? 1 : 0; cnt[i] = 0; }
+    __syncthreads();
+    const int n2 = block_exclusive_scan(aux, n, wsum);
+    for (int i = tid; i < n; i += nthr) {
+        const int c = aux[par[i]];
+        atomicAdd(&cnt[c], 1);
+        if (par[i] == i) rep_out[c] = rep_in ? rep_in[i] : i;
+    }
+    __syncthreads();
+    block_exclusive_scan(cnt, n2, wsum);
+    for (int c = tid; c < n2; c += nthr) moff[c] = cnt[c];
+    if (tid == 0) { moff[n2] = n; nd[slot + 1] = n2; }
+    __syncthreads();
+    for (int i = tid; i < n; i += nthr) memb[atomicAdd(&cnt[aux[par[i]]], 1)] = i;     // order inside a component is free: only minima follow
+}
+
+// Contract: out[A][C] = min over members i of A, j of C of in[i][j]; plus the row arg-min of out for the next
+// round.  grid (rows of out, B), one CTA per component A; the diagonal of out is never read.
+__global__ void __launch_bounds__(256)
+boruvka_contract_kernel(const double* __restrict__ in_all, size_t in_stride, int in_pitch, double* __restrict__ out_all,
+                        size_t out_stride, int out_pitch, const int* __restrict__ nd_all, int slot,
+                        const int* __restrict__ memb_all, const int* __restrict__ moff_all, double* __restrict__ rmw_all,
+                        int* __restrict__ rmj_all, int N) {
+    extern __shared__ __align__(16) double colmin[];               // [n]
+    __shared__ uint4 scratch[64];
+    const int b = blockIdx.y, A = blockIdx.x;
+    const int n = node_count(nd_all, b, slot, N), n2 = nd_all[b * 8 + slot + 1];
+    if (n <= 1 || A >= n2) return;
+    const double* in = in_all + (size_t)b * in_stride;
+    double* out = out_all + (size_t)b * out_stride + (size_t)A * out_pitch;
+    const int* memb = memb_all + (size_t)b * N;
+    const int* moff = moff_all + (size_t)b * (N + 1);
+    const int m0 = moff[A], m1 = moff[A + 1];
+    for (int j0 = threadIdx.x; j0 < n; j0 += 4 * blockDim.x) {
+        double acc[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
+        for (int t = m0; t < m1; ++t) {
+            const double* row = in + (size_t)memb[t] * in_pitch;
+            double v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int j = j0 + u * blockDim.x; v[u] = j < n ? __ldcs(row + j) : INFINITY; }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u] = fmin(acc[u], v[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int j = j0 + u * blockDim.x; if (j < n) colmin[j] = acc[u]; }
+    }
+    __syncthreads();
+    double bv = INFINITY;
+    int bi = kNoIdx;
+    for (int C = threadIdx.x; C < n2; C += blockDim.x) {
+        double m = INFINITY;
+        for (int t = moff[C]; t < moff[C + 1]; ++t) m = fmin(m, colmin[memb[t]]);
+        out[C] = m;
+        if (C != A && m < bv) { bv = m; bi = C; }
+    }
+    unsigned phase = 0u;
+    const LexKey r = block_lexmin(bv, bi, scratch, phase);
+    if (threadIdx.x == 0) { rmw_all[(size_t)b * N + A] = key_value(r); rmj_all[(size_t)b * N + A] = r.idx; }
 }
 
 static int next_pow2(int v) {
@@ -291,14 +608,65 @@ static int next_pow2(int v) {
 
 }  // namespace hpcs
 
+namespace hpcs {
+
+constexpr int kMaxRounds = 3;
+
+// Workspace layout shared by hpcs_linkage_workspace_bytes and hpcs_linkage_f64 (arrays of B clouds each).
+struct LinkWs {
+    int rounds;                       // Boruvka rounds before Prim (single linkage, N >= 256), else 0
+    int pitch[kMaxRounds + 1];        // row pitch (= node capacity) of matrix r
+    size_t off_m[kMaxRounds + 1], off_recx, off_recy, off_rech, off_rmw, off_rmj, off_memb, off_moff, off_nd, off_tie;
+    size_t off_rep[kMaxRounds + 1];
+    size_t total;
+};
+
+static LinkWs link_ws(int B, int N, int method) {
+    LinkWs L{};
+    L.rounds = (method == 0 && N >= 256) ? (N <= 1024 ? 2 : 3) : 0;
+    L.pitch[0] = N;
+    for (int r = 1; r <= kMaxRounds; ++r) L.pitch[r] = (L.pitch[r - 1] / 2 + 3) / 4 * 4;    // a round at least halves the nodes
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t at = off; off += align_up(bytes, 256); return at; };
+    for (int r = 0; r <= L.rounds; ++r) L.off_m[r] = take((size_t)B * L.pitch[r] * L.pitch[r] * sizeof(double));
+    L.off_recx = take((size_t)B * N * sizeof(int));
+    L.off_recy = take((size_t)B * N * sizeof(int));
+    L.off_rech = take((size_t)B * N * sizeof(double));
+    if (L.rounds) {
+        L.off_rmw = take((size_t)B * N * sizeof(double));
+        L.off_rmj = take((size_t)B * N * sizeof(int));
+        L.off_memb = take((size_t)B * N * sizeof(int));
+        L.off_moff = take((size_t)B * (N + 1) * sizeof(int));
+        L.off_nd = take((size_t)B * 8 * sizeof(int));
+        L.off_tie = take((size_t)B * sizeof(int));
+        for (int r = 1; r <= L.rounds; ++r) L.off_rep[r] = take((size_t)B * L.pitch[r] * sizeof(int));
+    }
+    L.total = off;
+    return L;
+}
+
+template <int METHOD>
+static void launch_linkage(int cpt, int B, int threads, size_t smem, cudaStream_t st, double* dm, size_t dm_stride, int pitch,
+                           const int* nd, int nd_slot, const int* rep, int rep_stride, int N, int NP2, int* recx, int* recy,
+                           double* rech, double* Z, int* tie_flag, const int* gate) {
+    auto go = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<B, threads, smem, st>>>(dm, dm_stride, pitch, nd, nd_slot, rep, rep_stride, N, NP2, recx, recy, rech, Z, tie_flag, gate);
+    };
+    if (cpt == 1) go(linkage_kernel<METHOD, 1>);
+    else if (cpt == 2) go(linkage_kernel<METHOD, 2>);
+    else if (cpt == 4) go(linkage_kernel<METHOD, 4>);
+    else go(linkage_kernel<METHOD, 8>);
+}
+
+}  // namespace hpcs
+
 extern "C" {
 
 size_t hpcs_linkage_workspace_bytes(int B, int N, int D, int method) {
-    (void)D; (void)method;
+    (void)D;
     if (B <= 0 || N <= 1) return 0;
-    using hpcs::align_up;
-    return align_up((size_t)B * N * N * sizeof(double), 256) + 2 * align_up((size_t)B * N * sizeof(int), 256) +
-           align_up((size_t)B * N * sizeof(double), 256);
+    return hpcs::link_ws(B, N, method).total;
 }
 
 int hpcs_linkage_f64(const float* leaves, int B, int N, int D, int method, double* Z, void* ws,
@@ -311,29 +679,63 @@ int hpcs_linkage_f64(const float* leaves, int B, int N, int D, int method, doubl
     const int NP2 = next_pow2(N - 1 > 1 ? N - 1 : 2);
     const size_t smem_link = (size_t)12 * NP2 + (size_t)16 * N;
     if (smem_link > 227 * 1024) return fail(HPCS_ERR_ARG, "linkage: N=%d too large (max 8192)", N);
-    const size_t smem_pd = ((size_t)2 * kTile * D + 2 * kTile + kTile * 33) * sizeof(double);
+    const size_t smem_pd = ((size_t)2 * D * kPLD + 2 * kPT) * sizeof(double);
     if (smem_pd > 200 * 1024) return fail(HPCS_ERR_ARG, "linkage: D=%d too large", D);
     cudaStream_t st = as_stream(stream);
+    const LinkWs L = link_ws(B, N, method);
     char* w = static_cast<char*>(ws);
-    double* dm = reinterpret_cast<double*>(w);  w += align_up((size_t)B * N * N * sizeof(double), 256);
-    int* recx = reinterpret_cast<int*>(w);      w += align_up((size_t)B * N * sizeof(int), 256);
-    int* recy = reinterpret_cast<int*>(w);      w += align_up((size_t)B * N * sizeof(int), 256);
-    double* rech = reinterpret_cast<double*>(w);
+    double* dm = reinterpret_cast<double*>(w + L.off_m[0]);
+    int* recx = reinterpret_cast<int*>(w + L.off_recx);
+    int* recy = reinterpret_cast<int*>(w + L.off_recy);
+    double* rech = reinterpret_cast<double*>(w + L.off_rech);
 
-    const int T = (N + kTile - 1) / kTile;
+    const int T = (N + kPT - 1) / kPT;
     cudaFuncSetAttribute(pdist_cosine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pd);
     pdist_cosine_kernel<<<dim3(T * (T + 1) / 2, B), 256, smem_pd, st>>>(leaves, N, D, dm);
     int rc = check_launch("pdist_cosine_kernel");
     if (rc) return rc;
-    const int threads = N >= 1024 ? 1024 : (N + 31) / 32 * 32;
-    if (method == 0) {
-        cudaFuncSetAttribute(linkage_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_link);
-        linkage_kernel<0><<<B, threads, smem_link, st>>>(dm, N, NP2, recx, recy, rech, Z);
-    } else {
-        cudaFuncSetAttribute(linkage_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_link);
-        linkage_kernel<1><<<B, threads, smem_link, st>>>(dm, N, NP2, recx, recy, rech, Z);
+    // direct form: columns per thread 1 up to 512 points, else the smallest of 2/4/8 that covers N with <= 1024 threads
+    const int cpt0 = N <= 512 ? 1 : N <= 2048 ? 2 : N <= 4096 ? 4 : 8;
+    const int threads0 = ((N + cpt0 - 1) / cpt0 + 31) / 32 * 32;
+    const size_t stride0 = (size_t)N * N;
+    if (L.rounds == 0) {
+        if (method == 0) launch_linkage<0>(cpt0, B, threads0, smem_link, st, dm, stride0, N, nullptr, 0, nullptr, 0, N, NP2, recx, recy, rech, Z, nullptr, nullptr);
+        else launch_linkage<1>(cpt0, B, threads0, smem_link, st, dm, stride0, N, nullptr, 0, nullptr, 0, N, NP2, recx, recy, rech, Z, nullptr, nullptr);
+        return check_launch("linkage_kernel");
     }
-    return check_launch("linkage_kernel");
+    // ---- single linkage: Boruvka rounds, Prim on the contracted matrix, exact redo of clouds with tied heights ----
+    double* rmw = reinterpret_cast<double*>(w + L.off_rmw);
+    int* rmj = reinterpret_cast<int*>(w + L.off_rmj);
+    int* memb = reinterpret_cast<int*>(w + L.off_memb);
+    int* moff = reinterpret_cast<int*>(w + L.off_moff);
+    int* nd = reinterpret_cast<int*>(w + L.off_nd);
+    int* tie = reinterpret_cast<int*>(w + L.off_tie);
+    boruvka_rowmin_kernel<<<dim3(N, B), 256, 0, st>>>(dm, stride0, N, nd, 0, rmw, rmj, N);
+    if ((rc = check_launch("boruvka_rowmin_kernel"))) return rc;
+    for (int r = 0; r < L.rounds; ++r) {
+        const int cap = L.pitch[r], cap2 = L.pitch[r + 1];
+        const int* rep_in = r ? reinterpret_cast<int*>(w + L.off_rep[r]) : nullptr;
+        int* rep_out = reinterpret_cast<int*>(w + L.off_rep[r + 1]);
+        const size_t smem_hook = (size_t)3 * cap * sizeof(int);
+        cudaFuncSetAttribute(boruvka_hook_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_hook);
+        boruvka_hook_kernel<<<B, cap >= 1024 ? 1024 : (cap + 31) / 32 * 32, smem_hook, st>>>(rmw, rmj, nd, r, rep_in, cap, rep_out, cap2, memb, moff,
+                                                                                           recx, recy, rech, N);
+        if ((rc = check_launch("boruvka_hook_kernel"))) return rc;
+        const double* in = reinterpret_cast<double*>(w + L.off_m[r]);
+        double* out = reinterpret_cast<double*>(w + L.off_m[r + 1]);
+        const size_t smem_con = (size_t)cap * sizeof(double);
+        cudaFuncSetAttribute(boruvka_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_con);
+        boruvka_contract_kernel<<<dim3(cap2, B), 256, smem_con, st>>>(in, (size_t)cap * cap, cap, out, (size_t)cap2 * cap2, cap2, nd, r, memb, moff, rmw, rmj, N);
+        if ((rc = check_launch("boruvka_contract_kernel"))) return rc;
+    }
+    const int capR = L.pitch[L.rounds];
+    const int threadsR = N >= 2048 ? 1024 : 512;
+    const int cptR = (capR + threadsR - 1) / threadsR <= 1 ? 1 : (capR + threadsR - 1) / threadsR <= 2 ? 2 : (capR + threadsR - 1) / threadsR <= 4 ? 4 : 8;
+    launch_linkage<0>(cptR, B, threadsR, smem_link, st, reinterpret_cast<double*>(w + L.off_m[L.rounds]), (size_t)capR * capR, capR, nd, L.rounds,
+                      reinterpret_cast<int*>(w + L.off_rep[L.rounds]), capR, N, NP2, recx, recy, rech, Z, tie, nullptr);
+    if ((rc = check_launch("linkage_kernel"))) return rc;
+    launch_linkage<0>(cpt0, B, threads0, smem_link, st, dm, stride0, N, nullptr, 0, nullptr, 0, N, NP2, recx, recy, rech, Z, nullptr, tie);
+    return check_launch("linkage_kernel(redo)");
 }
 
 }  // extern "C"

@@ -17,7 +17,7 @@ from . import _lib
 from .hyperbolic import normalize_project
 
 METHODS = {"single": 0, "complete": 1}
-_WS_BUDGET = 24 << 30          # bytes of fp64 distance matrices resident at once
+_WS_FRACTION = 0.4             # share of the device memory the fp64 distance matrices of one chunk may take
 
 
 def linkage_from_leaves(leaves: torch.Tensor, method: str = "complete") -> torch.Tensor:
@@ -34,7 +34,9 @@ def linkage_from_leaves(leaves: torch.Tensor, method: str = "complete") -> torch
         raise ValueError("need at least two leaves")
     Z = torch.empty((B, N - 1, 4), dtype=torch.float64, device=dev)
     per_cloud = lib.hpcs_linkage_workspace_bytes(1, N, D, METHODS[method])
-    chunk = max(1, min(B, _WS_BUDGET // max(per_cloud, 1)))
+    budget = int(torch.cuda.get_device_properties(dev).total_memory * _WS_FRACTION)
+    chunk = max(1, min(B, budget // max(per_cloud, 1)))
+    chunk = -(-B // -(-B // chunk))                     # equal chunks (every launch is one CTA chain per cloud)
     for b0 in range(0, B, chunk):
         nb = min(chunk, B - b0)
         ws = _lib.workspace(lib.hpcs_linkage_workspace_bytes(nb, N, D, METHODS[method]), dev)

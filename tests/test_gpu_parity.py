@@ -393,7 +393,7 @@ def _check_Z(Z, ref):
 
 
 @pytest.mark.parametrize("method", ["single", "complete"])
-@pytest.mark.parametrize("N,D", [(96, 32), (200, 32), (1024, 32), (150, 5), (64, 50)])
+@pytest.mark.parametrize("N,D", [(96, 32), (200, 32), (1024, 32), (150, 5), (64, 50), (300, 32), (777, 7), (1500, 32)])
 def test_linkage_bit_exact_vs_scipy(hb, method, N, D):
     from scipy.cluster.hierarchy import linkage
     gen = torch.Generator().manual_seed(N + D)
@@ -420,6 +420,27 @@ def test_linkage_duplicates_and_single_cloud_api(hb):
         assert isinstance(Z, np.ndarray) and Z.dtype == np.float64 and Z.shape == (119, 4)
         leaves = hb.normalize_project(dev(x), scale).cpu().numpy()
         _check_Z(Z, linkage(leaves, method=method, metric="cosine"))
+
+
+def test_linkage_boruvka_path_ties_and_clusters(hb):
+    """N >= 256 single linkage runs Boruvka rounds + Prim on the contracted matrix; a cloud whose merge heights tie
+    (duplicate points here) must come out of the exact redo identical to scipy, next to clouds that do not tie."""
+    from scipy.cluster.hierarchy import linkage
+    gen = torch.Generator().manual_seed(11)
+    cen = torch.randn(5, 32, generator=gen)
+    x = O.expmap0(cen[torch.randint(0, 5, (4, 400), generator=gen)] + 0.2 * torch.randn(4, 400, 32, generator=gen))
+    x[1, 10] = x[1, 3]; x[1, 377] = x[1, 3]; x[1, 50] = x[1, 51]              # cloud 1: exact distance ties
+    x[3, 200:220] = x[3, 100:120]                                            # cloud 3: twenty duplicate pairs
+    scale = dev(torch.tensor([0.3]))
+    Z, leaves = hb.decode_linkage_batch(dev(x), scale, "single", return_leaves=True)
+    for b in range(4):
+        _check_Z(Z[b].cpu().numpy(), linkage(leaves[b].cpu().numpy(), method="single", metric="cosine"))
+    # two-point and three-point clouds, and a size just above the Boruvka threshold
+    for n in (2, 3, 256, 257):
+        xs = O.expmap0(torch.randn(2, n, 32, generator=gen))
+        Z, leaves = hb.decode_linkage_batch(dev(xs), scale, "single", return_leaves=True)
+        for b in range(2):
+            _check_Z(Z[b].cpu().numpy(), linkage(leaves[b].cpu().numpy(), method="single", metric="cosine"))
 
 
 @pytest.mark.parametrize("key", ["96", "200", "clu"])
