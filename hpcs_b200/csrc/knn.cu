@@ -26,6 +26,10 @@ int knn_tc_run(const float* x, int B, int D, int N, int k, int64_t* idx, float* 
                cudaStream_t st);
 int knn_tc_fallback_rows(const void* ws, int B, int D, int N, int k, cudaStream_t st, int* out_host);
 
+// coordinate kNN, warp per row (knn_d3.cu)
+bool knn_d3_applicable(int D, int N, int k);
+int knn_d3_run(const float* x, int B, int N, int k, int64_t* idx, float* val, cudaStream_t st);
+
 constexpr int kKnnWarps = 8;
 constexpr int kRowQueue = 48;          // per-thread FIFO depth of the row-parallel kernel (flush when > 16 pending)
 
@@ -413,6 +417,7 @@ int hpcs_knn_f32(const float* x, int B, int D, int N, int k, int64_t* idx, float
     int rc = knn_check(x, B, D, N, k, idx, ws, ws_bytes);
     if (rc) return rc;
     if (knn_tc_applicable(D, N, k)) return knn_tc_run(x, B, D, N, k, idx, val, ws, ws_bytes, as_stream(stream));
+    if (knn_d3_applicable(D, N, k)) return knn_d3_run(x, B, N, k, idx, val, as_stream(stream));
     return knn_ffma(x, B, D, N, k, idx, val, ws, as_stream(stream));
 }
 

@@ -26,13 +26,15 @@ constexpr int kPT = 64;           // pdist tile edge
 constexpr int kPLD = kPT + 2;     // shared-memory row pitch in doubles (keeps 16-byte alignment, spreads banks)
 
 // fp64 cosine distance matrix, bit-identical to scipy's pdist(., 'cosine') on the same fp32 rows.
-// grid: (T*(T+1)/2 upper 64x64 tiles, B); block 256 = 16 x 16 threads, 4 x 4 outputs each: rows ty*4+ii, columns
-// tx+16*jj.  dm[b][i][j] full symmetric, zero diagonal.
+// grid: (T*(T+1)/2 upper 64x64 tiles, B); block (64/MR) x 16 threads, MR x 4 outputs each: rows ty*MR+ii, columns
+// tx+16*jj.  The kernel is bound by shared-memory operand delivery (128 B/clk/SM against 64 DFMA lanes/clk/SM), so the
+// taller micro-tile (MR = 8: 12 doubles loaded per 32 DFMA) would help if occupancy held; at 178 registers it does not.  dm[b][i][j] full symmetric, zero diagonal.
 // scipy sums a dot product as two running sums (even / odd elements, separate multiply and add), added at the end,
 // an odd tail element last.  Every operand here is an fp32 value widened to fp64, so a product has at most 48
 // significant bits and is exact in fp64: fma(a, b, acc) rounds the same real number as add(mul(a, b), acc) and gives
 // the same bits.  The kernel therefore runs on DFMA (half the fp64 instructions) without changing any result.
-__global__ void __launch_bounds__(256)
+template <int MR>                               // rows per thread: 64 / MR x 16 threads, MR x 4 outputs each
+__global__ void __launch_bounds__(1024 / MR)
 pdist_cosine_kernel(const float* __restrict__ leaves, int N, int D, double* __restrict__ dm) {
     extern __shared__ __align__(16) double sm[];
     double* as = sm;                          // [D][kPLD] rows of the i-tile, feature-major
@@ -66,26 +68,27 @@ pdist_cosine_kernel(const float* __restrict__ leaves, int N, int D, double* __re
         (threadIdx.x >= kPT ? nb : na)[threadIdx.x & (kPT - 1)] = __dsqrt_rn(s);
     }
     const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    double ev[4][4], od[4][4];
+    double ev[MR][4], od[MR][4];
 #pragma unroll
-    for (int ii = 0; ii < 4; ++ii)
+    for (int ii = 0; ii < MR; ++ii)
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) { ev[ii][jj] = 0.0; od[ii][jj] = 0.0; }
-    const double* ap = as + ty * 4;
+    const double* ap = as + ty * MR;
     const double* bp = bs + tx;
     int q = 0;
     for (; q + 1 < D; q += 2) {
-        const double2 a01 = *reinterpret_cast<const double2*>(ap + q * kPLD);
-        const double2 a23 = *reinterpret_cast<const double2*>(ap + q * kPLD + 2);
-        const double2 c01 = *reinterpret_cast<const double2*>(ap + (q + 1) * kPLD);
-        const double2 c23 = *reinterpret_cast<const double2*>(ap + (q + 1) * kPLD + 2);
-        const double a[4] = {a01.x, a01.y, a23.x, a23.y};
-        const double c[4] = {c01.x, c01.y, c23.x, c23.y};
-        double be[4], bo[4];
+        double a[MR], c[MR], be[4], bo[4];
+#pragma unroll
+        for (int ii = 0; ii < MR; ii += 2) {
+            const double2 t0 = *reinterpret_cast<const double2*>(ap + q * kPLD + ii);
+            const double2 t1 = *reinterpret_cast<const double2*>(ap + (q + 1) * kPLD + ii);
+            a[ii] = t0.x; a[ii + 1] = t0.y;
+            c[ii] = t1.x; c[ii + 1] = t1.y;
+        }
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) { be[jj] = bp[q * kPLD + 16 * jj]; bo[jj] = bp[(q + 1) * kPLD + 16 * jj]; }
 #pragma unroll
-        for (int ii = 0; ii < 4; ++ii)
+        for (int ii = 0; ii < MR; ++ii)
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
                 ev[ii][jj] = fma(a[ii], be[jj], ev[ii][jj]);
@@ -93,45 +96,37 @@ pdist_cosine_kernel(const float* __restrict__ leaves, int N, int D, double* __re
             }
     }
     __syncthreads();                           // norms written
-    double res[4][4];
+    double* db = dm + (size_t)b * N * N;
+    const bool vec_ok = (N & 3) == 0;          // rows start 32-byte aligned
+    const int gi0 = bi * kPT + ty * MR;
 #pragma unroll
-    for (int ii = 0; ii < 4; ++ii) {
-        const int i = ty * 4 + ii;
+    for (int ii = 0; ii < MR; ++ii) {
+        const int i = ty * MR + ii;
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
             const int j = tx + 16 * jj;
             double s = __dadd_rn(ev[ii][jj], od[ii][jj]);
             if (D & 1) s = fma(as[(D - 1) * kPLD + i], bs[(D - 1) * kPLD + j], s);
-            double c = __ddiv_rn(s, __dmul_rn(na[i], nb[j]));
-            if (fabs(c) > 1.0) c = copysign(1.0, c);
-            res[ii][jj] = (bi * kPT + i == bj * kPT + j) ? 0.0 : __dsub_rn(1.0, c);
+            double cs = __ddiv_rn(s, __dmul_rn(na[i], nb[j]));
+            if (fabs(cs) > 1.0) cs = copysign(1.0, cs);
+            const double r = (bi * kPT + i == bj * kPT + j) ? 0.0 : __dsub_rn(1.0, cs);
+            ev[ii][jj] = r;                    // results replace the accumulators
+            const int gj = bj * kPT + j;
+            if (gi0 + ii < N && gj < N) db[(size_t)(gi0 + ii) * N + gj] = r;      // 16 lanes x 8 B contiguous
         }
     }
-    double* db = dm + (size_t)b * N * N;
-    const bool vec_ok = (N & 3) == 0;          // rows start 32-byte aligned
-#pragma unroll
-    for (int ii = 0; ii < 4; ++ii) {
-        const int gi = bi * kPT + ty * 4 + ii;
-        if (gi >= N) continue;
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-            const int gj = bj * kPT + tx + 16 * jj;
-            if (gj < N) db[(size_t)gi * N + gj] = res[ii][jj];          // 16 lanes x 8 B contiguous
-        }
-    }
-    if (bi != bj) {                            // mirrored tile: this thread's 4 rows are 4 consecutive columns there
-        const int gi0 = bi * kPT + ty * 4;
+    if (bi != bj) {                            // mirrored tile: this thread's MR rows are MR consecutive columns there
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
             const int gj = bj * kPT + tx + 16 * jj;
             if (gj >= N) continue;
             double* dst = db + (size_t)gj * N + gi0;
-            if (vec_ok && gi0 + 3 < N) {
-                *reinterpret_cast<double2*>(dst) = make_double2(res[0][jj], res[1][jj]);
-                *reinterpret_cast<double2*>(dst + 2) = make_double2(res[2][jj], res[3][jj]);
+            if (vec_ok && gi0 + MR - 1 < N) {
+#pragma unroll
+                for (int ii = 0; ii < MR; ii += 2) *reinterpret_cast<double2*>(dst + ii) = make_double2(ev[ii][jj], ev[ii + 1][jj]);
             } else {
 #pragma unroll
-                for (int ii = 0; ii < 4; ++ii) if (gi0 + ii < N) dst[ii] = res[ii][jj];
+                for (int ii = 0; ii < MR; ++ii) if (gi0 + ii < N) dst[ii] = ev[ii][jj];
             }
         }
     }
@@ -210,9 +205,9 @@ linkage_kernel(double* dm_all, size_t dm_stride, int pitch, const int* __restric
     // shared-memory regions
     double* A = reinterpret_cast<double*>(raw);                      // [NP2]  sort keys
     int* ordv = reinterpret_cast<int*>(raw + (size_t)8 * NP2);       // [NP2]  sort payload
-    unsigned char* regC = raw + (size_t)12 * NP2;                    // 8N bytes: NN chain, later the sorted (x,y)
-    int* csize = reinterpret_cast<int*>(regC + (size_t)8 * N);       // [2N]
-    int* parent = reinterpret_cast<int*>(raw);                       // [N] overlays A after the sort
+    const size_t sort_bytes = ((size_t)12 * (NP2 > N ? NP2 : N) + 15) / 16 * 16;   // >= 12N so that node[N] (16N bytes) ends before usize
+    int* csize = reinterpret_cast<int*>(raw + sort_bytes);           // [2N] relabel scratch, directly behind the sort arrays
+    unsigned char* regC = raw + sort_bytes + (size_t)8 * N;          // 8N bytes: NN chain, later the sorted (x,y)
 
     unsigned alive = 0u, phase = 0u;
 #pragma unroll
@@ -364,47 +359,53 @@ linkage_kernel(double* dm_all, size_t dm_stride, int pitch, const int* __restric
     __syncthreads();
     if (tie_flag && tid == 0) tie_flag[b] = tie_s;
     // ---- union-find relabel (scipy `label`): ids of the two clusters a merge joins, size of the union --------------
-    // The forest lives on the N leaves with union by size, and cid[root] carries the scipy id of the cluster (leaf id,
-    // or N + i for the cluster made by sorted merge i).  Single-linkage dendrograms are chains -- one big cluster
-    // swallowing points -- and union by size keeps the big cluster's root fixed, so a find is one or two hops instead
-    // of a walk up a chain of merge nodes.
-    int* cid = csize + N;                                             // [N] (csize is [2N]: second half)
-    for (int v = tid; v < N; v += nthr) { parent[v] = v; csize[v] = 1; cid[v] = v; }
+    // The forest lives on the N leaves with union by size, one packed record per leaf {parent, size, cluster id} so
+    // that a find that lands on a root has everything after ONE 16-byte load; the cluster id is the leaf id, or N + i
+    // for the cluster made by sorted merge i.  Single-linkage dendrograms are chains -- one big cluster swallowing
+    // points -- and union by size keeps the big cluster's root fixed: a find is one or two hops.  The loop is a serial
+    // dependency chain, so it runs on one thread with as few instructions as possible; results are staged in shared
+    // memory (ids over the consumed exy records) and written out by the whole CTA afterwards.
+    int4* node = reinterpret_cast<int4*>(raw);                        // [N] overlays A, ordv and the head of csize
+    int* usize = csize + N;                                           // [N] size of the union made by merge i (csize is [2N])
+    for (int v = tid; v < N; v += nthr) node[v] = make_int4(v, 1, v, 0);
     __syncthreads();
-    if (tid < 32) {
-        // lanes 0 and 1 chase the two roots of a merge at the same time (they are in different trees)
-        const int lane = tid;
+    if (tid == 0) {
         int2 e = exy[0];
         for (int i = 0; i < M; ++i) {
-            const int2 nxt = i + 1 < M ? exy[i + 1] : e;             // next record: independent of the chase below
-            int r = lane == 1 ? e.y : e.x;
-            int sz = 0, id = 0;
-            if (lane < 2) {
-                while (true) {
-                    const int p = parent[r];
-                    if (p == r) break;
-                    const int g = parent[p];
-                    parent[r] = g;
-                    r = g;
-                }
-                sz = csize[r];
-                id = cid[r];
+            const int2 nxt = exy[i + 1 < M ? i + 1 : i];              // next record: independent of the chase below
+            int rx = e.x, ry = e.y;
+            int4 nx = node[rx], ny = node[ry];
+            while (nx.x != rx) {                                      // path halving; stops one hop early at a root parent
+                const int p = nx.x;
+                const int4 np = node[p];
+                if (np.x == p) { rx = p; nx = np; break; }
+                node[rx].x = np.x;
+                rx = np.x;
+                nx = node[rx];
             }
-            const int rx = __shfl_sync(kFull, r, 0), ry = __shfl_sync(kFull, r, 1);
-            const int sx = __shfl_sync(kFull, sz, 0), sy = __shfl_sync(kFull, sz, 1);
-            const int ix = __shfl_sync(kFull, id, 0), iy = __shfl_sync(kFull, id, 1);
-            if (lane == 0) {
-                const int big = sx >= sy ? rx : ry, small = sx >= sy ? ry : rx;
-                parent[small] = big;
-                csize[big] = sx + sy;
-                cid[big] = N + i;
-                Z[(size_t)i * 4 + 0] = (double)(ix < iy ? ix : iy);
-                Z[(size_t)i * 4 + 1] = (double)(ix < iy ? iy : ix);
-                Z[(size_t)i * 4 + 3] = (double)(sx + sy);
+            while (ny.x != ry) {
+                const int p = ny.x;
+                const int4 np = node[p];
+                if (np.x == p) { ry = p; ny = np; break; }
+                node[ry].x = np.x;
+                ry = np.x;
+                ny = node[ry];
             }
-            __syncwarp();
+            const bool xbig = nx.y >= ny.y;
+            const int big = xbig ? rx : ry, small = xbig ? ry : rx;
+            node[small].x = big;
+            node[big] = make_int4(big, nx.y + ny.y, N + i, 0);
+            exy[i] = make_int2(min(nx.z, ny.z), max(nx.z, ny.z));
+            usize[i] = nx.y + ny.y;
             e = nxt;
         }
+    }
+    __syncthreads();
+    for (int i = tid; i < M; i += nthr) {
+        const int2 ids = exy[i];
+        Z[(size_t)i * 4 + 0] = (double)ids.x;
+        Z[(size_t)i * 4 + 1] = (double)ids.y;
+        Z[(size_t)i * 4 + 3] = (double)usize[i];
     }
 }
 
@@ -573,18 +574,23 @@ boruvka_contract_kernel(const double* __restrict__ in_all, size_t in_stride, int
     const int* memb = memb_all + (size_t)b * N;
     const int* moff = moff_all + (size_t)b * (N + 1);
     const int m0 = moff[A], m1 = moff[A + 1];
-    for (int j0 = threadIdx.x; j0 < n; j0 += 4 * blockDim.x) {
-        double acc[4] = {INFINITY, INFINITY, INFINITY, INFINITY};
-        for (int t = m0; t < m1; ++t) {
-            const double* row = in + (size_t)memb[t] * in_pitch;
-            double v[4];
+    for (int j0 = threadIdx.x; j0 < n; j0 += 2 * blockDim.x) {
+        double acc[2] = {INFINITY, INFINITY};
+        for (int t = m0; t < m1; t += 4) {                             // 4 member rows x 2 columns in flight per thread
+            double v[4][2];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) { const int j = j0 + u * blockDim.x; v[u] = j < n ? __ldcs(row + j) : INFINITY; }
+            for (int w = 0; w < 4; ++w) {
+                const double* row = in + (size_t)memb[min(t + w, m1 - 1)] * in_pitch;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) acc[u] = fmin(acc[u], v[u]);
+                for (int u = 0; u < 2; ++u) { const int j = j0 + u * blockDim.x; v[w][u] = j < n ? __ldcs(row + j) : INFINITY; }
+            }
+#pragma unroll
+            for (int w = 0; w < 4; ++w)
+#pragma unroll
+                for (int u = 0; u < 2; ++u) acc[u] = fmin(acc[u], v[w][u]);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) { const int j = j0 + u * blockDim.x; if (j < n) colmin[j] = acc[u]; }
+        for (int u = 0; u < 2; ++u) { const int j = j0 + u * blockDim.x; if (j < n) colmin[j] = acc[u]; }
     }
     __syncthreads();
     double bv = INFINITY;
@@ -677,7 +683,7 @@ int hpcs_linkage_f64(const float* leaves, int B, int N, int D, int method, doubl
     if (B > 65535) return fail(HPCS_ERR_ARG, "linkage: B > 65535");
     if (ws_bytes < hpcs_linkage_workspace_bytes(B, N, D, method)) return fail(HPCS_ERR_WORKSPACE, "linkage: workspace too small");
     const int NP2 = next_pow2(N - 1 > 1 ? N - 1 : 2);
-    const size_t smem_link = (size_t)12 * NP2 + (size_t)16 * N;
+    const size_t smem_link = ((size_t)12 * (NP2 > N ? NP2 : N) + 15) / 16 * 16 + (size_t)16 * N;
     if (smem_link > 227 * 1024) return fail(HPCS_ERR_ARG, "linkage: N=%d too large (max 8192)", N);
     const size_t smem_pd = ((size_t)2 * D * kPLD + 2 * kPT) * sizeof(double);
     if (smem_pd > 200 * 1024) return fail(HPCS_ERR_ARG, "linkage: D=%d too large", D);
@@ -690,8 +696,9 @@ int hpcs_linkage_f64(const float* leaves, int B, int N, int D, int method, doubl
     double* rech = reinterpret_cast<double*>(w + L.off_rech);
 
     const int T = (N + kPT - 1) / kPT;
-    cudaFuncSetAttribute(pdist_cosine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pd);
-    pdist_cosine_kernel<<<dim3(T * (T + 1) / 2, B), 256, smem_pd, st>>>(leaves, N, D, dm);
+    // MR = 4 measured best on B200 (N=1024/8192, B=64: 333 us / 20.0 ms against 399 us / 23.0 ms for MR = 8 at half the warps)
+    cudaFuncSetAttribute(pdist_cosine_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pd);
+    pdist_cosine_kernel<4><<<dim3(T * (T + 1) / 2, B), 256, smem_pd, st>>>(leaves, N, D, dm);
     int rc = check_launch("pdist_cosine_kernel");
     if (rc) return rc;
     // direct form: columns per thread 1 up to 512 points, else the smallest of 2/4/8 that covers N with <= 1024 threads

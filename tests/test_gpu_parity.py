@@ -84,6 +84,31 @@ def test_knn_tensor_core_path_bit_exact(hb, B, D, N, k, kind):
         assert stats["fallback_rows"] <= B * N // 100          # the candidate stage decides almost every row itself
 
 
+@pytest.mark.parametrize("B,N,k,kind", [(3, 1024, 20, "cloud"), (2, 1000, 32, "cloud"), (2, 33, 20, "cloud"), (2, 20, 20, "cloud"),
+                                        (1, 2048, 10, "cloud"), (2, 1500, 1, "cloud"), (2, 777, 20, "dups"), (2, 512, 20, "grid"),
+                                        (1, 1024, 20, "same")])
+def test_knn_d3_warp_kernel_bit_exact(hb, B, N, k, kind):
+    """D = 3, k <= 32, N <= 2048 runs knn_d3_kernel (warp per row, threshold selection): indices and value bits must
+    equal the canonical oracle and the all-FFMA kernels, also when exact ties push rows onto its slow path
+    (duplicated points, a lattice with many equal distances, all points identical)."""
+    gen = torch.Generator().manual_seed(B * 31 + N + k)
+    x = cloud(gen, B, N)
+    if kind == "dups":
+        x[:, :, N // 3:2 * (N // 3)] = x[:, :, :N // 3]                     # every third point twice
+        x[:, :, -40:] = x[:, :, :1]                                         # and one point 41 times
+    elif kind == "grid":
+        g = torch.arange(8.0)
+        x = torch.stack(torch.meshgrid(g, g, g, indexing="ij")).reshape(1, 3, 512).repeat(B, 1, 1).contiguous()
+    elif kind == "same":
+        x = torch.ones(B, 3, N) * 0.25
+    want_i, want_v = O.knn_canonical(x, k, return_values=True)
+    got_i, got_v = hb.knn(dev(x), k, return_values=True)
+    assert torch.equal(got_i.cpu(), want_i)
+    assert torch.equal(got_v.cpu().view(torch.int32), want_v.view(torch.int32))
+    ffma_i, ffma_v = hb.knn(dev(x), k, return_values=True, method="ffma")
+    assert torch.equal(got_i, ffma_i) and torch.equal(got_v.view(torch.int32), ffma_v.view(torch.int32))
+
+
 def test_knn_ties_lower_index_first(hb):
     x = torch.zeros(1, 3, 64)
     x[0, 0] = torch.arange(64).div(4, rounding_mode="floor").float()   # groups of 4 identical points
