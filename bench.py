@@ -5,10 +5,11 @@
 
 Workload (BASELINE.json configs[1]): ShapeNet-shaped training step, batch 32 clouds x 1024 points per
 GPU, k=20, 32-d embeddings, 50 mined triplets per anchor.  One "step" is one pass of the hot path over
-one batch of synthetic input:
-    kNN(D=3)  -> edge features C=1  fwd+bwd      (vn_dgcnn_partseg.py:65)
-    kNN(D=63) -> edge features C=21 fwd+bwd  x2  (vn_dgcnn_partseg.py:70,75)
+one batch of synthetic input, in the order a training step runs it:
+    kNN(D=3)  -> edge features C=1  forward      (vn_dgcnn_partseg.py:65)
+    kNN(D=63) -> edge features C=21 forward  x2  (vn_dgcnn_partseg.py:70,75)
     fused Poincare triplet loss fwd+bwd over 1.64 M mined triplets ('easy' filter in-kernel)
+    edge features backward x3 (last layer first)
 The dense VN/conv layers between these ops are outside the path, so the inputs of
 the 63-d layers, the upstream gradients of the edge features and the embeddings are synthetic tensors.
 Clouds are independent: ranks own disjoint batches (weak scaling); the only collective is the
@@ -181,14 +182,6 @@ def run_native(args):
     g2 = torch.randn(B, 2 * C_FEAT, 3, N_PTS, K_NN, device=dev, generator=gen)
     g3 = torch.randn(B, 2 * C_FEAT, 3, N_PTS, K_NN, device=dev, generator=gen)
 
-    def layer(x, g):
-        xr = x.detach().requires_grad_(True)
-        Bc, C, _, Np = xr.shape
-        idx = hb.knn(xr.detach().view(Bc, 3 * C, Np), K_NN)
-        y = hb.get_graph_feature(xr, K_NN, idx=idx)
-        (gx,) = torch.autograd.grad(y, xr, g)
-        return gx
-
     def loss_fwd_bwd(emb_in, tr):
         emb = emb_in.detach().requires_grad_(True)
         sc = scale.detach().requires_grad_(True)            # fresh leaves: keeps autograd on the capturing stream
@@ -197,14 +190,23 @@ def run_native(args):
         return loss, kept, ge, gs
 
     def step(inp, tr):
-        gx1 = layer(inp["pts"], g1)
-        gx2 = layer(inp["f1"], g2)
-        gx3 = layer(inp["f2"], g3)
+        """The order a training step runs these ops in: the three layers' kNN + edge features (forward), the loss
+        forward+backward on the embeddings, then the edge-feature backwards from the last layer to the first.  The
+        all-reduce of d loss / d scale (the path's only parameter) is issued as soon as the loss backward has produced
+        it and overlaps the edge backwards."""
+        xs = [inp[k].detach().requires_grad_(True) for k in ("pts", "f1", "f2")]
+        ys = []
+        for x in xs:
+            Bc, C, _, Np = x.shape
+            idx = hb.knn(x.detach().view(Bc, 3 * C, Np), K_NN)
+            ys.append(hb.get_graph_feature(x, K_NN, idx=idx))
         loss, kept, ge, gs = loss_fwd_bwd(inp["emb"], tr)
-        if world > 1:
-            dist.all_reduce(gs, op=dist.ReduceOp.SUM)           # d loss / d scale: the path's only parameter
+        work = dist.all_reduce(gs, op=dist.ReduceOp.SUM, async_op=True) if world > 1 else None
+        gxs = [torch.autograd.grad(y, x, g)[0] for y, x, g in zip(ys[::-1], xs[::-1], (g3, g2, g1))]
+        if work is not None:
+            work.wait()
             gs = gs / world
-        return loss, kept, gs, (gx1, gx2, gx3, ge)
+        return loss, kept, gs, (gxs[2], gxs[1], gxs[0], ge)
 
     def barrier():
         if world > 1:
@@ -301,82 +303,100 @@ def run_native(args):
     barrier()
 
     # ---- end-to-end from pinned host buffers ----------------------------------------------------------
-    # Every step uploads its inputs (points, layer inputs, embeddings, mined triplets as int32) from pinned host
-    # memory and downloads its result (loss, kept, d scale).  Two device
-    # buffer sets alternate, so the upload of step i+1 and the download of step i-1 overlap the compute
-    # of step i on separate streams; all of it is inside the timed region.
+    # Every step uploads its inputs from pinned host memory and downloads its result (loss, kept, d scale).  Two device
+    # buffer sets alternate, so the upload of step i+1 and the download of step i-1 overlap the compute of step i on
+    # separate streams; all of it is inside the timed region.  Two variants:
+    #   "device" (the headline e2e): points, both 63-d layer inputs, embeddings and the sampling plan (label-sorted point
+    #            order, 131 KB, + 1 KB of per-label segments, both derived from the labels on the host) go up;
+    #            the 1.64 M triplets are drawn on the GPU inside the step (hpcs_triplet_sample_i32);
+    #   "host":  as the reference does it -- triplets sampled on the host beforehand and uploaded (int32) every step.
     pin = {k: host[k].pin_memory() for k in ("pts", "f1", "f2", "emb")}
     trip_pin = tuple(t.to(torch.int32).pin_memory() for t in trip_host)       # int32 indices: half the upload
-    h2d_bytes = sum(v.numel() * v.element_size() for v in pin.values()) + sum(t.numel() * t.element_size() for t in trip_pin)
-    sets = []
-    for _ in range(2):
-        inp = {k: torch.empty_like(v, device=dev) for k, v in pin.items()}
-        tr = tuple(torch.empty_like(t, device=dev) for t in trip_pin)
-        for k in pin:
-            inp[k].copy_(pin[k])
-        for a_, b_ in zip(tr, trip_pin):
-            a_.copy_(b_)
-        if use_graph:
-            g_, outs = capture(inp, tr)
-        else:
-            g_, outs = None, None
-        sets.append({"inp": inp, "tr": tr, "graph": g_, "outs": outs})
+    order_host, seg_host, T0_plan = hb.triplet_plan(host["labels"], T_PER_ANCHOR, 0.0)   # from the host-side labels, like the host sampler
+    order_pin, seg_pin = order_host.pin_memory(), seg_host.pin_memory()
+    assert T0_plan == T0
+    s_up, s_run, s_down = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
 
     def flat_outs(outs):
         # the step's result as the caller reads it on the host: loss, surviving triplets, d loss / d scale.  The
         # four input gradients stay in HBM, where the backbone's backward consumes them.
         loss, kept, gs, _grads = outs
-        return [loss.reshape(1), kept.reshape(1), gs.reshape(1)]
+        return [loss.detach().reshape(1), kept.reshape(1), gs.reshape(1)]
 
-    probe = flat_outs(sets[0]["outs"] if use_graph else step(sets[0]["inp"], sets[0]["tr"]))
-    res_pin = [[torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in probe] for _ in range(2)]
-    d2h_bytes = sum(o.numel() * o.element_size() for o in probe)
-    s_up, s_run, s_down = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
-    ev_up = [torch.cuda.Event() for _ in range(2)]
-    ev_run = [torch.cuda.Event() for _ in range(2)]
-    ev_down = [torch.cuda.Event() for _ in range(2)]
+    def run_e2e(variant):
+        ups = dict(pin)
+        if variant == "device":
+            ups.update(order=order_pin, seg=seg_pin)
+        else:
+            ups.update(ta=trip_pin[0], tp=trip_pin[1], tn=trip_pin[2])
+        h2d = sum(v.numel() * v.element_size() for v in ups.values())
 
-    def e2e_loop(n_steps):
-        for i in range(n_steps):
-            st_ = sets[i % 2]
-            with torch.cuda.stream(s_up):
-                s_up.wait_event(ev_run[i % 2])               # buffer set free (its previous compute finished)
-                for k in pin:
-                    st_["inp"][k].copy_(pin[k], non_blocking=True)
-                for a_, b_ in zip(st_["tr"], trip_pin):
-                    a_.copy_(b_, non_blocking=True)
-                ev_up[i % 2].record(s_up)
-            with torch.cuda.stream(s_run):
-                s_run.wait_event(ev_up[i % 2])
-                s_run.wait_event(ev_down[i % 2])             # previous results of this set already copied out
-                if use_graph:
-                    st_["graph"].replay()
-                    outs = st_["outs"]
-                else:
-                    outs = step(st_["inp"], st_["tr"])
-                ev_run[i % 2].record(s_run)
-            with torch.cuda.stream(s_down):
-                s_down.wait_event(ev_run[i % 2])
-                for dst, src in zip(res_pin[i % 2], flat_outs(outs)):
-                    dst.copy_(src, non_blocking=True)
-                ev_down[i % 2].record(s_down)
+        def step_of(inp):
+            if variant == "device":
+                tr = hb.sample_triplets_device(None, seed=1234 + rank, plan=(inp["order"], inp["seg"], T0_plan))
+            else:
+                tr = (inp["ta"], inp["tp"], inp["tn"])
+            return step(inp, tr)
 
-    e2e_loop(4)
-    barrier()
+        sets = []
+        for _ in range(2):
+            inp = {k: torch.empty_like(v, device=dev) for k, v in ups.items()}
+            for k in ups:
+                inp[k].copy_(ups[k])
+            if use_graph:
+                g_, outs = capture_fn(lambda: step_of(inp))
+            else:
+                g_, outs = None, None
+            sets.append({"inp": inp, "graph": g_, "outs": outs})
+        probe = flat_outs(sets[0]["outs"] if use_graph else step_of(sets[0]["inp"]))
+        res_pin = [[torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in probe] for _ in range(2)]
+        d2h = sum(o.numel() * o.element_size() for o in probe)
+        ev_up = [torch.cuda.Event() for _ in range(2)]
+        ev_run = [torch.cuda.Event() for _ in range(2)]
+        ev_down = [torch.cuda.Event() for _ in range(2)]
+
+        def loop(n_steps):
+            for i in range(n_steps):
+                st_ = sets[i % 2]
+                with torch.cuda.stream(s_up):
+                    s_up.wait_event(ev_run[i % 2])               # buffer set free (its previous compute finished)
+                    for k in ups:
+                        st_["inp"][k].copy_(ups[k], non_blocking=True)
+                    ev_up[i % 2].record(s_up)
+                with torch.cuda.stream(s_run):
+                    s_run.wait_event(ev_up[i % 2])
+                    s_run.wait_event(ev_down[i % 2])             # previous results of this set already copied out
+                    if use_graph:
+                        st_["graph"].replay()
+                        outs = st_["outs"]
+                    else:
+                        outs = step_of(st_["inp"])
+                    ev_run[i % 2].record(s_run)
+                with torch.cuda.stream(s_down):
+                    s_down.wait_event(ev_run[i % 2])
+                    for dst, src in zip(res_pin[i % 2], flat_outs(outs)):
+                        dst.copy_(src, non_blocking=True)
+                    ev_down[i % 2].record(s_down)
+
+        loop(4)
+        barrier()
+        te0, te1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        te0.record()
+        loop(args.steps)
+        for s_ in (s_up, s_run, s_down):
+            torch.cuda.current_stream().wait_stream(s_)
+        te1.record()
+        barrier()
+        ms_e = torch.tensor([te0.elapsed_time(te1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
+        return {"value": round(world * B / (ms_e.item() / args.steps * 1e-3), 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "loss": float(res_pin[(args.steps - 1) % 2][0])}
+
     sampler.region = "e2e"
-    te0, te1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    te0.record()
-    e2e_loop(args.steps)
-    for s_ in (s_up, s_run, s_down):
-        torch.cuda.current_stream().wait_stream(s_)
-    te1.record()
-    barrier()
+    e2e_dev = run_e2e("device")
+    e2e_host = run_e2e("host")
     clocks = sampler.stop()
-    ms_e = torch.tensor([te0.elapsed_time(te1)], device=dev)
-    if world > 1:
-        dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
-    e2e_value = world * B / (ms_e.item() / args.steps * 1e-3)
-    e2e_loss = float(res_pin[(args.steps - 1) % 2][0])
 
     if rank != 0:
         return
@@ -411,15 +431,19 @@ def run_native(args):
                    "l2": "per-step working set ~1.4 GB (edge-feature tensors) exceeds the 126 MB L2; no explicit flush",
                    "launch": "cuda-graph replay of one captured step" if use_graph else "eager",
                    "ops_timing": "each op captured into its own CUDA graph, replayed `steps` times between CUDA events, after the timed region",
-                   "e2e_pipeline": "2 device buffer sets; upload / compute / download on 3 streams"},
-        "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes),
-                "d2h_bytes_per_step": int(d2h_bytes)},
+                   "e2e_pipeline": "2 device buffer sets; upload / compute / download on 3 streams",
+                   "overlap": "the reverse graph of each layer's backward is built on a second stream during that layer's forward"},
+        "e2e": {"value": e2e_dev["value"], "unit": UNIT, "h2d_bytes_per_step": e2e_dev["h2d_bytes_per_step"],
+                "d2h_bytes_per_step": e2e_dev["d2h_bytes_per_step"],
+                "inputs": "points, layer inputs, embeddings, sampling plan (label-sorted order + segments); triplets drawn on the GPU inside the step"},
+        "e2e_host_sampled_triplets": {k: e2e_host[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
         "ops": ops,
         "loss": loss_val,
-        "e2e_loss": e2e_loss,
+        "e2e_loss": e2e_host["loss"],
+        "e2e_loss_device_sampler": e2e_dev["loss"],
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_pass(steps=2, warmup=1)

@@ -6,7 +6,8 @@ is cheap and works anywhere, but every op raises unless its tensors live on a CC
 from .graph import knn, get_graph_feature, get_graph_feature_cross
 from .hyperbolic import hyp_lca, expmap0, ExpMap, normalize_project
 from .loss import (CosineSimilarity, RandomTripletMarginMiner, MetricHyperbolicLoss, CosFaceLoss,
-                   get_balanced_random_triplet_indices, hyp_triplet_loss, filter_triplets)
+                   get_balanced_random_triplet_indices, hyp_triplet_loss, filter_triplets,
+                   sample_triplets_device, triplet_segments, triplet_plan)
 from .decode import decode_linkage, decode_linkage_batch, linkage_from_leaves
 
 __all__ = [
@@ -14,5 +15,6 @@ __all__ = [
     "hyp_lca", "expmap0", "ExpMap", "normalize_project",
     "CosineSimilarity", "RandomTripletMarginMiner", "MetricHyperbolicLoss", "CosFaceLoss",
     "get_balanced_random_triplet_indices", "hyp_triplet_loss", "filter_triplets",
+    "sample_triplets_device", "triplet_segments", "triplet_plan",
     "decode_linkage", "decode_linkage_batch", "linkage_from_leaves",
 ]

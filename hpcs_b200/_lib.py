@@ -36,12 +36,15 @@ SIGNATURES = {
     "hpcs_edge_feat_bwd_workspace_bytes": (_Z, [_I, _I, _I]),
     "hpcs_edge_feat_bwd_is_fast": (_I, [_P, _I, _I, _I]),
     "hpcs_edge_feat_bwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _Z, _P]),
+    "hpcs_edge_rev_build": (_I, [_P, _I, _I, _I, _P, _Z, _P]),
+    "hpcs_edge_feat_bwd_prebuilt_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _Z, _P]),
     "hpcs_hyp_triplet_workspace_bytes": (_Z, [_L, _I]),
     "hpcs_hyp_triplet_fwd_f32": (_I, [_P, _L, _I, _P, _P, _P, _L, _P, _F, _I, _F, _I, _P, _P, _P, _Z, _P]),
     "hpcs_hyp_triplet_fwd_i32_f32": (_I, [_P, _L, _I, _P, _P, _P, _L, _P, _F, _I, _F, _I, _P, _P, _P, _Z, _P]),
     "hpcs_triplet_filter_i32_f32": (_I, [_P, _L, _I, _P, _P, _P, _L, _I, _F, _P, _P, _Z, _P]),
     "hpcs_hyp_triplet_bwd_f32": (_I, [_P, _P, _L, _I, _P, _P, _Z, _P, _P, _P]),
     "hpcs_triplet_filter_f32": (_I, [_P, _L, _I, _P, _P, _P, _L, _I, _F, _P, _P, _Z, _P]),
+    "hpcs_triplet_sample_i32": (_I, [_P, _L, _P, _I, _L, _c.c_uint64, _P, _P, _P, _P]),
     "hpcs_hyp_lca_fwd_f32": (_I, [_P, _P, _L, _I, _I, _P, _P]),
     "hpcs_hyp_lca_bwd_f32": (_I, [_P, _P, _P, _L, _I, _I, _P, _P, _P]),
     "hpcs_expmap0_fwd_f32": (_I, [_P, _L, _I, _P, _P]),

@@ -573,15 +573,17 @@ size_t edge_bwd_fast_workspace_bytes(int B, int N, int k) {
     return (size_t)B * rev2_dims(N, k).bytes_per_cloud;
 }
 
-int edge_bwd_fast_run(const float* gout, const int64_t* idx, int B, int C, int N, int k, float* gx, void* ws, cudaStream_t st) {
+// reverse graph of every cloud into ws (depends on idx only: may run ahead of the gradient, on another stream)
+int edge_bwd_fast_build(const int64_t* idx, int B, int N, int k, void* ws, cudaStream_t st) {
     const Rev2Dims d = rev2_dims(N, k);
-    {
-        const size_t smem = (size_t)d.NS * d.W * (sizeof(unsigned) + sizeof(uint16_t)) + (size_t)(4 * d.NS + 3 * d.GS + 1) * sizeof(int);
-        cudaFuncSetAttribute(edge_rev2_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        edge_rev2_build_kernel<<<dim3(d.S, B), kRevThreads, smem, st>>>(idx, N, k, 0xFFFFFFFFu / (unsigned)k + 1u, ws);
-        int rc = check_launch("edge_rev2_build_kernel");
-        if (rc) return rc;
-    }
+    const size_t smem = (size_t)d.NS * d.W * (sizeof(unsigned) + sizeof(uint16_t)) + (size_t)(4 * d.NS + 3 * d.GS + 1) * sizeof(int);
+    cudaFuncSetAttribute(edge_rev2_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    edge_rev2_build_kernel<<<dim3(d.S, B), kRevThreads, smem, st>>>(idx, N, k, 0xFFFFFFFFu / (unsigned)k + 1u, ws);
+    return check_launch("edge_rev2_build_kernel");
+}
+
+int edge_bwd_fast_gather(const float* gout, const int64_t* idx, int B, int C, int N, int k, float* gx, const void* ws, cudaStream_t st) {
+    const Rev2Dims d = rev2_dims(N, k);
     const GatherSmem g = gather_smem(N, k, d, kSmemBudget, NBUF);
     const int items = B * 3 * C;
     int grid = sm_count();
@@ -595,6 +597,11 @@ int edge_bwd_fast_run(const float* gout, const int64_t* idx, int B, int C, int N
     cudaFuncSetAttribute(edge_bwd_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.total);
     edge_bwd_gather_kernel<<<grid, kGatherThreads, g.total, st>>>(gout, idx, ws, B, C, N, k, per_cta, kSmemBudget, prof, gx);
     return check_launch("edge_bwd_gather_kernel");
+}
+
+int edge_bwd_fast_run(const float* gout, const int64_t* idx, int B, int C, int N, int k, float* gx, void* ws, cudaStream_t st) {
+    const int rc = edge_bwd_fast_build(idx, B, N, k, ws, st);
+    return rc ? rc : edge_bwd_fast_gather(gout, idx, B, C, N, k, gx, ws, st);
 }
 
 }  // namespace hpcs

@@ -20,6 +20,8 @@ namespace hpcs {
 bool edge_bwd_fast_applicable(const float* gout, int N, int k);
 size_t edge_bwd_fast_workspace_bytes(int B, int N, int k);
 int edge_bwd_fast_run(const float* gout, const int64_t* idx, int B, int C, int N, int k, float* gx, void* ws, cudaStream_t st);
+int edge_bwd_fast_build(const int64_t* idx, int B, int N, int k, void* ws, cudaStream_t st);
+int edge_bwd_fast_gather(const float* gout, const int64_t* idx, int B, int C, int N, int k, float* gx, const void* ws, cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------
 // forward
@@ -476,6 +478,25 @@ size_t hpcs_edge_feat_bwd_workspace_bytes(int B, int N, int k) {
 
 int hpcs_edge_feat_bwd_is_fast(const float* gout, int N, int k, int cross) {
     return (!cross && N > 0 && k > 0 && hpcs::edge_bwd_fast_applicable(gout, N, k)) ? 1 : 0;
+}
+
+int hpcs_edge_rev_build(const int64_t* idx, int B, int N, int k, void* ws, size_t ws_bytes, void* stream) {
+    using namespace hpcs;
+    if (!idx || !ws) return fail(HPCS_ERR_ARG, "edge_rev_build: null pointer");
+    if (B <= 0 || N <= 0 || k <= 0 || B > 65535) return fail(HPCS_ERR_ARG, "edge_rev_build: bad shape");
+    if (ws_bytes < hpcs_edge_feat_bwd_workspace_bytes(B, N, k)) return fail(HPCS_ERR_WORKSPACE, "edge_rev_build: workspace too small");
+    if (!edge_bwd_fast_applicable(static_cast<const float*>(nullptr), N, k)) return fail(HPCS_ERR_ARG, "edge_rev_build: shape N=%d k=%d is not on the persistent-gather path", N, k);
+    return edge_bwd_fast_build(idx, B, N, k, ws, as_stream(stream));
+}
+
+int hpcs_edge_feat_bwd_prebuilt_f32(const float* gout, const float* x, const int64_t* idx, int B, int C, int N, int k,
+                                    int cross, float* gx, void* ws, size_t ws_bytes, void* stream) {
+    using namespace hpcs;
+    if (!gout || !idx || !gx || !ws) return fail(HPCS_ERR_ARG, "edge_feat_bwd_prebuilt: null pointer");
+    if (B <= 0 || C <= 0 || N <= 0 || k <= 0 || B > 65535) return fail(HPCS_ERR_ARG, "edge_feat_bwd_prebuilt: bad shape");
+    if (ws_bytes < hpcs_edge_feat_bwd_workspace_bytes(B, N, k)) return fail(HPCS_ERR_WORKSPACE, "edge_feat_bwd_prebuilt: workspace too small");
+    if (!cross && edge_bwd_fast_applicable(gout, N, k)) return edge_bwd_fast_gather(gout, idx, B, C, N, k, gx, ws, as_stream(stream));
+    return hpcs_edge_feat_bwd_f32(gout, x, idx, B, C, N, k, cross, gx, ws, ws_bytes, stream);   // e.g. a misaligned gradient: rebuild
 }
 
 int hpcs_edge_feat_bwd_f32(const float* gout, const float* x, const int64_t* idx, int B, int C, int N, int k,

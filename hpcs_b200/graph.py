@@ -64,34 +64,86 @@ def edge_features_forward(x: torch.Tensor, idx: torch.Tensor, cross: bool = Fals
     return out
 
 
-def edge_features_backward(gout: torch.Tensor, x: torch.Tensor, idx: torch.Tensor, cross: bool = False) -> torch.Tensor:
-    """Raw backward launch: gradient of the edge features wrt x (deterministic gather, see csrc/edge_feat.cu)."""
+def edge_features_backward(gout: torch.Tensor, x: torch.Tensor, idx: torch.Tensor, cross: bool = False,
+                           prebuilt: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Raw backward launch: gradient of the edge features wrt x (deterministic gather, see csrc/edge_feat.cu).
+    ``prebuilt``: workspace already filled by :func:`build_reverse_graph` for this ``idx``."""
     B, C, _, N = x.shape
     k = idx.shape[2]
     dev = x.device
     lib = _lib.load()
     gout = gout.contiguous()
     gx = torch.empty_like(x)
-    ws = _lib.workspace(lib.hpcs_edge_feat_bwd_workspace_bytes(B, N, k), dev)
+    ws = prebuilt if prebuilt is not None else _lib.workspace(lib.hpcs_edge_feat_bwd_workspace_bytes(B, N, k), dev)
+    entry = lib.hpcs_edge_feat_bwd_prebuilt_f32 if prebuilt is not None else lib.hpcs_edge_feat_bwd_f32
     with torch.cuda.device(dev):
-        _lib.check(lib.hpcs_edge_feat_bwd_f32(gout.data_ptr(), x.data_ptr(), idx.data_ptr(), B, C, N, k,
-                                              int(cross), gx.data_ptr(), ws.data_ptr(), ws.numel(),
-                                              _lib.stream_ptr(dev)), "hpcs_edge_feat_bwd_f32")
+        _lib.check(entry(gout.data_ptr(), x.data_ptr(), idx.data_ptr(), B, C, N, k, int(cross), gx.data_ptr(),
+                         ws.data_ptr(), ws.numel(), _lib.stream_ptr(dev)), "hpcs_edge_feat_bwd_f32")
     return gx
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(dev: torch.device) -> torch.cuda.Stream:
+    s = _SIDE_STREAMS.get(dev.index)
+    if s is None:
+        s = _SIDE_STREAMS[dev.index] = torch.cuda.Stream(device=dev)
+    return s
+
+
+def build_reverse_graph(idx: torch.Tensor, overlap: bool = True) -> Optional[torch.Tensor]:
+    """Reverse (target -> sources) graph of ``idx[B,N,k]`` for the backward's persistent gather, or None when the shape
+    is not on that path.  With ``overlap`` the build is launched on a second stream that forks from the current one
+    here; the caller joins it with :func:`join_reverse_graph` AFTER enqueueing the work it should overlap with."""
+    B, N, k = idx.shape
+    dev = idx.device
+    lib = _lib.load()
+    nbytes = lib.hpcs_edge_feat_bwd_workspace_bytes(B, N, k)
+    ws = _lib.workspace(nbytes, dev)
+    if not lib.hpcs_edge_feat_bwd_is_fast(ws.data_ptr(), N, k, 0):
+        return None
+    with torch.cuda.device(dev):
+        if overlap:
+            cur, side = torch.cuda.current_stream(dev), _side_stream(dev)
+            side.wait_stream(cur)                                  # idx (and the allocation of ws) are ready
+            # no record_stream: join_reverse_graph orders every later use (and the free) of ws after the build
+            with torch.cuda.stream(side):
+                _lib.check(lib.hpcs_edge_rev_build(idx.data_ptr(), B, N, k, ws.data_ptr(), ws.numel(),
+                                                   _lib.stream_ptr(dev)), "hpcs_edge_rev_build")
+        else:
+            _lib.check(lib.hpcs_edge_rev_build(idx.data_ptr(), B, N, k, ws.data_ptr(), ws.numel(),
+                                               _lib.stream_ptr(dev)), "hpcs_edge_rev_build")
+    return ws
+
+
+def join_reverse_graph(dev: torch.device) -> None:
+    """Make the current stream wait for the build forked by :func:`build_reverse_graph` (also closes the fork when a
+    CUDA graph is being captured)."""
+    torch.cuda.current_stream(dev).wait_stream(_side_stream(dev))
+
+
 class _EdgeFeature(torch.autograd.Function):
+    """Forward: one gather kernel.  When the input needs a gradient, the reverse graph the backward gathers through is
+    built NOW, on a second stream next to the forward kernel: it depends on ``idx`` only, and its 30 us of
+    latency-bound shared-memory work hide behind the HBM-bound forward instead of sitting in front of the backward."""
+
     @staticmethod
     def forward(ctx, x, idx, cross):
+        rev = None
+        if ctx.needs_input_grad[0] and not cross:
+            rev = build_reverse_graph(idx, overlap=True)
         out = edge_features_forward(x, idx, cross)
+        if rev is not None:
+            join_reverse_graph(x.device)
         ctx.save_for_backward(x, idx)
-        ctx.cross = cross
+        ctx.cross, ctx.rev = cross, rev
         return out
 
     @staticmethod
     def backward(ctx, gout):
         x, idx = ctx.saved_tensors
-        return edge_features_backward(gout, x, idx, ctx.cross), None, None
+        return edge_features_backward(gout, x, idx, ctx.cross, prebuilt=ctx.rev), None, None
 
 
 def _edge_features(x: torch.Tensor, k: int, idx: Optional[torch.Tensor], x_coord: Optional[torch.Tensor],

@@ -75,6 +75,16 @@ size_t hpcs_edge_feat_bwd_workspace_bytes(int B, int N, int k);
 int hpcs_edge_feat_bwd_is_fast(const float* gout, int N, int k, int cross);
 int hpcs_edge_feat_bwd_f32(const float* gout, const float* x, const int64_t* idx, int B, int C, int N,
                            int k, int cross, float* gx, void* ws, size_t ws_bytes, void* stream);
+/* The reverse graph depends on idx only, so a caller that will need the backward can build it while the forward
+ * runs (hpcs_b200/graph.py launches it on a second stream next to hpcs_edge_feat_fwd_f32, where the build's
+ * latency-bound 30 us hide behind an HBM-bound kernel) and hand the filled workspace to the backward:
+ *   hpcs_edge_rev_build              fills ws for (idx, B, N, k); only for shapes hpcs_edge_feat_bwd_is_fast accepts
+ *                                    (pass any 16-byte aligned pointer as gout there), HPCS_ERR_ARG otherwise.
+ *   hpcs_edge_feat_bwd_prebuilt_f32  same result as hpcs_edge_feat_bwd_f32, skipping the build when the persistent
+ *                                    gather applies; falls back to the full call (rebuilding in ws) otherwise. */
+int hpcs_edge_rev_build(const int64_t* idx, int B, int N, int k, void* ws, size_t ws_bytes, void* stream);
+int hpcs_edge_feat_bwd_prebuilt_f32(const float* gout, const float* x, const int64_t* idx, int B, int C, int N,
+                                    int k, int cross, float* gx, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- part 2: Poincare-ball triplet objective -------------------------------------------------
  * MetricHyperbolicLoss.compute_hyp    hpcs/loss/ultrametric_loss.py:57-93 (+ :139-143)
@@ -106,6 +116,16 @@ int hpcs_triplet_filter_f32(const float* x, int64_t n, int D, const int64_t* a, 
 int hpcs_triplet_filter_i32_f32(const float* x, int64_t n, int D, const int32_t* a, const int32_t* p,
                                 const int32_t* ng, int64_t T0, int filter_mode, float margin, uint8_t* keep,
                                 void* ws, size_t ws_bytes, void* stream);
+
+/* get_balanced_random_triplet_indices on the device   hpcs/miner/loss_and_miner_utils.py:7-75   
+ *   order[n] int32: stable argsort of the labels; seg[4][L] int64: per label with >= 2 members and >= 1 non-member, in
+ *   ascending label order: {start in order, members m_l, k_l = int(t_per_anchor (max_count / m_l)^fraction), first
+ *   triplet}; T0 = sum m_l k_l.  Writes a,p,ng[T0] int32: the anchors exactly as the reference emits them (label by
+ *   label, member by member, k_l times each), positives uniform over the other members, negatives uniform over the
+ *   non-members, drawn from Philox4x32-10 keyed by (seed, triplet number) -- same distribution as the reference
+ *   sampler, not the same draws (the host sampler keeps RNG parity and stays the default). */
+int hpcs_triplet_sample_i32(const int32_t* order, int64_t n, const int64_t* seg, int L, int64_t T0, uint64_t seed,
+                            int32_t* a, int32_t* p, int32_t* ng, void* stream);
 
 /* hyp_lca(a, b, return_coord)         hpcs/distances/lca.py:37-52 (general, unequal norms)
  *   a,b[T,D] fp32 -> out[T,D] (return_coord) or out[T,1] = 2 artanh(|proj|); scalar chain in fp64. */

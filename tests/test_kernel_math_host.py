@@ -125,3 +125,23 @@ def test_general_lca_duals(hm, golden):
             gb = k * (2 * o[10] * b[t].numpy() + o[11] * a[t].numpy())
             np.testing.assert_allclose(ga, ga_ref[t], rtol=2e-5, atol=1e-9)
             np.testing.assert_allclose(gb, gb_ref[t], rtol=2e-5, atol=1e-9)
+
+
+def test_device_sampler_plan_matches_reference_sampler_structure():
+    """triplet_segments (the host plan of the device sampler) must give the reference sampler's triplet count and its
+    anchor sequence: labels ascending, members ascending, k_l repeats -- for fraction 0 and 1.2, with singleton labels."""
+    import torch
+    from hpcs_b200.loss import triplet_segments, get_balanced_random_triplet_indices
+    gen = torch.Generator().manual_seed(3)
+    for fraction, t in ((0.0, 7), (1.2, 5), (0.5, 3)):
+        labels = torch.randint(0, 9, (400,), generator=gen)
+        labels[labels == 4] = 5                       # label 4 absent
+        labels[17] = 40                               # a singleton label: skipped by the reference
+        torch.manual_seed(0)
+        a, p, n = get_balanced_random_triplet_indices(labels, t_per_anchor=t, fraction=fraction)
+        seg, T0 = triplet_segments(torch.bincount(labels), t, fraction)
+        assert T0 == a.numel()
+        order = torch.sort(labels, stable=True)[1]
+        want = torch.cat([order[s:s + m].repeat_interleave(r) for s, m, r, _ in seg.t().tolist()])
+        assert torch.equal(want, a)
+        assert seg[3].tolist() == (torch.cumsum(seg[1] * seg[2], 0) - seg[1] * seg[2]).tolist()
