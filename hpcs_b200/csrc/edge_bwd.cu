@@ -337,7 +337,11 @@ __device__ __forceinline__ float row_sum(const float* __restrict__ row, int k) {
 }
 
 // (Two CTAs per SM with one plane buffer each was measured slower: the gather phase is bound by shared-memory
-// wavefronts -- random 4-byte reads, ~3 bank conflicts each -- which a second resident CTA only contends for.)
+// wavefronts -- random 4-byte reads, ~3 bank conflicts each -- which a second resident CTA only contends for.
+// Also measured slower, 144 us against 130 us: streaming only the difference planes through the two buffers and
+// taking the centre plane's row sums straight from HBM into registers before the gather (coalesced LDG.128, partial
+// sums redistributed by shuffles in the combine).  The L1 fills of those loads go through the same l1tex data pipe as
+// the gather's shared-memory reads and slow it by more than the removed centre phase saved; TMA writes do not.)
 constexpr int NBUF = 2;
 
 __global__ void __launch_bounds__(kGatherThreads, 1)

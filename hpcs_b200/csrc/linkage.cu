@@ -629,7 +629,7 @@ struct LinkWs {
 
 static LinkWs link_ws(int B, int N, int method) {
     LinkWs L{};
-    L.rounds = (method == 0 && N >= 256) ? (N <= 1024 ? 2 : 3) : 0;
+    L.rounds = (method == 0 && N >= 256) ? (N < 512 ? 2 : 3) : 0;
     L.pitch[0] = N;
     for (int r = 1; r <= kMaxRounds; ++r) L.pitch[r] = (L.pitch[r - 1] / 2 + 3) / 4 * 4;    // a round at least halves the nodes
     size_t off = 0;
