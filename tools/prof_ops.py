@@ -1,5 +1,5 @@
 """Run each hot-path op a few times on the bench shapes (for ncu launch lists / captures).
-  python tools/prof_ops.py [--ops knn3,knn63,edge,loss,decode] [--reps 3]"""
+  python tools/prof_ops.py [--ops knn3,knn63,edge,loss,sampler,decode] [--reps 3]"""
 import argparse
 import os
 import sys
@@ -61,6 +61,10 @@ def main():
             l = hb.hyp_triplet_loss(emb, trip, sc, bench.TEMPERATURE, "easy", 0.0)
             torch.autograd.grad(l, (emb, sc))
         timeit("hyp_loss", loss)
+    if "sampler" in ops:
+        order, seg, T0 = hb.triplet_plan(host["labels"], bench.T_PER_ANCHOR, 0.0)
+        plan = (order.to(dev), seg.to(dev), T0)
+        timeit("triplet_sampler", lambda: hb.sample_triplets_device(None, seed=1, plan=plan))
     if "decode" in ops:
         x = d["emb"].view(B, N, -1)
         sc = torch.tensor([bench.SCALE], device=dev)
