@@ -24,6 +24,7 @@ namespace hpcs {
 
 constexpr int kPT = 64;           // pdist tile edge
 constexpr int kPLD = kPT + 2;     // shared-memory row pitch in doubles (keeps 16-byte alignment, spreads banks)
+constexpr int kNoIdxPd = 0x7fffffff;
 
 // fp64 cosine distance matrix, bit-identical to scipy's pdist(., 'cosine') on the same fp32 rows.
 // grid: (T*(T+1)/2 upper 64x64 tiles, B); block (64/MR) x 16 threads, MR x 4 outputs each: rows ty*MR+ii, columns
@@ -130,6 +131,228 @@ pdist_cosine_kernel(const float* __restrict__ leaves, int N, int D, double* __re
             }
         }
     }
+}
+
+// ---- row-block form of the distance kernel (the one that runs) -----------------------------------------------------
+// Same arithmetic and output as pdist_cosine_kernel above; what changes is the schedule.  A CTA owns one 64-row block
+// `bi` of one cloud and walks the column blocks bj = bi .. T-1 itself: the A tile and its norms are staged once, the
+// next B tile is fetched from global memory into registers WHILE the current tile is computed (so the load latency
+// that took a quarter of the tile-per-CTA kernel's samples is hidden), norms come from a one-off norms kernel instead
+// of being recomputed per tile, and the runtime division by D in the staging index is a multiply-high.
+// With ROWMIN the kernel also delivers what the first Boruvka round needs -- the (distance, index) arg-min of every
+// matrix row -- without a second pass over the matrix: a thread keeps the running minima of its 4 rows over every
+// tile it computes (direct orientation), column minima of a tile (the mirrored orientation: rows of block bj against
+// columns of block bi) are combined across the CTA through shared memory, and both land as per-(row, column-block)
+// partials pmin[slot][row] that a tiny kernel folds.  Ties resolve to the lower index everywhere (lexicographic min).
+__global__ void pdist_norms_kernel(const float* __restrict__ leaves, size_t rows, int D, double* __restrict__ norms) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const float* v = leaves + i * D;
+    double even = 0.0, odd = 0.0;
+    int q = 0;
+    for (; q + 1 < D; q += 2) {
+        const double v0 = (double)__ldg(v + q), v1 = (double)__ldg(v + q + 1);
+        even = fma(v0, v0, even);
+        odd = fma(v1, v1, odd);
+    }
+    double s = __dadd_rn(even, odd);
+    if (D & 1) { const double t = (double)__ldg(v + D - 1); s = fma(t, t, s); }
+    norms[i] = __dsqrt_rn(s);
+}
+
+__device__ __forceinline__ void lex_take(double& v, int& j, double ov, int oj) {
+    if (ov < v || (ov == v && oj < j)) { v = ov; j = oj; }
+}
+
+// PF = floats a thread prefetches per B tile (64 * D <= 256 * PF); PF = 0: any D, no prefetch.
+template <int PF, bool ROWMIN>
+__global__ void __launch_bounds__(256, 2)
+pdist_rowblock_kernel(const float* __restrict__ leaves, const double* __restrict__ norms, int N, int D, unsigned d_magic,
+                      double* __restrict__ dm, double* __restrict__ pmin_v, int* __restrict__ pmin_j) {
+    extern __shared__ __align__(16) double sm[];
+    double* as = sm;                          // [D][kPLD]
+    double* bs = as + (size_t)D * kPLD;       // [D][kPLD]
+    double* na = bs + (size_t)D * kPLD;       // [64]
+    double* nb = na + kPT;                    // [64]
+    double* wv = nb + kPT;                    // ROWMIN: [8 warps][64 cols] column minima of the current tile
+    int* wj = reinterpret_cast<int*>(wv + 8 * kPT);
+    const int b = blockIdx.y, bi = blockIdx.x;
+    const int T = (N + kPT - 1) / kPT;
+    const float* lb = leaves + (size_t)b * N * D;
+    const double* nrm = norms + (size_t)b * N;
+    double* db = dm + (size_t)b * N * N;
+    const int tile_elems = kPT * D;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool vec_ok = (N & 3) == 0;
+
+    auto stage = [&](double* dst, double* ndst, int blk) {        // plain staging (A tile; B tiles when PF == 0)
+        for (int e = threadIdx.x; e < tile_elems; e += 256) {
+            const int r = (int)__umulhi((unsigned)e, d_magic), q = e - r * D;
+            const int g = blk * kPT + r;
+            dst[q * kPLD + r] = g < N ? (double)__ldg(lb + (size_t)g * D + q) : 0.0;
+        }
+        if (threadIdx.x < kPT) { const int g = blk * kPT + threadIdx.x; ndst[threadIdx.x] = g < N ? nrm[g] : 0.0; }
+    };
+    float pre[PF > 0 ? PF : 1];
+    double pre_n = 0.0;
+    auto prefetch = [&](int blk) {                                  // global -> registers, consumed after the tile
+        if (PF > 0) {
+            const float* src = lb + (size_t)blk * kPT * D;
+            const int left = (N - blk * kPT) * D;                    // floats of the cloud from this block on
+#pragma unroll
+            for (int i = 0; i < PF; ++i) {
+                const int e = threadIdx.x + 256 * i;
+                pre[i] = (e < tile_elems && e < left) ? __ldg(src + e) : 0.f;
+            }
+            if (threadIdx.x < kPT) { const int g = blk * kPT + threadIdx.x; pre_n = g < N ? nrm[g] : 0.0; }
+        }
+    };
+    auto commit = [&]() {                                           // registers -> bs / nb
+        if (PF > 0) {
+#pragma unroll
+            for (int i = 0; i < PF; ++i) {
+                const int e = threadIdx.x + 256 * i;
+                if (e < tile_elems) {
+                    const int r = (int)__umulhi((unsigned)e, d_magic), q = e - r * D;
+                    bs[q * kPLD + r] = (double)pre[i];
+                }
+            }
+            if (threadIdx.x < kPT) nb[threadIdx.x] = pre_n;
+        }
+    };
+
+    stage(as, na, bi);
+    if (PF > 0) { prefetch(bi); commit(); } else stage(bs, nb, bi);
+    __syncthreads();
+
+    double best_v[4];                                               // ROWMIN: running minima of this thread's rows
+    int best_j[4];
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) { best_v[ii] = INFINITY; best_j[ii] = kNoIdxPd; }
+    const int gi0 = bi * kPT + ty * 4;
+    const double* ap = as + ty * 4;
+    const double* bp = bs + tx;
+
+    for (int bj = bi; bj < T; ++bj) {
+        if (bj + 1 < T) prefetch(bj + 1);
+        double ev[4][4], od[4][4];
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) { ev[ii][jj] = 0.0; od[ii][jj] = 0.0; }
+        int q = 0;
+        for (; q + 1 < D; q += 2) {
+            const double2 a01 = *reinterpret_cast<const double2*>(ap + q * kPLD);
+            const double2 a23 = *reinterpret_cast<const double2*>(ap + q * kPLD + 2);
+            const double2 c01 = *reinterpret_cast<const double2*>(ap + (q + 1) * kPLD);
+            const double2 c23 = *reinterpret_cast<const double2*>(ap + (q + 1) * kPLD + 2);
+            const double a[4] = {a01.x, a01.y, a23.x, a23.y};
+            const double c[4] = {c01.x, c01.y, c23.x, c23.y};
+            double be[4], bo[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) { be[jj] = bp[q * kPLD + 16 * jj]; bo[jj] = bp[(q + 1) * kPLD + 16 * jj]; }
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    ev[ii][jj] = fma(a[ii], be[jj], ev[ii][jj]);
+                    od[ii][jj] = fma(c[ii], bo[jj], od[ii][jj]);
+                }
+        }
+        double cmin_v[4];                                           // ROWMIN, mirrored orientation: per column of mine
+        int cmin_i[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) { cmin_v[jj] = INFINITY; cmin_i[jj] = kNoIdxPd; }
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+            const int i = ty * 4 + ii;
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int j = tx + 16 * jj;
+                double s = __dadd_rn(ev[ii][jj], od[ii][jj]);
+                if (D & 1) s = fma(as[(D - 1) * kPLD + i], bs[(D - 1) * kPLD + j], s);
+                double cs = __ddiv_rn(s, __dmul_rn(na[i], nb[j]));
+                if (fabs(cs) > 1.0) cs = copysign(1.0, cs);
+                const int gi = gi0 + ii, gj = bj * kPT + j;
+                const double r = gi == gj ? 0.0 : __dsub_rn(1.0, cs);
+                ev[ii][jj] = r;                                     // results replace the accumulators
+                if (gi < N && gj < N) {
+                    db[(size_t)gi * N + gj] = r;                    // 16 lanes x 8 B contiguous
+                    if (ROWMIN && gi != gj) {
+                        if (r < best_v[ii]) { best_v[ii] = r; best_j[ii] = gj; }             // gj ascends: lowest index wins ties
+                        if (bi != bj && r < cmin_v[jj]) { cmin_v[jj] = r; cmin_i[jj] = gi; }   // gi ascends over ii
+                    }
+                }
+            }
+        }
+        if (bi != bj) {                                             // mirrored tile
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int gj = bj * kPT + tx + 16 * jj;
+                if (gj < N) {
+                    double* dst = db + (size_t)gj * N + gi0;
+                    if (vec_ok && gi0 + 3 < N) {
+                        *reinterpret_cast<double2*>(dst) = make_double2(ev[0][jj], ev[1][jj]);
+                        *reinterpret_cast<double2*>(dst + 2) = make_double2(ev[2][jj], ev[3][jj]);
+                    } else {
+#pragma unroll
+                        for (int ii = 0; ii < 4; ++ii) if (gi0 + ii < N) dst[ii] = ev[ii][jj];
+                    }
+                }
+                if (ROWMIN) {                                       // the two ty halves of the warp, then one entry per warp
+                    const double ov = __shfl_xor_sync(kFull, cmin_v[jj], 16);
+                    const int oi = __shfl_xor_sync(kFull, cmin_i[jj], 16);
+                    lex_take(cmin_v[jj], cmin_i[jj], ov, oi);
+                    if (lane < 16) { wv[warp * kPT + tx + 16 * jj] = cmin_v[jj]; wj[warp * kPT + tx + 16 * jj] = cmin_i[jj]; }
+                }
+            }
+        }
+        __syncthreads();                                            // tile consumed; column minima of all warps visible
+        if (ROWMIN && bi != bj && threadIdx.x < kPT) {
+            const int gj = bj * kPT + threadIdx.x;
+            if (gj < N) {
+                double v = wv[threadIdx.x];
+                int j = wj[threadIdx.x];
+#pragma unroll
+                for (int w = 1; w < 8; ++w) lex_take(v, j, wv[w * kPT + threadIdx.x], wj[w * kPT + threadIdx.x]);
+                pmin_v[((size_t)b * T + bi) * N + gj] = v;          // slot bi of row gj: its minimum over column block bi
+                pmin_j[((size_t)b * T + bi) * N + gj] = j;
+            }
+        }
+        if (bj + 1 < T) { if (PF > 0) commit(); else stage(bs, nb, bj + 1); }
+        __syncthreads();
+    }
+    if (ROWMIN) {
+        // direct orientation: fold the 16 tx lanes of a row (a half-warp) and store slot bi of rows gi0 .. gi0+3
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(kFull, best_v[ii], o);
+                const int oj = __shfl_xor_sync(kFull, best_j[ii], o);
+                lex_take(best_v[ii], best_j[ii], ov, oj);
+            }
+            if (tx == 0 && gi0 + ii < N) {
+                pmin_v[((size_t)b * T + bi) * N + gi0 + ii] = best_v[ii];
+                pmin_j[((size_t)b * T + bi) * N + gi0 + ii] = best_j[ii];
+            }
+        }
+    }
+}
+
+// fold the per-column-block partials of every row: slots 0 .. block(row)
+__global__ void __launch_bounds__(256)
+boruvka_rowmin_fold_kernel(const double* __restrict__ pmin_v, const int* __restrict__ pmin_j, int N, int T,
+                           double* __restrict__ rmw, int* __restrict__ rmj) {
+    const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double v = INFINITY;
+    int j = kNoIdxPd;
+    const int last = i / kPT;
+    for (int s = 0; s <= last; ++s) lex_take(v, j, pmin_v[((size_t)b * T + s) * N + i], pmin_j[((size_t)b * T + s) * N + i]);
+    rmw[(size_t)b * N + i] = v;
+    rmj[(size_t)b * N + i] = j;
 }
 
 __device__ __forceinline__ bool am_less(double v, int i, double ov, int oi) { return v < ov || (v == ov && i < oi); }
@@ -622,7 +845,7 @@ constexpr int kMaxRounds = 3;
 struct LinkWs {
     int rounds;                       // Boruvka rounds before Prim (single linkage, N >= 256), else 0
     int pitch[kMaxRounds + 1];        // row pitch (= node capacity) of matrix r
-    size_t off_m[kMaxRounds + 1], off_recx, off_recy, off_rech, off_rmw, off_rmj, off_memb, off_moff, off_nd, off_tie;
+    size_t off_m[kMaxRounds + 1], off_recx, off_recy, off_rech, off_rmw, off_rmj, off_memb, off_moff, off_nd, off_tie, off_norm, off_pmv, off_pmj;
     size_t off_rep[kMaxRounds + 1];
     size_t total;
 };
@@ -638,6 +861,7 @@ static LinkWs link_ws(int B, int N, int method) {
     L.off_recx = take((size_t)B * N * sizeof(int));
     L.off_recy = take((size_t)B * N * sizeof(int));
     L.off_rech = take((size_t)B * N * sizeof(double));
+    L.off_norm = take((size_t)B * N * sizeof(double));
     if (L.rounds) {
         L.off_rmw = take((size_t)B * N * sizeof(double));
         L.off_rmj = take((size_t)B * N * sizeof(int));
@@ -645,6 +869,9 @@ static LinkWs link_ws(int B, int N, int method) {
         L.off_moff = take((size_t)B * (N + 1) * sizeof(int));
         L.off_nd = take((size_t)B * 8 * sizeof(int));
         L.off_tie = take((size_t)B * sizeof(int));
+        const size_t T = (size_t)(N + kPT - 1) / kPT;
+        L.off_pmv = take((size_t)B * T * N * sizeof(double));
+        L.off_pmj = take((size_t)B * T * N * sizeof(int));
         for (int r = 1; r <= L.rounds; ++r) L.off_rep[r] = take((size_t)B * L.pitch[r] * sizeof(int));
     }
     L.total = off;
@@ -696,11 +923,25 @@ int hpcs_linkage_f64(const float* leaves, int B, int N, int D, int method, doubl
     double* rech = reinterpret_cast<double*>(w + L.off_rech);
 
     const int T = (N + kPT - 1) / kPT;
-    // MR = 4 measured best on B200 (N=1024/8192, B=64: 333 us / 20.0 ms against 399 us / 23.0 ms for MR = 8 at half the warps)
-    cudaFuncSetAttribute(pdist_cosine_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pd);
-    pdist_cosine_kernel<4><<<dim3(T * (T + 1) / 2, B), 256, smem_pd, st>>>(leaves, N, D, dm);
-    int rc = check_launch("pdist_cosine_kernel");
+    double* norms = reinterpret_cast<double*>(w + L.off_norm);
+    pdist_norms_kernel<<<(unsigned)(((size_t)B * N + 255) / 256), 256, 0, st>>>(leaves, (size_t)B * N, D, norms);
+    int rc = check_launch("pdist_norms_kernel");
     if (rc) return rc;
+    {
+        const bool rowmin = L.rounds > 0;
+        double* pmv = rowmin ? reinterpret_cast<double*>(w + L.off_pmv) : nullptr;
+        int* pmj = rowmin ? reinterpret_cast<int*>(w + L.off_pmj) : nullptr;
+        const size_t smem_rb = smem_pd + (rowmin ? (size_t)8 * kPT * (sizeof(double) + sizeof(int)) : 0);
+        const unsigned d_magic = 0xFFFFFFFFu / (unsigned)D + 1u;                 // e / D == umulhi(e, magic) for e < 2^16
+        auto go = [&](auto kern) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rb);
+            kern<<<dim3(T, B), 256, smem_rb, st>>>(leaves, norms, N, D, d_magic, dm, pmv, pmj);
+        };
+        if (D <= 32) { if (rowmin) go(pdist_rowblock_kernel<8, true>); else go(pdist_rowblock_kernel<8, false>); }
+        else if (D <= 64) { if (rowmin) go(pdist_rowblock_kernel<16, true>); else go(pdist_rowblock_kernel<16, false>); }
+        else { if (rowmin) go(pdist_rowblock_kernel<0, true>); else go(pdist_rowblock_kernel<0, false>); }
+        if ((rc = check_launch("pdist_rowblock_kernel"))) return rc;
+    }
     // direct form: columns per thread 1 up to 512 points, else the smallest of 2/4/8 that covers N with <= 1024 threads
     const int cpt0 = N <= 512 ? 1 : N <= 2048 ? 2 : N <= 4096 ? 4 : 8;
     const int threads0 = ((N + cpt0 - 1) / cpt0 + 31) / 32 * 32;
@@ -717,8 +958,9 @@ int hpcs_linkage_f64(const float* leaves, int B, int N, int D, int method, doubl
     int* moff = reinterpret_cast<int*>(w + L.off_moff);
     int* nd = reinterpret_cast<int*>(w + L.off_nd);
     int* tie = reinterpret_cast<int*>(w + L.off_tie);
-    boruvka_rowmin_kernel<<<dim3(N, B), 256, 0, st>>>(dm, stride0, N, nd, 0, rmw, rmj, N);
-    if ((rc = check_launch("boruvka_rowmin_kernel"))) return rc;
+    boruvka_rowmin_fold_kernel<<<dim3((N + 255) / 256, B), 256, 0, st>>>(reinterpret_cast<double*>(w + L.off_pmv), reinterpret_cast<int*>(w + L.off_pmj),
+                                                                        N, T, rmw, rmj);
+    if ((rc = check_launch("boruvka_rowmin_fold_kernel"))) return rc;
     for (int r = 0; r < L.rounds; ++r) {
         const int cap = L.pitch[r], cap2 = L.pitch[r + 1];
         const int* rep_in = r ? reinterpret_cast<int*>(w + L.off_rep[r]) : nullptr;
