@@ -341,6 +341,149 @@ pdist_rowblock_kernel(const float* __restrict__ leaves, const double* __restrict
     }
 }
 
+// ---- fp64 tensor-core form (the one that runs) -----------------------------------------------------------------------
+// mma.sync.m8n8k4.f64 adds its four products as an FMA chain in ascending k (measured on B200 with
+// tools/probes/dmma_order_probe.cu: 128000 of 128000 outputs equal the chain bit for bit, 95.7 % equal a descending
+// chain or a single rounding of the exact sum).  scipy's dot product is two such chains -- over the even and over the
+// odd feature indices -- so feeding one accumulator the k-slices (0,2,4,6), (8,10,12,14), ... and another the slices
+// (1,3,5,7), ... reproduces both running sums exactly (products of fp32-origin operands are exact in fp64, so FMA and
+// multiply-then-add round the same number; zero padding adds +0 and changes nothing).  What the tensor cores buy is not
+// flops (64 fp64 FMA lanes per SM per clock either way) but operand delivery: a thread loads ONE double per operand
+// fragment for 8 FMAs, 2 B per FMA against 4 B at a 4x4 register tile, and issues one instruction per 256 FMAs -- the
+// DFMA kernel sat at 61 % of the shared-memory pipe with the fp64 pipe 28 % busy.
+// Schedule as pdist_rowblock_kernel: CTA = (row block bi, cloud), walks bj = bi .. T-1, B tiles prefetched through
+// registers.  Warp w: rows 16 (w >> 1) .. +15, columns 32 (w & 1) .. +31 of the 64x64 tile = 2 x 4 MMA tiles, two
+// accumulator fragments (even / odd chain) each.  Fragment coordinates: g = lane >> 2, t = lane & 3; A[row g][k t],
+// B[k t][col g], C[row g][cols 2t, 2t+1].  Shared memory holds the tiles feature-major with the features of a slice
+// step interleaved as the fragments want them; rows [2P, 8S) stay zero, the odd tail feature lives in row 8S.
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+template <int PF>
+__global__ void __launch_bounds__(256, 2)
+pdist_mma_kernel(const float* __restrict__ leaves, const double* __restrict__ norms, int N, int D, unsigned d_magic,
+                 double* __restrict__ dm) {
+    extern __shared__ __align__(16) double sm[];
+    const int P = D >> 1, S = (P + 3) >> 2;      // feature pairs; slice steps of 4 pairs
+    const int rows = 8 * S + 1;                   // staged feature rows (+ the tail row)
+    double* as = sm;                              // [rows][kPLD]
+    double* bs = as + (size_t)rows * kPLD;        // [rows][kPLD]
+    double* na = bs + (size_t)rows * kPLD;        // [64]
+    double* nb = na + kPT;                        // [64]
+    const int b = blockIdx.y, bi = blockIdx.x;
+    const int T = (N + kPT - 1) / kPT;
+    const float* lb = leaves + (size_t)b * N * D;
+    const double* nrm = norms + (size_t)b * N;
+    double* db = dm + (size_t)b * N * N;
+    const int tile_elems = kPT * D;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int r0 = 16 * (warp >> 1), c0 = 32 * (warp & 1);
+    const bool vec_ok = (N & 1) == 0;
+
+    auto row_of = [&](int q) { return q < 2 * P ? q : 8 * S; };     // the odd tail feature goes to the last row
+    auto stage = [&](double* dst, double* ndst, int blk) {
+        for (int e = threadIdx.x; e < tile_elems; e += 256) {
+            const int r = (int)__umulhi((unsigned)e, d_magic), q = e - r * D;
+            const int gr = blk * kPT + r;
+            dst[row_of(q) * kPLD + r] = gr < N ? (double)__ldg(lb + (size_t)gr * D + q) : 0.0;
+        }
+        if (threadIdx.x < kPT) { const int gr = blk * kPT + threadIdx.x; ndst[threadIdx.x] = gr < N ? nrm[gr] : 0.0; }
+    };
+    float pre[PF > 0 ? PF : 1];
+    double pre_n = 0.0;
+    auto prefetch = [&](int blk) {
+        if (PF > 0) {
+            const float* src = lb + (size_t)blk * kPT * D;
+            const int left = (N - blk * kPT) * D;
+#pragma unroll
+            for (int i = 0; i < PF; ++i) {
+                const int e = threadIdx.x + 256 * i;
+                pre[i] = (e < tile_elems && e < left) ? __ldg(src + e) : 0.f;
+            }
+            if (threadIdx.x < kPT) { const int gr = blk * kPT + threadIdx.x; pre_n = gr < N ? nrm[gr] : 0.0; }
+        }
+    };
+    auto commit = [&]() {
+        if (PF > 0) {
+#pragma unroll
+            for (int i = 0; i < PF; ++i) {
+                const int e = threadIdx.x + 256 * i;
+                if (e < tile_elems) {
+                    const int r = (int)__umulhi((unsigned)e, d_magic), q = e - r * D;
+                    bs[row_of(q) * kPLD + r] = (double)pre[i];
+                }
+            }
+            if (threadIdx.x < kPT) nb[threadIdx.x] = pre_n;
+        }
+    };
+
+    for (int e = threadIdx.x; e < (8 * S - 2 * P) * kPLD; e += 256) {       // zero padding rows of both tiles, once
+        as[2 * P * kPLD + e] = 0.0;
+        bs[2 * P * kPLD + e] = 0.0;
+    }
+    if (!(D & 1)) for (int e = threadIdx.x; e < kPLD; e += 256) { as[8 * S * kPLD + e] = 0.0; bs[8 * S * kPLD + e] = 0.0; }
+    stage(as, na, bi);
+    if (PF > 0) { prefetch(bi); commit(); } else stage(bs, nb, bi);
+    __syncthreads();
+
+    const double* ap = as + (2 * t) * kPLD + r0 + g;                  // fragment element of slice step 0, even chain
+    const double* bp = bs + (2 * t) * kPLD + c0 + g;
+    for (int bj = bi; bj < T; ++bj) {
+        if (bj + 1 < T) prefetch(bj + 1);
+        double ev[2][4][2], od[2][4][2];
+#pragma unroll
+        for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+            for (int ct = 0; ct < 4; ++ct) { ev[rt][ct][0] = ev[rt][ct][1] = 0.0; od[rt][ct][0] = od[rt][ct][1] = 0.0; }
+        for (int s = 0; s < S; ++s) {
+            double ae[2], ao[2], be[4], bo[4];
+#pragma unroll
+            for (int rt = 0; rt < 2; ++rt) { ae[rt] = ap[(8 * s) * kPLD + 8 * rt]; ao[rt] = ap[(8 * s + 1) * kPLD + 8 * rt]; }
+#pragma unroll
+            for (int ct = 0; ct < 4; ++ct) { be[ct] = bp[(8 * s) * kPLD + 8 * ct]; bo[ct] = bp[(8 * s + 1) * kPLD + 8 * ct]; }
+#pragma unroll
+            for (int rt = 0; rt < 2; ++rt)
+#pragma unroll
+                for (int ct = 0; ct < 4; ++ct) {
+                    dmma_m8n8k4(ev[rt][ct][0], ev[rt][ct][1], ae[rt], be[ct]);
+                    dmma_m8n8k4(od[rt][ct][0], od[rt][ct][1], ao[rt], bo[ct]);
+                }
+        }
+#pragma unroll
+        for (int rt = 0; rt < 2; ++rt) {
+            const int i = r0 + 8 * rt + g, gi = bi * kPT + i;
+            const double ni = na[i], ti = as[8 * S * kPLD + i];
+#pragma unroll
+            for (int ct = 0; ct < 4; ++ct) {
+                const int j = c0 + 8 * ct + 2 * t, gj = bj * kPT + j;
+                double res[2];
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    double sum = __dadd_rn(ev[rt][ct][e], od[rt][ct][e]);
+                    if (D & 1) sum = fma(ti, bs[8 * S * kPLD + j + e], sum);
+                    double cs = __ddiv_rn(sum, __dmul_rn(ni, nb[j + e]));
+                    if (fabs(cs) > 1.0) cs = copysign(1.0, cs);
+                    res[e] = gi == gj + e ? 0.0 : __dsub_rn(1.0, cs);
+                }
+                if (gi < N) {
+                    double* dst = db + (size_t)gi * N + gj;
+                    if (vec_ok && gj + 1 < N) *reinterpret_cast<double2*>(dst) = make_double2(res[0], res[1]);
+                    else { if (gj < N) dst[0] = res[0]; if (gj + 1 < N) dst[1] = res[1]; }
+                    if (bi != bj) {                                  // mirrored tile: 8 lanes (g) x 8 B contiguous per column
+                        if (gj < N) db[(size_t)gj * N + gi] = res[0];
+                        if (gj + 1 < N) db[(size_t)(gj + 1) * N + gi] = res[1];
+                    }
+                }
+            }
+        }
+        __syncthreads();                                            // tile consumed
+        if (bj + 1 < T) { if (PF > 0) commit(); else stage(bs, nb, bj + 1); }
+        __syncthreads();
+    }
+}
+
 // fold the per-column-block partials of every row: slots 0 .. block(row)
 __global__ void __launch_bounds__(256)
 boruvka_rowmin_fold_kernel(const double* __restrict__ pmin_v, const int* __restrict__ pmin_j, int N, int T,
@@ -928,19 +1071,18 @@ int hpcs_linkage_f64(const float* leaves, int B, int N, int D, int method, doubl
     int rc = check_launch("pdist_norms_kernel");
     if (rc) return rc;
     {
-        const bool rowmin = L.rounds > 0;
-        double* pmv = rowmin ? reinterpret_cast<double*>(w + L.off_pmv) : nullptr;
-        int* pmj = rowmin ? reinterpret_cast<int*>(w + L.off_pmj) : nullptr;
-        const size_t smem_rb = smem_pd + (rowmin ? (size_t)8 * kPT * (sizeof(double) + sizeof(int)) : 0);
+        const int S8 = 8 * ((D / 2 + 3) / 4) + 1;                                  // staged feature rows per tile
+        const size_t smem_mma = ((size_t)2 * S8 * kPLD + 2 * kPT) * sizeof(double);
+        if (smem_mma > 200 * 1024) return fail(HPCS_ERR_ARG, "linkage: D=%d too large", D);
         const unsigned d_magic = 0xFFFFFFFFu / (unsigned)D + 1u;                 // e / D == umulhi(e, magic) for e < 2^16
         auto go = [&](auto kern) {
-            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_rb);
-            kern<<<dim3(T, B), 256, smem_rb, st>>>(leaves, norms, N, D, d_magic, dm, pmv, pmj);
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma);
+            kern<<<dim3(T, B), 256, smem_mma, st>>>(leaves, norms, N, D, d_magic, dm);
         };
-        if (D <= 32) { if (rowmin) go(pdist_rowblock_kernel<8, true>); else go(pdist_rowblock_kernel<8, false>); }
-        else if (D <= 64) { if (rowmin) go(pdist_rowblock_kernel<16, true>); else go(pdist_rowblock_kernel<16, false>); }
-        else { if (rowmin) go(pdist_rowblock_kernel<0, true>); else go(pdist_rowblock_kernel<0, false>); }
-        if ((rc = check_launch("pdist_rowblock_kernel"))) return rc;
+        if (D <= 32) go(pdist_mma_kernel<8>);
+        else if (D <= 64) go(pdist_mma_kernel<16>);
+        else go(pdist_mma_kernel<0>);
+        if ((rc = check_launch("pdist_mma_kernel"))) return rc;
     }
     // direct form: columns per thread 1 up to 512 points, else the smallest of 2/4/8 that covers N with <= 1024 threads
     const int cpt0 = N <= 512 ? 1 : N <= 2048 ? 2 : N <= 4096 ? 4 : 8;
@@ -958,9 +1100,8 @@ int hpcs_linkage_f64(const float* leaves, int B, int N, int D, int method, doubl
     int* moff = reinterpret_cast<int*>(w + L.off_moff);
     int* nd = reinterpret_cast<int*>(w + L.off_nd);
     int* tie = reinterpret_cast<int*>(w + L.off_tie);
-    boruvka_rowmin_fold_kernel<<<dim3((N + 255) / 256, B), 256, 0, st>>>(reinterpret_cast<double*>(w + L.off_pmv), reinterpret_cast<int*>(w + L.off_pmj),
-                                                                        N, T, rmw, rmj);
-    if ((rc = check_launch("boruvka_rowmin_fold_kernel"))) return rc;
+    boruvka_rowmin_kernel<<<dim3(N, B), 256, 0, st>>>(dm, stride0, N, nd, 0, rmw, rmj, N);
+    if ((rc = check_launch("boruvka_rowmin_kernel"))) return rc;
     for (int r = 0; r < L.rounds; ++r) {
         const int cap = L.pitch[r], cap2 = L.pitch[r + 1];
         const int* rep_in = r ? reinterpret_cast<int*>(w + L.off_rep[r]) : nullptr;
