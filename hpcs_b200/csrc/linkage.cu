@@ -3,8 +3,8 @@
 // Replaces, per cloud, the D2H copy + scipy.cluster.hierarchy.linkage(leaves, method, 'cosine')
 // of BaseSimilarityHypHC._decode_linkage (hpcs/models/base_hyp_hc.py:81-86) and the Python loop
 // over clouds at :135-137: all B clouds are decoded by one launch sequence, one CTA per cloud.
-//   1. pdist_cosine_kernel  -- fp64 cosine distance matrix, bit-identical to scipy's pdist
-//      (two running sums over even/odd elements, see oracle), 64x64 tiles, 4x4 outputs per thread on DFMA;
+//   1. pdist_norms_kernel + pdist_mma_kernel  -- fp64 cosine distance matrix, bit-identical to scipy's pdist
+//      (two running sums over even/odd elements, see oracle), on the fp64 tensor cores (mma.sync m8n8k4);
 //   2. linkage_kernel<0,.>  -- 'single': Prim's MST from node 0 over matrix rows (what scipy's
 //      mst_single_linkage does); a thread keeps the running minima of its columns in registers, loads
 //      its part of the row in one batch and the block takes a (value, index) arg-min with redux.sync
@@ -24,126 +24,13 @@ namespace hpcs {
 
 constexpr int kPT = 64;           // pdist tile edge
 constexpr int kPLD = kPT + 2;     // shared-memory row pitch in doubles (keeps 16-byte alignment, spreads banks)
-constexpr int kNoIdxPd = 0x7fffffff;
 
-// fp64 cosine distance matrix, bit-identical to scipy's pdist(., 'cosine') on the same fp32 rows.
-// grid: (T*(T+1)/2 upper 64x64 tiles, B); block (64/MR) x 16 threads, MR x 4 outputs each: rows ty*MR+ii, columns
-// tx+16*jj.  The kernel is bound by shared-memory operand delivery (128 B/clk/SM against 64 DFMA lanes/clk/SM), so the
-// taller micro-tile (MR = 8: 12 doubles loaded per 32 DFMA) would help if occupancy held; at 178 registers it does not.  dm[b][i][j] full symmetric, zero diagonal.
-// scipy sums a dot product as two running sums (even / odd elements, separate multiply and add), added at the end,
-// an odd tail element last.  Every operand here is an fp32 value widened to fp64, so a product has at most 48
-// significant bits and is exact in fp64: fma(a, b, acc) rounds the same real number as add(mul(a, b), acc) and gives
-// the same bits.  The kernel therefore runs on DFMA (half the fp64 instructions) without changing any result.
-template <int MR>                               // rows per thread: 64 / MR x 16 threads, MR x 4 outputs each
-__global__ void __launch_bounds__(1024 / MR)
-pdist_cosine_kernel(const float* __restrict__ leaves, int N, int D, double* __restrict__ dm) {
-    extern __shared__ __align__(16) double sm[];
-    double* as = sm;                          // [D][kPLD] rows of the i-tile, feature-major
-    double* bs = as + (size_t)D * kPLD;       // [D][kPLD] rows of the j-tile
-    double* na = bs + (size_t)D * kPLD;       // [64] norms
-    double* nb = na + kPT;
-    const int b = blockIdx.y;
-    const int T = (N + kPT - 1) / kPT;
-    int bi = 0, rem = blockIdx.x;             // linear upper-triangular tile index -> (bi, bj), bi <= bj
-    while (rem >= T - bi) { rem -= T - bi; ++bi; }
-    const int bj = bi + rem;
-    const float* lb = leaves + (size_t)b * N * D;
-    for (int e = threadIdx.x; e < kPT * D; e += blockDim.x) {
-        const int r = e / D, q = e - r * D;
-        const int gi = bi * kPT + r, gj = bj * kPT + r;
-        as[q * kPLD + r] = gi < N ? (double)__ldg(lb + (size_t)gi * D + q) : 0.0;
-        bs[q * kPLD + r] = gj < N ? (double)__ldg(lb + (size_t)gj * D + q) : 0.0;
-    }
-    __syncthreads();
-    if (threadIdx.x < 2 * kPT) {
-        const double* src = (threadIdx.x >= kPT ? bs : as) + (threadIdx.x & (kPT - 1));
-        double even = 0.0, odd = 0.0;
-        int q = 0;
-        for (; q + 1 < D; q += 2) {
-            const double v0 = src[q * kPLD], v1 = src[(q + 1) * kPLD];
-            even = fma(v0, v0, even);
-            odd = fma(v1, v1, odd);
-        }
-        double s = __dadd_rn(even, odd);
-        if (D & 1) { const double v = src[(D - 1) * kPLD]; s = fma(v, v, s); }
-        (threadIdx.x >= kPT ? nb : na)[threadIdx.x & (kPT - 1)] = __dsqrt_rn(s);
-    }
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    double ev[MR][4], od[MR][4];
-#pragma unroll
-    for (int ii = 0; ii < MR; ++ii)
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) { ev[ii][jj] = 0.0; od[ii][jj] = 0.0; }
-    const double* ap = as + ty * MR;
-    const double* bp = bs + tx;
-    int q = 0;
-    for (; q + 1 < D; q += 2) {
-        double a[MR], c[MR], be[4], bo[4];
-#pragma unroll
-        for (int ii = 0; ii < MR; ii += 2) {
-            const double2 t0 = *reinterpret_cast<const double2*>(ap + q * kPLD + ii);
-            const double2 t1 = *reinterpret_cast<const double2*>(ap + (q + 1) * kPLD + ii);
-            a[ii] = t0.x; a[ii + 1] = t0.y;
-            c[ii] = t1.x; c[ii + 1] = t1.y;
-        }
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) { be[jj] = bp[q * kPLD + 16 * jj]; bo[jj] = bp[(q + 1) * kPLD + 16 * jj]; }
-#pragma unroll
-        for (int ii = 0; ii < MR; ++ii)
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                ev[ii][jj] = fma(a[ii], be[jj], ev[ii][jj]);
-                od[ii][jj] = fma(c[ii], bo[jj], od[ii][jj]);
-            }
-    }
-    __syncthreads();                           // norms written
-    double* db = dm + (size_t)b * N * N;
-    const bool vec_ok = (N & 3) == 0;          // rows start 32-byte aligned
-    const int gi0 = bi * kPT + ty * MR;
-#pragma unroll
-    for (int ii = 0; ii < MR; ++ii) {
-        const int i = ty * MR + ii;
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-            const int j = tx + 16 * jj;
-            double s = __dadd_rn(ev[ii][jj], od[ii][jj]);
-            if (D & 1) s = fma(as[(D - 1) * kPLD + i], bs[(D - 1) * kPLD + j], s);
-            double cs = __ddiv_rn(s, __dmul_rn(na[i], nb[j]));
-            if (fabs(cs) > 1.0) cs = copysign(1.0, cs);
-            const double r = (bi * kPT + i == bj * kPT + j) ? 0.0 : __dsub_rn(1.0, cs);
-            ev[ii][jj] = r;                    // results replace the accumulators
-            const int gj = bj * kPT + j;
-            if (gi0 + ii < N && gj < N) db[(size_t)(gi0 + ii) * N + gj] = r;      // 16 lanes x 8 B contiguous
-        }
-    }
-    if (bi != bj) {                            // mirrored tile: this thread's MR rows are MR consecutive columns there
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-            const int gj = bj * kPT + tx + 16 * jj;
-            if (gj >= N) continue;
-            double* dst = db + (size_t)gj * N + gi0;
-            if (vec_ok && gi0 + MR - 1 < N) {
-#pragma unroll
-                for (int ii = 0; ii < MR; ii += 2) *reinterpret_cast<double2*>(dst + ii) = make_double2(ev[ii][jj], ev[ii + 1][jj]);
-            } else {
-#pragma unroll
-                for (int ii = 0; ii < MR; ++ii) if (gi0 + ii < N) dst[ii] = ev[ii][jj];
-            }
-        }
-    }
-}
-
-// ---- row-block form of the distance kernel (the one that runs) -----------------------------------------------------
-// Same arithmetic and output as pdist_cosine_kernel above; what changes is the schedule.  A CTA owns one 64-row block
-// `bi` of one cloud and walks the column blocks bj = bi .. T-1 itself: the A tile and its norms are staged once, the
-// next B tile is fetched from global memory into registers WHILE the current tile is computed (so the load latency
-// that took a quarter of the tile-per-CTA kernel's samples is hidden), norms come from a one-off norms kernel instead
-// of being recomputed per tile, and the runtime division by D in the staging index is a multiply-high.
-// With ROWMIN the kernel also delivers what the first Boruvka round needs -- the (distance, index) arg-min of every
-// matrix row -- without a second pass over the matrix: a thread keeps the running minima of its 4 rows over every
-// tile it computes (direct orientation), column minima of a tile (the mirrored orientation: rows of block bj against
-// columns of block bi) are combined across the CTA through shared memory, and both land as per-(row, column-block)
-// partials pmin[slot][row] that a tiny kernel folds.  Ties resolve to the lower index everywhere (lexicographic min).
+// ---- distance matrix ------------------------------------------------------------------------------------------------
+// fp64 cosine distances, bit-identical to scipy's pdist(., 'cosine') on the same fp32 rows: dm[b][i][j] full symmetric,
+// zero diagonal.  scipy sums a dot product as two running sums (even / odd elements, separate multiply and add), added
+// at the end, an odd tail element last; norms the same way; then 1 - dot / (n_i n_j).  Every operand here is an fp32
+// value widened to fp64, so a product has at most 48 significant bits and is exact in fp64: fma(a, b, acc) rounds the
+// same real number as add(mul(a, b), acc) and gives the same bits.
 __global__ void pdist_norms_kernel(const float* __restrict__ leaves, size_t rows, int D, double* __restrict__ norms) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows) return;
@@ -160,188 +47,7 @@ __global__ void pdist_norms_kernel(const float* __restrict__ leaves, size_t rows
     norms[i] = __dsqrt_rn(s);
 }
 
-__device__ __forceinline__ void lex_take(double& v, int& j, double ov, int oj) {
-    if (ov < v || (ov == v && oj < j)) { v = ov; j = oj; }
-}
-
-// PF = floats a thread prefetches per B tile (64 * D <= 256 * PF); PF = 0: any D, no prefetch.
-template <int PF, bool ROWMIN>
-__global__ void __launch_bounds__(256, 2)
-pdist_rowblock_kernel(const float* __restrict__ leaves, const double* __restrict__ norms, int N, int D, unsigned d_magic,
-                      double* __restrict__ dm, double* __restrict__ pmin_v, int* __restrict__ pmin_j) {
-    extern __shared__ __align__(16) double sm[];
-    double* as = sm;                          // [D][kPLD]
-    double* bs = as + (size_t)D * kPLD;       // [D][kPLD]
-    double* na = bs + (size_t)D * kPLD;       // [64]
-    double* nb = na + kPT;                    // [64]
-    double* wv = nb + kPT;                    // ROWMIN: [8 warps][64 cols] column minima of the current tile
-    int* wj = reinterpret_cast<int*>(wv + 8 * kPT);
-    const int b = blockIdx.y, bi = blockIdx.x;
-    const int T = (N + kPT - 1) / kPT;
-    const float* lb = leaves + (size_t)b * N * D;
-    const double* nrm = norms + (size_t)b * N;
-    double* db = dm + (size_t)b * N * N;
-    const int tile_elems = kPT * D;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const bool vec_ok = (N & 3) == 0;
-
-    auto stage = [&](double* dst, double* ndst, int blk) {        // plain staging (A tile; B tiles when PF == 0)
-        for (int e = threadIdx.x; e < tile_elems; e += 256) {
-            const int r = (int)__umulhi((unsigned)e, d_magic), q = e - r * D;
-            const int g = blk * kPT + r;
-            dst[q * kPLD + r] = g < N ? (double)__ldg(lb + (size_t)g * D + q) : 0.0;
-        }
-        if (threadIdx.x < kPT) { const int g = blk * kPT + threadIdx.x; ndst[threadIdx.x] = g < N ? nrm[g] : 0.0; }
-    };
-    float pre[PF > 0 ? PF : 1];
-    double pre_n = 0.0;
-    auto prefetch = [&](int blk) {                                  // global -> registers, consumed after the tile
-        if (PF > 0) {
-            const float* src = lb + (size_t)blk * kPT * D;
-            const int left = (N - blk * kPT) * D;                    // floats of the cloud from this block on
-#pragma unroll
-            for (int i = 0; i < PF; ++i) {
-                const int e = threadIdx.x + 256 * i;
-                pre[i] = (e < tile_elems && e < left) ? __ldg(src + e) : 0.f;
-            }
-            if (threadIdx.x < kPT) { const int g = blk * kPT + threadIdx.x; pre_n = g < N ? nrm[g] : 0.0; }
-        }
-    };
-    auto commit = [&]() {                                           // registers -> bs / nb
-        if (PF > 0) {
-#pragma unroll
-            for (int i = 0; i < PF; ++i) {
-                const int e = threadIdx.x + 256 * i;
-                if (e < tile_elems) {
-                    const int r = (int)__umulhi((unsigned)e, d_magic), q = e - r * D;
-                    bs[q * kPLD + r] = (double)pre[i];
-                }
-            }
-            if (threadIdx.x < kPT) nb[threadIdx.x] = pre_n;
-        }
-    };
-
-    stage(as, na, bi);
-    if (PF > 0) { prefetch(bi); commit(); } else stage(bs, nb, bi);
-    __syncthreads();
-
-    double best_v[4];                                               // ROWMIN: running minima of this thread's rows
-    int best_j[4];
-#pragma unroll
-    for (int ii = 0; ii < 4; ++ii) { best_v[ii] = INFINITY; best_j[ii] = kNoIdxPd; }
-    const int gi0 = bi * kPT + ty * 4;
-    const double* ap = as + ty * 4;
-    const double* bp = bs + tx;
-
-    for (int bj = bi; bj < T; ++bj) {
-        if (bj + 1 < T) prefetch(bj + 1);
-        double ev[4][4], od[4][4];
-#pragma unroll
-        for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) { ev[ii][jj] = 0.0; od[ii][jj] = 0.0; }
-        int q = 0;
-        for (; q + 1 < D; q += 2) {
-            const double2 a01 = *reinterpret_cast<const double2*>(ap + q * kPLD);
-            const double2 a23 = *reinterpret_cast<const double2*>(ap + q * kPLD + 2);
-            const double2 c01 = *reinterpret_cast<const double2*>(ap + (q + 1) * kPLD);
-            const double2 c23 = *reinterpret_cast<const double2*>(ap + (q + 1) * kPLD + 2);
-            const double a[4] = {a01.x, a01.y, a23.x, a23.y};
-            const double c[4] = {c01.x, c01.y, c23.x, c23.y};
-            double be[4], bo[4];
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) { be[jj] = bp[q * kPLD + 16 * jj]; bo[jj] = bp[(q + 1) * kPLD + 16 * jj]; }
-#pragma unroll
-            for (int ii = 0; ii < 4; ++ii)
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    ev[ii][jj] = fma(a[ii], be[jj], ev[ii][jj]);
-                    od[ii][jj] = fma(c[ii], bo[jj], od[ii][jj]);
-                }
-        }
-        double cmin_v[4];                                           // ROWMIN, mirrored orientation: per column of mine
-        int cmin_i[4];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) { cmin_v[jj] = INFINITY; cmin_i[jj] = kNoIdxPd; }
-#pragma unroll
-        for (int ii = 0; ii < 4; ++ii) {
-            const int i = ty * 4 + ii;
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const int j = tx + 16 * jj;
-                double s = __dadd_rn(ev[ii][jj], od[ii][jj]);
-                if (D & 1) s = fma(as[(D - 1) * kPLD + i], bs[(D - 1) * kPLD + j], s);
-                double cs = __ddiv_rn(s, __dmul_rn(na[i], nb[j]));
-                if (fabs(cs) > 1.0) cs = copysign(1.0, cs);
-                const int gi = gi0 + ii, gj = bj * kPT + j;
-                const double r = gi == gj ? 0.0 : __dsub_rn(1.0, cs);
-                ev[ii][jj] = r;                                     // results replace the accumulators
-                if (gi < N && gj < N) {
-                    db[(size_t)gi * N + gj] = r;                    // 16 lanes x 8 B contiguous
-                    if (ROWMIN && gi != gj) {
-                        if (r < best_v[ii]) { best_v[ii] = r; best_j[ii] = gj; }             // gj ascends: lowest index wins ties
-                        if (bi != bj && r < cmin_v[jj]) { cmin_v[jj] = r; cmin_i[jj] = gi; }   // gi ascends over ii
-                    }
-                }
-            }
-        }
-        if (bi != bj) {                                             // mirrored tile
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const int gj = bj * kPT + tx + 16 * jj;
-                if (gj < N) {
-                    double* dst = db + (size_t)gj * N + gi0;
-                    if (vec_ok && gi0 + 3 < N) {
-                        *reinterpret_cast<double2*>(dst) = make_double2(ev[0][jj], ev[1][jj]);
-                        *reinterpret_cast<double2*>(dst + 2) = make_double2(ev[2][jj], ev[3][jj]);
-                    } else {
-#pragma unroll
-                        for (int ii = 0; ii < 4; ++ii) if (gi0 + ii < N) dst[ii] = ev[ii][jj];
-                    }
-                }
-                if (ROWMIN) {                                       // the two ty halves of the warp, then one entry per warp
-                    const double ov = __shfl_xor_sync(kFull, cmin_v[jj], 16);
-                    const int oi = __shfl_xor_sync(kFull, cmin_i[jj], 16);
-                    lex_take(cmin_v[jj], cmin_i[jj], ov, oi);
-                    if (lane < 16) { wv[warp * kPT + tx + 16 * jj] = cmin_v[jj]; wj[warp * kPT + tx + 16 * jj] = cmin_i[jj]; }
-                }
-            }
-        }
-        __syncthreads();                                            // tile consumed; column minima of all warps visible
-        if (ROWMIN && bi != bj && threadIdx.x < kPT) {
-            const int gj = bj * kPT + threadIdx.x;
-            if (gj < N) {
-                double v = wv[threadIdx.x];
-                int j = wj[threadIdx.x];
-#pragma unroll
-                for (int w = 1; w < 8; ++w) lex_take(v, j, wv[w * kPT + threadIdx.x], wj[w * kPT + threadIdx.x]);
-                pmin_v[((size_t)b * T + bi) * N + gj] = v;          // slot bi of row gj: its minimum over column block bi
-                pmin_j[((size_t)b * T + bi) * N + gj] = j;
-            }
-        }
-        if (bj + 1 < T) { if (PF > 0) commit(); else stage(bs, nb, bj + 1); }
-        __syncthreads();
-    }
-    if (ROWMIN) {
-        // direct orientation: fold the 16 tx lanes of a row (a half-warp) and store slot bi of rows gi0 .. gi0+3
-#pragma unroll
-        for (int ii = 0; ii < 4; ++ii) {
-#pragma unroll
-            for (int o = 8; o > 0; o >>= 1) {
-                const double ov = __shfl_xor_sync(kFull, best_v[ii], o);
-                const int oj = __shfl_xor_sync(kFull, best_j[ii], o);
-                lex_take(best_v[ii], best_j[ii], ov, oj);
-            }
-            if (tx == 0 && gi0 + ii < N) {
-                pmin_v[((size_t)b * T + bi) * N + gi0 + ii] = best_v[ii];
-                pmin_j[((size_t)b * T + bi) * N + gi0 + ii] = best_j[ii];
-            }
-        }
-    }
-}
-
-// ---- fp64 tensor-core form (the one that runs) -----------------------------------------------------------------------
+// ---- the distance kernel, on the fp64 tensor cores -----------------------------------------------------------------
 // mma.sync.m8n8k4.f64 adds its four products as an FMA chain in ascending k (measured on B200 with
 // tools/probes/dmma_order_probe.cu: 128000 of 128000 outputs equal the chain bit for bit, 95.7 % equal a descending
 // chain or a single rounding of the exact sum).  scipy's dot product is two such chains -- over the even and over the
@@ -351,8 +57,13 @@ pdist_rowblock_kernel(const float* __restrict__ leaves, const double* __restrict
 // flops (64 fp64 FMA lanes per SM per clock either way) but operand delivery: a thread loads ONE double per operand
 // fragment for 8 FMAs, 2 B per FMA against 4 B at a 4x4 register tile, and issues one instruction per 256 FMAs -- the
 // DFMA kernel sat at 61 % of the shared-memory pipe with the fp64 pipe 28 % busy.
-// Schedule as pdist_rowblock_kernel: CTA = (row block bi, cloud), walks bj = bi .. T-1, B tiles prefetched through
-// registers.  Warp w: rows 16 (w >> 1) .. +15, columns 32 (w & 1) .. +31 of the 64x64 tile = 2 x 4 MMA tiles, two
+// Earlier forms, measured at B=64, N=1024 / 8192: one 64x64 tile per CTA on DFMA, 4x4 outputs per thread: 333 us /
+// 20.0 ms (an 8x4 micro-tile: 399 us / 23.0 ms -- 178 registers, half the warps); the same with the schedule below:
+// no faster (the staging was not the limit); this kernel: 227 us / 10.6 ms.
+// Schedule: CTA = (64-row block bi, cloud); it stages the A tile and its norms once and walks the column blocks
+// bj = bi .. T-1 itself, the next B tile fetched from global memory into registers (PF floats per thread, 64 D <= 256 PF;
+// PF = 0: any D, no prefetch) while the current one is computed; norms come from pdist_norms_kernel; the runtime
+// division by D in the staging index is a multiply-high.  Warp w: rows 16 (w >> 1) .. +15, columns 32 (w & 1) .. +31 of the 64x64 tile = 2 x 4 MMA tiles, two
 // accumulator fragments (even / odd chain) each.  Fragment coordinates: g = lane >> 2, t = lane & 3; A[row g][k t],
 // B[k t][col g], C[row g][cols 2t, 2t+1].  Shared memory holds the tiles feature-major with the features of a slice
 // step interleaved as the fragments want them; rows [2P, 8S) stay zero, the odd tail feature lives in row 8S.
@@ -482,20 +193,6 @@ pdist_mma_kernel(const float* __restrict__ leaves, const double* __restrict__ no
         if (bj + 1 < T) { if (PF > 0) commit(); else stage(bs, nb, bj + 1); }
         __syncthreads();
     }
-}
-
-// fold the per-column-block partials of every row: slots 0 .. block(row)
-__global__ void __launch_bounds__(256)
-boruvka_rowmin_fold_kernel(const double* __restrict__ pmin_v, const int* __restrict__ pmin_j, int N, int T,
-                           double* __restrict__ rmw, int* __restrict__ rmj) {
-    const int b = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= N) return;
-    double v = INFINITY;
-    int j = kNoIdxPd;
-    const int last = i / kPT;
-    for (int s = 0; s <= last; ++s) lex_take(v, j, pmin_v[((size_t)b * T + s) * N + i], pmin_j[((size_t)b * T + s) * N + i]);
-    rmw[(size_t)b * N + i] = v;
-    rmj[(size_t)b * N + i] = j;
 }
 
 __device__ __forceinline__ bool am_less(double v, int i, double ov, int oi) { return v < ov || (v == ov && i < oi); }
@@ -961,11 +658,40 @@ boruvka_contract_kernel(const double* __restrict__ in_all, size_t in_stride, int
     __syncthreads();
     double bv = INFINITY;
     int bi = kNoIdx;
-    for (int C = threadIdx.x; C < n2; C += blockDim.x) {
+    // Four components per thread at a time, their list bounds loaded together, then the first four members of each
+    // (components have about three): two dependent L2 latencies per batch instead of two per component.
+    // (Only worth it when a thread has several components: measured 61.7 -> 69.7 us per launch at N = 1024, but
+    // 4.2 -> 3.7 ms at N = 8192.)
+    const bool batched = n2 > 4 * (int)blockDim.x;
+    for (int C = threadIdx.x; !batched && C < n2; C += blockDim.x) {
         double m = INFINITY;
         for (int t = moff[C]; t < moff[C + 1]; ++t) m = fmin(m, colmin[memb[t]]);
         out[C] = m;
         if (C != A && m < bv) { bv = m; bi = C; }
+    }
+    for (int C0 = threadIdx.x; batched && C0 < n2; C0 += 4 * blockDim.x) {
+        int lo[4], hi[4], mem[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int C = C0 + u * blockDim.x;
+            lo[u] = C < n2 ? moff[C] : 0;
+            hi[u] = C < n2 ? moff[C + 1] : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int w = 0; w < 4; ++w) mem[u][w] = lo[u] < hi[u] ? memb[min(lo[u] + w, hi[u] - 1)] : 0;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int C = C0 + u * blockDim.x;
+            if (C >= n2) continue;
+            double m = INFINITY;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) m = fmin(m, colmin[mem[u][w]]);
+            for (int t = lo[u] + 4; t < hi[u]; ++t) m = fmin(m, colmin[memb[t]]);
+            out[C] = m;
+            if (C != A && m < bv) { bv = m; bi = C; }
+        }
     }
     unsigned phase = 0u;
     const LexKey r = block_lexmin(bv, bi, scratch, phase);
@@ -988,7 +714,7 @@ constexpr int kMaxRounds = 3;
 struct LinkWs {
     int rounds;                       // Boruvka rounds before Prim (single linkage, N >= 256), else 0
     int pitch[kMaxRounds + 1];        // row pitch (= node capacity) of matrix r
-    size_t off_m[kMaxRounds + 1], off_recx, off_recy, off_rech, off_rmw, off_rmj, off_memb, off_moff, off_nd, off_tie, off_norm, off_pmv, off_pmj;
+    size_t off_m[kMaxRounds + 1], off_recx, off_recy, off_rech, off_rmw, off_rmj, off_memb, off_moff, off_nd, off_tie, off_norm;
     size_t off_rep[kMaxRounds + 1];
     size_t total;
 };
@@ -1012,9 +738,6 @@ static LinkWs link_ws(int B, int N, int method) {
         L.off_moff = take((size_t)B * (N + 1) * sizeof(int));
         L.off_nd = take((size_t)B * 8 * sizeof(int));
         L.off_tie = take((size_t)B * sizeof(int));
-        const size_t T = (size_t)(N + kPT - 1) / kPT;
-        L.off_pmv = take((size_t)B * T * N * sizeof(double));
-        L.off_pmj = take((size_t)B * T * N * sizeof(int));
         for (int r = 1; r <= L.rounds; ++r) L.off_rep[r] = take((size_t)B * L.pitch[r] * sizeof(int));
     }
     L.total = off;
@@ -1055,8 +778,6 @@ int hpcs_linkage_f64(const float* leaves, int B, int N, int D, int method, doubl
     const int NP2 = next_pow2(N - 1 > 1 ? N - 1 : 2);
     const size_t smem_link = ((size_t)12 * (NP2 > N ? NP2 : N) + 15) / 16 * 16 + (size_t)16 * N;
     if (smem_link > 227 * 1024) return fail(HPCS_ERR_ARG, "linkage: N=%d too large (max 8192)", N);
-    const size_t smem_pd = ((size_t)2 * D * kPLD + 2 * kPT) * sizeof(double);
-    if (smem_pd > 200 * 1024) return fail(HPCS_ERR_ARG, "linkage: D=%d too large", D);
     cudaStream_t st = as_stream(stream);
     const LinkWs L = link_ws(B, N, method);
     char* w = static_cast<char*>(ws);
