@@ -507,7 +507,8 @@ def _check_Z(Z, ref):
 
 
 @pytest.mark.parametrize("method", ["single", "complete"])
-@pytest.mark.parametrize("N,D", [(96, 32), (200, 32), (1024, 32), (150, 5), (64, 50), (300, 32), (777, 7), (1500, 32)])
+@pytest.mark.parametrize("N,D", [(96, 32), (200, 32), (1024, 32), (150, 5), (64, 50), (300, 32), (777, 7), (1500, 32),
+                                 (300, 70), (130, 33), (257, 2), (90, 1)])
 def test_linkage_bit_exact_vs_scipy(hb, method, N, D):
     from scipy.cluster.hierarchy import linkage
     gen = torch.Generator().manual_seed(N + D)
