@@ -43,7 +43,7 @@ METRIC = "point clouds/sec (1024 pts, k=20) fwd+bwd"
 UNIT = "clouds/s"
 
 
-# DRAM bytes per op from the committed `ncu --set full` capture (profiles/r01_b_ops_ncu_full.md): read + written,
+# DRAM bytes per op from the committed `ncu --set full` capture (profiles/r01_d_ncu_full.md): read + written,
 # summed over the op's kernels (edge bwd = reverse-graph build 5.3 MB + gather 332.9 + 9.8 MB; edge fwd 13.5 + 273.0 MB,
 # below the algorithmic 343.8 MB because the tail of the output is still in L2 when the kernel ends)
 NCU_TRAFFIC_BYTES = {"edge_bwd_c21": 348.0e6, "edge_fwd_c21": 286.5e6}
@@ -418,7 +418,7 @@ def run_native(args):
     top = max((n for n in ops if ops[n].get("peak")), key=lambda n: ops[n]["share"])
     roofline = {"kernel": top, "bound": ops[top]["bound"], "achieved": ops[top]["achieved"], "peak": ops[top]["peak"],
                 "unit": ops[top]["unit"], "frac": ops[top]["frac"], "traffic": NCU_TRAFFIC_BYTES.get(top),
-                "traffic_source": "profiles/r01_b_ops_ncu_full.md (dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+                "traffic_source": "profiles/r01_d_ncu_full.md (dram__bytes_read.sum + dram__bytes_write.sum per launch)",
                 "algorithmic_bytes": work[top].get("bytes"), "peak_source": pk["source"]}
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,

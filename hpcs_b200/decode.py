@@ -61,3 +61,28 @@ def decode_linkage(leaves_embeddings: torch.Tensor, scale: torch.Tensor, method:
     """One cloud [N,D] -> numpy Z[N-1,4] float64, the reference's return type."""
     Z = decode_linkage_batch(leaves_embeddings.unsqueeze(0), scale, method)
     return Z[0].cpu().numpy()
+
+
+def fcluster_maxclust(Z: torch.Tensor, ks) -> torch.Tensor:
+    """``scipy.cluster.hierarchy.fcluster(Z[b], k, criterion='maxclust')`` for every cloud ``b`` and every ``k`` in
+    ``ks``, on the GPU: Z[B,N-1,4] (or [N-1,4]) fp64 as returned by :func:`decode_linkage_batch` -> int32 labels
+    [B,K,N] (1-based, scipy's cluster numbering).  Replaces the per-k host calls of ``get_optimal_k``
+    (hpcs/utils/scores.py:141-177, ``fcluster(linkage_matrix, k, criterion='maxclust')`` at :151) so Z never leaves
+    the device."""
+    single = Z.dim() == 2
+    Zb = Z.unsqueeze(0) if single else Z
+    if Zb.dim() != 3 or Zb.shape[2] != 4 or Zb.dtype != torch.float64:
+        raise ValueError(f"expected Z[B,N-1,4] float64, got {tuple(Z.shape)} {Z.dtype}")
+    dev = _lib.require_cuda(Zb)
+    lib = _lib.load()
+    ks = [int(k) for k in ks]
+    if not ks or min(ks) < 1:
+        raise ValueError("ks must be a non-empty list of k >= 1")
+    B, M, _ = Zb.shape
+    Zc = Zb.contiguous()
+    ks_dev = torch.tensor(ks, dtype=torch.int32, device=dev)
+    labels = torch.empty((B, len(ks), M + 1), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.hpcs_fcluster_maxclust_i32(Zc.data_ptr(), B, M + 1, ks_dev.data_ptr(), len(ks), max(ks),
+                                                  labels.data_ptr(), _lib.stream_ptr(dev)), "hpcs_fcluster_maxclust_i32")
+    return labels[0] if single else labels

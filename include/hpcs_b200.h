@@ -150,6 +150,14 @@ size_t hpcs_linkage_workspace_bytes(int B, int N, int D, int method);
 int hpcs_linkage_f64(const float* leaves, int B, int N, int D, int method, double* Z,
                      void* ws, size_t ws_bytes, void* stream);
 
+/* scipy.cluster.hierarchy.fcluster(Z, k, criterion='maxclust') for a batch   (hpcs/utils/scores.py:151)
+ *   Z[B,N-1,4] fp64 in scipy linkage format with non-decreasing heights (what hpcs_linkage_f64 writes), ks[K] device
+ *   ints, k_max = max(ks) <= 256 (host copy, for validation) -> labels[B,K,N] int32, 1-based, with scipy's exact cluster
+ *   numbering (depth-first, left child first; subtrees numbered on entry, singleton leaves on the way out; k >= N:
+ *   label = point index + 1); tied heights are never split, so ties can give fewer than k clusters, as in scipy. */
+int hpcs_fcluster_maxclust_i32(const double* Z, int B, int N, const int* ks, int K, int k_max, int32_t* labels,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -397,3 +397,58 @@ def linkage_restated(dm: np.ndarray, method: str) -> np.ndarray:
         raise ValueError(method)
     order = np.argsort(np.array([r[2] for r in rows]), kind="stable")
     return _label([rows[i] for i in order], n)
+
+
+def fcluster_maxclust_restated(Z: np.ndarray, k: int) -> np.ndarray:
+    """scipy.cluster.hierarchy.fcluster(Z, k, 'maxclust') restated (scipy/cluster/_hierarchy.pyx: cluster_maxclust_monocrit
+    + cluster_monocrit) for a monotone Z, the way csrc/cut.cu evaluates it: the cut merges the fewest rows that leave
+    <= k clusters (whole runs of equal heights), then the depth-first numbering restricted to the rows above the
+    cutoff, subtrees filled through the dendrogram's leaf order.  Checked against scipy itself in tests/test_oracle_golden.py."""
+    Z = np.asarray(Z, dtype=np.float64)
+    M = Z.shape[0]
+    N = M + 1
+    if k >= N:                          # scipy's shortcut: every point its own cluster, numbered by point index
+        return np.arange(1, N + 1, dtype=np.int32)
+    left, right, size, h = Z[:, 0].astype(int), Z[:, 1].astype(int), Z[:, 3].astype(int), Z[:, 2]
+    lo = np.zeros(2 * N - 1, dtype=int)
+    for i in range(M - 1, -1, -1):
+        lo[left[i]] = lo[N + i]
+        lo[right[i]] = lo[N + i] + (1 if left[i] < N else size[left[i] - N])
+    order = np.zeros(N, dtype=int)
+    order[lo[:N]] = np.arange(N)
+    j = N - k - 1                       # merging rows 0..j leaves k clusters
+    c = 0                               # rows with height <= cutoff: [0, c)
+    if j >= 0:
+        c = j + 1
+        while c < M and h[c] == h[j]:   # a cut cannot split a run of equal heights: fewer than k clusters then
+            c += 1
+    clusters = []
+    if M - 1 < c:
+        clusters.append(N + M - 1)
+    else:
+        stack = [[M - 1, 0]]
+        while stack:
+            row, st = stack[-1]
+            l, r = left[row], right[row]
+            if st == 0:
+                stack[-1][1] = 1
+                if l >= N:
+                    if l - N >= c:
+                        stack.append([l - N, 0]); continue
+                    clusters.append(l)
+            if stack[-1][1] == 1:
+                stack[-1][1] = 2
+                if r >= N:
+                    if r - N >= c:
+                        stack.append([r - N, 0]); continue
+                    clusters.append(r)
+            if l < N:
+                clusters.append(l)
+            if r < N:
+                clusters.append(r)
+            stack.pop()
+    T = np.zeros(N, dtype=np.int32)
+    for cid, node in enumerate(clusters, start=1):
+        cnt = 1 if node < N else size[node - N]
+        T[order[lo[node]:lo[node] + cnt]] = cid
+    return T

@@ -558,6 +558,34 @@ def test_linkage_boruvka_path_ties_and_clusters(hb):
             _check_Z(Z[b].cpu().numpy(), linkage(leaves[b].cpu().numpy(), method="single", metric="cosine"))
 
 
+def test_fcluster_maxclust_matches_scipy(hb):
+    """hpcs_fcluster_maxclust_i32 == scipy.cluster.hierarchy.fcluster(Z, k, 'maxclust') label for label (partition AND
+    numbering), on Z produced by the GPU decoder (single and complete) and on scipy's own Z with tied heights."""
+    from scipy.cluster.hierarchy import fcluster, linkage
+    gen = torch.Generator().manual_seed(17)
+    cen = torch.randn(5, 32, generator=gen)
+    x = O.expmap0(cen[torch.randint(0, 5, (3, 500), generator=gen)] + 0.25 * torch.randn(3, 500, 32, generator=gen))
+    ks = list(range(1, 12)) + [40, 200]
+    for method in ("single", "complete"):
+        Z = hb.decode_linkage_batch(dev(x), dev(torch.tensor([1e-3])), method)
+        lab = hb.fcluster_maxclust(Z, ks).cpu().numpy()
+        assert lab.shape == (3, len(ks), 500) and lab.dtype == np.int32
+        Zc = Z.cpu().numpy()
+        for b in range(3):
+            for i, k in enumerate(ks):
+                assert np.array_equal(lab[b, i], fcluster(Zc[b], k, criterion="maxclust")), (method, b, k)
+    rng = np.random.default_rng(3)
+    for n in (3, 4, 9, 64):
+        pts = rng.standard_normal((n, 4))
+        pts[n // 2:n // 2 + n // 4] = pts[:n // 4]                            # duplicates: tied heights
+        for method in ("single", "complete"):
+            Zs = linkage(pts, method=method)
+            ks2 = [k for k in (1, 2, 3, 5, n - 1, n, n + 2) if k >= 1]
+            got = hb.fcluster_maxclust(dev(torch.from_numpy(Zs)), ks2).cpu().numpy()
+            for i, k in enumerate(ks2):
+                assert np.array_equal(got[i], fcluster(Zs, k, criterion="maxclust")), (n, method, k)
+
+
 @pytest.mark.parametrize("key", ["96", "200", "clu"])
 def test_linkage_vs_reference_golden(hb, golden, key):
     """Golden Z comes from the reference pipeline (torch-CPU normalize + project + scipy).  The leaves

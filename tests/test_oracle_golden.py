@@ -150,3 +150,22 @@ def test_linkage_restatement_matches_scipy(method, D):
     assert np.array_equal(dm, squareform(pdist(X.astype(np.float64), "cosine")))
     Z = O.linkage_restated(dm, method)
     assert np.array_equal(Z, linkage(X.astype(np.float64), method=method, metric="cosine"))
+
+
+def test_fcluster_maxclust_restatement_matches_scipy():
+    """The cut rule and cluster numbering csrc/cut.cu implements, restated in numpy, against scipy.fcluster itself:
+    single and complete linkage, distinct and tied heights (duplicated points), k from 1 past N."""
+    from scipy.cluster.hierarchy import fcluster, linkage
+    rng = np.random.default_rng(5)
+    for n, dup in ((3, False), (4, False), (7, True), (40, False), (40, True), (300, False), (300, True)):
+        x = rng.standard_normal((n, 6))
+        if dup:
+            x[n // 2:n // 2 + n // 4] = x[:n // 4]                      # exact duplicates: tied heights
+        for method in ("single", "complete"):
+            Z = linkage(x, method=method, metric="euclidean")
+            for k in list(range(1, min(n, 12))) + [n - 2, n - 1, n, n + 3]:
+                if k < 1:
+                    continue
+                want = fcluster(Z, k, criterion="maxclust")
+                got = O.fcluster_maxclust_restated(Z, k)
+                assert np.array_equal(got, want), (n, dup, method, k)
