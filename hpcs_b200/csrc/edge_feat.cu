@@ -514,9 +514,10 @@ int hpcs_edge_feat_bwd_f32(const float* gout, const float* x, const int64_t* idx
         // warps per CTA: as many private histogram rows as fit in ~128 KB of shared memory
         const int G = (N + 31) / 32;
         int nw = 32;
-        while (nw > 1 && (size_t)nw * N * sizeof(int) > 128 * 1024) nw >>= 1;
-        const size_t smem = ((size_t)nw * N + (size_t)N + (N + 1) + (N + 2) + N + G + (G + 1)) * sizeof(int);
-        if (smem > 220 * 1024) return fail(HPCS_ERR_ARG, "edge_feat_bwd: N=%d too large (max ~9000)", N);
+        auto smem_for = [&](int w) { return ((size_t)w * N + (size_t)N + (N + 1) + (N + 2) + N + G + (G + 1)) * sizeof(int); };
+        while (nw > 1 && ((size_t)nw * N * sizeof(int) > 128 * 1024 || smem_for(nw) > 220 * 1024)) nw >>= 1;
+        const size_t smem = smem_for(nw);
+        if (smem > 220 * 1024) return fail(HPCS_ERR_ARG, "edge_feat_bwd: N=%d too large (max ~11000)", N);
         cudaFuncSetAttribute(edge_rev_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         edge_rev_build_kernel<<<B, nw * 32, smem, st>>>(idx, N, k, wsi);
         int rc = check_launch("edge_rev_build_kernel");

@@ -96,7 +96,7 @@ pdist_mma_kernel(const float* __restrict__ leaves, const double* __restrict__ no
     auto row_of = [&](int q) { return q < 2 * P ? q : 8 * S; };     // the odd tail feature goes to the last row
     auto stage = [&](double* dst, double* ndst, int blk) {
         for (int e = threadIdx.x; e < tile_elems; e += 256) {
-            const int r = (int)__umulhi((unsigned)e, d_magic), q = e - r * D;
+            const int r = D == 1 ? e : (int)__umulhi((unsigned)e, d_magic), q = e - r * D;     // (the magic number wraps to 0 for D = 1)
             const int gr = blk * kPT + r;
             dst[row_of(q) * kPLD + r] = gr < N ? (double)__ldg(lb + (size_t)gr * D + q) : 0.0;
         }
@@ -122,7 +122,7 @@ pdist_mma_kernel(const float* __restrict__ leaves, const double* __restrict__ no
             for (int i = 0; i < PF; ++i) {
                 const int e = threadIdx.x + 256 * i;
                 if (e < tile_elems) {
-                    const int r = (int)__umulhi((unsigned)e, d_magic), q = e - r * D;
+                    const int r = D == 1 ? e : (int)__umulhi((unsigned)e, d_magic), q = e - r * D;     // (the magic number wraps to 0 for D = 1)
                     bs[row_of(q) * kPLD + r] = (double)pre[i];
                 }
             }

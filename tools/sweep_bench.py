@@ -15,13 +15,29 @@ from hpcs_b200 import graph as hgraph  # noqa: E402
 
 
 def timed(fn, reps=10, warm=3):
-    for _ in range(warm):
-        fn()
+    """Average duration of fn in microseconds: captured into a CUDA graph and replayed (no Python / launch overhead in the
+    number, like bench.py's per-op timings); eager as a fallback."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(warm):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    run = fn
+    try:
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            fn()
+        run = graph.replay
+    except Exception:                                   # e.g. an op that cannot be captured: time it eagerly
+        torch.cuda.synchronize()
+    run()
     torch.cuda.synchronize()
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s.record()
     for _ in range(reps):
-        fn()
+        run()
     e.record()
     torch.cuda.synchronize()
     return s.elapsed_time(e) / reps * 1e3          # us
@@ -52,11 +68,14 @@ def main():
         # edge features (C = 21): skip shapes whose output would not fit comfortably
         C = 21
         out_bytes = B * 2 * C * 3 * N * k * 4
-        if out_bytes <= 24e9:
+        if N > 11000:
+            edge = "— | — (N beyond the general backward's shared-memory limit, ~11000)"
+        elif out_bytes <= 24e9:
             x = x63.view(B, C, 3, N)
             g = torch.randn(B, 2 * C, 3, N, k, device=dev, generator=gen)
             tf = timed(lambda: hgraph.edge_features_forward(x, i63), reps=5)
             tb = timed(lambda: hgraph.edge_features_backward(g, x, i63), reps=5)
+            fast = bool(hb._lib.load().hpcs_edge_feat_bwd_is_fast(g.data_ptr(), N, k, 0))
             byt = out_bytes + B * 3 * C * N * 4 + B * N * k * 8
             # gradient check on one cloud in float64
             gx = hgraph.edge_features_backward(g, x, i63)[0].double()
@@ -66,7 +85,7 @@ def main():
             ref.index_add_(1, idx0.reshape(-1), g0[:C].reshape(C * 3, N * k))
             err = (gx.reshape(C * 3, N) - ref).abs().max().item() / ref.abs().max().item()
             ok.append("edge" if err < 1e-5 else f"EDGE-ERR {err:.1e}")
-            edge = f"{tf:.0f} ({byt / tf / 1e6:.2f}) | {tb:.0f} ({byt / tb / 1e6:.2f})"
+            edge = f"{tf:.0f} ({byt / tf / 1e6:.2f}) | {tb:.0f} ({byt / tb / 1e6:.2f}{'' if fast else ', general path'})"
             del g, gx
         else:
             edge = "— | —"
