@@ -110,6 +110,59 @@ fcluster_maxclust_kernel(const double* __restrict__ Z_all, int N, const int* __r
     }
 }
 
+// ---- scoring a cut against the ground-truth parts: the 'iou' index of get_optimal_k (scores.py:152-171) -------------
+// One CTA per (k, cloud).  Confusion counts C[true part][cluster] by shared-memory atomics; IoU of every pair as
+// float32(C / (|part| + |cluster| - C)) like the reference's float32 score matrix filled from sklearn's float64
+// jaccard_score; every true part takes its FIRST best cluster (torch.max); parts are applied in order, so a later part
+// overwrites an earlier one that chose the same cluster; score = agreements / (2N - agreements), which is what the
+// one-hot logical_and / logical_or ratio of the reference evaluates to.  k > n_true + extra is not scored (-1).
+__global__ void __launch_bounds__(256)
+cut_iou_score_kernel(const int* __restrict__ labels_all, const int* __restrict__ ytrue_all, const int* __restrict__ n_true,
+                     const int* __restrict__ ks, int K, int N, int t_cap, int p_cap, int extra, double* __restrict__ scores) {
+    extern __shared__ int cm[];
+    int* C = cm;                          // [t_cap][p_cap]
+    int* ct = C + t_cap * p_cap;          // [t_cap] part sizes
+    int* cp = ct + t_cap;                 // [p_cap] cluster sizes
+    int* ind = cp + p_cap;                // [t_cap] chosen cluster of a part
+    int* owner = ind + t_cap;             // [p_cap] part that ends up owning a cluster, -1 = none
+    const int ki = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, nthr = blockDim.x;
+    const int T = n_true[b], k = ks[ki];
+    double* out = scores + (size_t)b * K + ki;
+    if (k > T + extra || T > t_cap) { if (tid == 0) *out = -1.0; return; }
+    const int* lab = labels_all + ((size_t)b * K + ki) * N;
+    const int* yt = ytrue_all + (size_t)b * N;
+    for (int i = tid; i < t_cap * p_cap + t_cap + p_cap; i += nthr) C[i] = 0;     // C, ct, cp are contiguous
+    __syncthreads();
+    for (int p = tid; p < N; p += nthr) {
+        const int t = yt[p], c = lab[p] - 1;
+        if ((unsigned)t < (unsigned)T && (unsigned)c < (unsigned)p_cap) {
+            atomicAdd(&C[t * p_cap + c], 1);
+            atomicAdd(&ct[t], 1);
+            atomicAdd(&cp[c], 1);
+        }
+    }
+    __syncthreads();
+    for (int t = tid; t < T; t += nthr) {
+        float best = -1.f;
+        int bj = 0;
+        for (int c = 0; c < p_cap; ++c) {
+            if (cp[c] == 0) continue;                                  // labels are 1..P: empty columns lie beyond P
+            const int inter = C[t * p_cap + c], uni = ct[t] + cp[c] - inter;
+            const float v = uni > 0 ? (float)((double)inter / (double)uni) : 0.f;
+            if (v > best) { best = v; bj = c; }                        // strict: the first maximum wins
+        }
+        ind[t] = bj;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int c = 0; c < p_cap; ++c) owner[c] = -1;
+        for (int t = 0; t < T; ++t) owner[ind[t]] = t;
+        long long agree = 0;
+        for (int c = 0; c < p_cap; ++c) if (owner[c] >= 0) agree += C[owner[c] * p_cap + c];
+        *out = (double)agree / (double)(2LL * N - agree);
+    }
+}
+
 }  // namespace hpcs
 
 extern "C" int hpcs_fcluster_maxclust_i32(const double* Z, int B, int N, const int* ks, int K, int k_max, int32_t* labels,
@@ -123,4 +176,16 @@ extern "C" int hpcs_fcluster_maxclust_i32(const double* Z, int B, int N, const i
     cudaFuncSetAttribute(fcluster_maxclust_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     fcluster_maxclust_kernel<<<B, 512, smem, as_stream(stream)>>>(Z, N, ks, K, labels);
     return check_launch("fcluster_maxclust_kernel");
+}
+
+extern "C" int hpcs_cut_iou_scores_f64(const int32_t* labels, const int32_t* ytrue, const int32_t* n_true, const int* ks, int B,
+                                       int K, int N, int t_cap, int k_max, int extra, double* scores, void* stream) {
+    using namespace hpcs;
+    if (!labels || !ytrue || !n_true || !ks || !scores) return fail(HPCS_ERR_ARG, "cut_iou_scores: null pointer");
+    if (B <= 0 || K <= 0 || N <= 0 || t_cap <= 0 || k_max <= 0 || B > 65535) return fail(HPCS_ERR_ARG, "cut_iou_scores: bad arguments");
+    const size_t smem = ((size_t)t_cap * k_max + 2 * (size_t)t_cap + 2 * (size_t)k_max) * sizeof(int);
+    if (smem > 200 * 1024) return fail(HPCS_ERR_ARG, "cut_iou_scores: %d parts x %d clusters do not fit shared memory", t_cap, k_max);
+    cudaFuncSetAttribute(cut_iou_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cut_iou_score_kernel<<<dim3(K, B), 256, smem, as_stream(stream)>>>(labels, ytrue, n_true, ks, K, N, t_cap, k_max, extra, scores);
+    return check_launch("cut_iou_score_kernel");
 }

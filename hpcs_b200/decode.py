@@ -86,3 +86,40 @@ def fcluster_maxclust(Z: torch.Tensor, ks) -> torch.Tensor:
         _lib.check(lib.hpcs_fcluster_maxclust_i32(Zc.data_ptr(), B, M + 1, ks_dev.data_ptr(), len(ks), max(ks),
                                                   labels.data_ptr(), _lib.stream_ptr(dev)), "hpcs_fcluster_maxclust_i32")
     return labels[0] if single else labels
+
+
+def get_optimal_k_batch(y: torch.Tensor, Z: torch.Tensor, index: str = "iou", extra: int = 4):
+    """``get_optimal_k(y[b], Z[b], 'iou')`` of the reference (hpcs/utils/scores.py:141-177; called per cloud on the host
+    at base_hyp_hc.py:198) for a whole batch on the GPU: cut every dendrogram at k = 1 .. n_true+extra, score each cut
+    against the ground-truth parts, keep the first best.  y[B,N] integer part labels (any ids), Z[B,N-1,4] fp64 on the
+    device -> (best_pred[B,N] int32, 0-based cluster ids like the reference's ``fcluster(...) - 1``; best_k[B] int64;
+    best_score[B] float64).  A cloud whose every score is 0 gets k = 0 and pred = -1 (the reference returns None)."""
+    if index != "iou":
+        raise NotImplementedError("only index='iou' (what base_hyp_hc.py:198 uses) runs on the GPU")
+    if y.dim() != 2 or Z.dim() != 3 or y.shape[0] != Z.shape[0] or y.shape[1] != Z.shape[1] + 1:
+        raise ValueError(f"expected y[B,N] and Z[B,N-1,4], got {tuple(y.shape)} and {tuple(Z.shape)}")
+    dev = _lib.require_cuda(Z, y)
+    lib = _lib.load()
+    B, N = y.shape
+    # remap_labels (scores.py:126-139): rank of a label among the labels present in its cloud
+    yl = y.long()
+    base = int(yl.min())
+    span = int(yl.max()) - base + 1
+    present = torch.zeros((B, span), dtype=torch.int32, device=dev).scatter_(1, yl - base, 1)
+    ytrue = (present.cumsum(1) - 1).gather(1, yl - base).to(torch.int32).contiguous()
+    n_true = present.sum(1).to(torch.int32).contiguous()
+    t_cap = int(n_true.max())
+    ks = list(range(1, t_cap + extra + 1))
+    labels = fcluster_maxclust(Z, ks)                                     # [B,K,N]
+    ks_dev = torch.tensor(ks, dtype=torch.int32, device=dev)
+    scores = torch.empty((B, len(ks)), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.hpcs_cut_iou_scores_f64(labels.data_ptr(), ytrue.data_ptr(), n_true.data_ptr(), ks_dev.data_ptr(), B,
+                                               len(ks), N, t_cap, max(ks), int(extra), scores.data_ptr(),
+                                               _lib.stream_ptr(dev)), "hpcs_cut_iou_scores_f64")
+    best_score, best = scores.max(dim=1)                                  # first maximum, like the reference's strict '>'
+    found = best_score > 0
+    best_k = torch.where(found, best + 1, torch.zeros_like(best))
+    pred = labels[torch.arange(B, device=dev), best] - 1
+    pred = torch.where(found.view(B, 1), pred, torch.full_like(pred, -1))
+    return pred, best_k, torch.where(found, best_score, torch.zeros_like(best_score))

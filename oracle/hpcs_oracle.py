@@ -452,3 +452,34 @@ def fcluster_maxclust_restated(Z: np.ndarray, k: int) -> np.ndarray:
         cnt = 1 if node < N else size[node - N]
         T[order[lo[node]:lo[node] + cnt]] = cid
     return T
+
+
+def get_optimal_k_restated(y: np.ndarray, Z: np.ndarray, extra: int = 4):
+    """get_optimal_k(y, Z, 'iou') of hpcs/utils/scores.py:141-177 restated on confusion counts (no sklearn): remap the
+    labels to 0..T-1 (:126-139); for k = 1 .. T+extra cut the dendrogram (fcluster maxclust, :151), IoU of every
+    (true part, cluster) pair stored in a float32 matrix (:153,158), each true part takes its first best cluster
+    (torch.max, :159), later parts overwrite earlier ones in the remap (:161-162), score = agreements / (2N - agreements)
+    (one-hot and / or, :164-166); first strictly best k wins.  Returns (pred 0-based or None, k, score)."""
+    y = np.asarray(y)
+    N = y.shape[0]
+    uniq = np.unique(y)
+    yt = np.searchsorted(uniq, y)
+    T = len(uniq)
+    best = (None, 0, 0.0)
+    for k in range(1, T + extra + 1):
+        yp = fcluster_maxclust_restated(Z, k) - 1
+        P = int(yp.max()) + 1
+        C = np.zeros((T, P), dtype=np.int64)
+        np.add.at(C, (yt, yp), 1)
+        ct, cp = C.sum(1), C.sum(0)
+        union = ct[:, None] + cp[None, :] - C
+        iou = np.where(union > 0, C / np.maximum(union, 1), 0.0).astype(np.float32)
+        ind = iou.argmax(1)                                   # first maximum, like torch.max on CPU
+        owner = np.full(P, -1)
+        for i in range(T):
+            owner[ind[i]] = i                                 # later parts overwrite
+        agree = int(sum(C[owner[j], j] for j in range(P) if owner[j] >= 0))
+        score = agree / (2 * N - agree)
+        if score > best[2]:
+            best = (yp.astype(np.int32), k, score)
+    return best

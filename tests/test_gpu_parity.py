@@ -3,6 +3,8 @@ interface) against the CPU oracle on the same seeded inputs, against the committ
 (outputs of the reference itself), and -- at BASELINE.json's full sizes -- through size-independent
 properties.  Bars: kNN indices, edge-feature gathers and dendrogram merge order bit-exact; distances,
 losses and gradients within 1e-4 relative of the fp64 oracle (tolerance written at each assert)."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -584,6 +586,33 @@ def test_fcluster_maxclust_matches_scipy(hb):
             got = hb.fcluster_maxclust(dev(torch.from_numpy(Zs)), ks2).cpu().numpy()
             for i, k in enumerate(ks2):
                 assert np.array_equal(got[i], fcluster(Zs, k, criterion="maxclust")), (n, method, k)
+
+
+def test_get_optimal_k_batch_vs_reference_golden_and_oracle(hb):
+    """get_optimal_k_batch (cut + IoU scoring on the GPU) against the reference's get_optimal_k(y, Z, 'iou') outputs
+    committed in tests/golden/optimal_k.npz, and against the oracle restatement on a batch decoded on the GPU."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "optimal_k.npz"))
+    for ci in range(int(g["n_cases"])):
+        y, Z = torch.from_numpy(g[f"y{ci}"]), torch.from_numpy(g[f"Z{ci}"])
+        pred, k, score = hb.get_optimal_k_batch(dev(y).unsqueeze(0), dev(Z).unsqueeze(0))
+        assert int(k[0]) == int(g[f"k{ci}"]), ci
+        assert np.array_equal(pred[0].cpu().numpy(), g[f"pred{ci}"]), ci
+        assert float(score[0]) == float(g[f"score{ci}"]), ci
+    gen = torch.Generator().manual_seed(23)
+    B, N = 6, 400
+    cen = torch.randn(6, 32, generator=gen)
+    parts = torch.randint(0, 6, (B, N), generator=gen)
+    parts[1] = parts[1] % 2                                                   # clouds with different numbers of parts
+    parts[4] = parts[4] % 4
+    x = O.expmap0(cen[parts] + 0.6 * torch.randn(B, N, 32, generator=gen))
+    for method in ("single", "complete"):
+        Z = hb.decode_linkage_batch(dev(x), dev(torch.tensor([1e-3])), method)
+        pred, k, score = hb.get_optimal_k_batch(dev(parts * 7 + 1), Z)
+        Zc = Z.cpu().numpy()
+        for b in range(B):
+            wp, wk, ws = O.get_optimal_k_restated((parts[b] * 7 + 1).numpy(), Zc[b])
+            assert int(k[b]) == wk and float(score[b]) == ws, (method, b)
+            assert np.array_equal(pred[b].cpu().numpy(), wp), (method, b)
 
 
 @pytest.mark.parametrize("key", ["96", "200", "clu"])

@@ -1,5 +1,7 @@
 """Pin the oracle (oracle/hpcs_oracle.py, oracle/knn_canonical.c) to outputs of the reference itself
 (tests/golden/*.npz, produced by oracle/make_golden.py from /root/reference).  CPU only."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -169,3 +171,14 @@ def test_fcluster_maxclust_restatement_matches_scipy():
                 want = fcluster(Z, k, criterion="maxclust")
                 got = O.fcluster_maxclust_restated(Z, k)
                 assert np.array_equal(got, want), (n, dup, method, k)
+
+
+def test_get_optimal_k_restatement_matches_reference_golden():
+    """oracle.get_optimal_k_restated == the reference's get_optimal_k(y, Z, 'iou') run in the build container
+    (tests/golden/optimal_k.npz, oracle/make_golden_cut.py): best partition, best k, score."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "optimal_k.npz"))
+    for ci in range(int(g["n_cases"])):
+        pred, k, score = O.get_optimal_k_restated(g[f"y{ci}"], g[f"Z{ci}"])
+        assert k == int(g[f"k{ci}"]), ci
+        assert np.array_equal(pred, g[f"pred{ci}"]), ci
+        assert score == float(g[f"score{ci}"]), ci
