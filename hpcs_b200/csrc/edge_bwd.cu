@@ -89,7 +89,7 @@ __host__ __device__ inline Rev2 rev2_view(void* ws, const Rev2Dims& d, int b) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kRevThreads)
 edge_rev2_build_kernel(const int64_t* __restrict__ idx, int N, int k, unsigned k_magic, void* __restrict__ ws) {
-    extern __shared__ __align__(16) unsigned char sm_raw[];
+    extern __shared__ __align__(128) unsigned char sm_raw[];
     const Rev2Dims d = rev2_dims(N, k);
     const int s = blockIdx.x, b = blockIdx.y;
     const int E = N * k;
@@ -342,8 +342,10 @@ __device__ __forceinline__ float row_sum(const float* __restrict__ row, int k) {
 // taking the centre plane's row sums straight from HBM into registers before the gather (coalesced LDG.128, partial
 // sums redistributed by shuffles in the combine).  The L1 fills of those loads go through the same l1tex data pipe as
 // the gather's shared-memory reads and slow it by more than the removed centre phase saved; TMA writes do not.)
-constexpr int NBUF = 2;
-
+// NBUF = 2: the two planes of an item (and the next item's) alternate between two buffers, so a load is always in flight
+// while a plane is consumed.  NBUF = 1: one buffer, for shapes whose planes are too large for two (N*k up to 2^16 - 1:
+// k = 40, or N = 2048): loads and compute of a CTA alternate, the other SMs fill the gaps on the HBM side.
+template <int NBUF>
 __global__ void __launch_bounds__(kGatherThreads, 1)
 edge_bwd_gather_kernel(const float* __restrict__ gout, const int64_t* __restrict__ idx, const void* __restrict__ ws,
                        int B, int C, int N, int k, int per_cta, size_t smem_budget, long long* __restrict__ prof,
@@ -562,13 +564,21 @@ edge_bwd_gather_kernel(const float* __restrict__ gout, const int64_t* __restrict
 // ------------------------------------------------------------------------------------------------
 constexpr size_t kSmemBudget = 226 * 1024;
 
+// plane buffers the persistent gather can afford for this shape: 2, 1, or 0 (= not on this path)
+static int gather_buffers(int N, int k) {
+    const Rev2Dims d = rev2_dims(N, k);
+    for (int nbuf = 2; nbuf >= 1; --nbuf) {
+        const GatherSmem g = gather_smem(N, k, d, kSmemBudget, nbuf);
+        if (g.cache_entries >= 1024 && g.total <= kSmemBudget) return nbuf;
+    }
+    return 0;
+}
+
 bool edge_bwd_fast_applicable(const float* gout, int N, int k) {
     const size_t E = (size_t)N * k;
     if (N > 2048 || E > 65535 || (E & 3) != 0) return false;
     if ((reinterpret_cast<uintptr_t>(gout) & 15) != 0) return false;
-    const Rev2Dims d = rev2_dims(N, k);
-    const GatherSmem g = gather_smem(N, k, d, kSmemBudget, NBUF);
-    return g.cache_entries >= 1024 && g.total <= kSmemBudget;
+    return gather_buffers(N, k) != 0;
 }
 
 size_t edge_bwd_fast_workspace_bytes(int B, int N, int k) {
@@ -588,7 +598,8 @@ int edge_bwd_fast_build(const int64_t* idx, int B, int N, int k, void* ws, cudaS
 
 int edge_bwd_fast_gather(const float* gout, const int64_t* idx, int B, int C, int N, int k, float* gx, const void* ws, cudaStream_t st) {
     const Rev2Dims d = rev2_dims(N, k);
-    const GatherSmem g = gather_smem(N, k, d, kSmemBudget, NBUF);
+    const int nbuf = gather_buffers(N, k);
+    const GatherSmem g = gather_smem(N, k, d, kSmemBudget, nbuf);
     const int items = B * 3 * C;
     int grid = sm_count();
     if (grid > items) grid = items;
@@ -598,8 +609,11 @@ int edge_bwd_fast_gather(const float* gout, const int64_t* idx, int B, int C, in
 #ifdef HPCS_BWD_PROFILE
     if (const char* env = getenv("HPCS_BWD_PROF_PTR")) prof = reinterpret_cast<long long*>(strtoull(env, nullptr, 0));
 #endif
-    cudaFuncSetAttribute(edge_bwd_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.total);
-    edge_bwd_gather_kernel<<<grid, kGatherThreads, g.total, st>>>(gout, idx, ws, B, C, N, k, per_cta, kSmemBudget, prof, gx);
+    auto launch = [&](auto kern) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.total);
+        kern<<<grid, kGatherThreads, g.total, st>>>(gout, idx, ws, B, C, N, k, per_cta, kSmemBudget, prof, gx);
+    };
+    if (nbuf == 2) launch(edge_bwd_gather_kernel<2>); else launch(edge_bwd_gather_kernel<1>);
     return check_launch("edge_bwd_gather_kernel");
 }
 

@@ -70,7 +70,7 @@ int hpcs_edge_feat_fwd_f32(const float* x, const int64_t* idx, int B, int C, int
  * into a gather through a reverse (target -> sources) CSR built in the workspace. */
 size_t hpcs_edge_feat_bwd_workspace_bytes(int B, int N, int k);
 /* 1 when hpcs_edge_feat_bwd_f32 will take the persistent TMA gather for this shape (no cross term, N <= 2048,
- * N*k <= 65535, N*k % 4 == 0, 16-byte aligned gout, two N*k planes fit shared memory); that path sums in a fixed
+ * N*k <= 65535, N*k % 4 == 0, 16-byte aligned gout, at least one N*k plane fits shared memory: N*k <= ~45000); that path sums in a fixed
  * order (bitwise repeatable).  The general path is repeatable up to the placement of equal-degree targets. */
 int hpcs_edge_feat_bwd_is_fast(const float* gout, int N, int k, int cross);
 int hpcs_edge_feat_bwd_f32(const float* gout, const float* x, const int64_t* idx, int B, int C, int N,
