@@ -765,7 +765,7 @@ static TcLayout tc_layout(void* ws, int B, int D, int N, int KL) {
     return L;
 }
 
-bool knn_tc_applicable(int D, int N, int k) { return D >= 16 && D <= kKP - 1 && N >= 128 && N <= 4096 && k <= 48; }
+bool knn_tc_applicable(int D, int N, int k) { return D >= 16 && D <= kKP - 1 && N >= 128 && N <= 16384 && k <= 48; }
 
 static int tc_list_len(int k) { return k <= 24 ? 32 : 64; }
 
@@ -824,6 +824,7 @@ static int run_tc(const float* x, int B, int D, int N, int k, int64_t* idx, floa
     const int gate = (int)(rows / 16);
     {
         const size_t smem = (64 + (size_t)N) * sizeof(float);
+        cudaFuncSetAttribute(knn_fallback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         knn_fallback_kernel<<<4 * sm_count(), kFbThreads, smem, st>>>(x, L.sq, D, N, k, L.fb_list, L.fb_count, gate, idx, val);
         rc = check_launch("knn_fallback_kernel");
         if (rc) return rc;

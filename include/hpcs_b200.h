@@ -49,7 +49,7 @@ size_t hpcs_knn_workspace_bytes(int B, int D, int N, int k);
 int hpcs_knn_f32(const float* x, int B, int D, int N, int k, int64_t* idx, float* val,
                  void* ws, size_t ws_bytes, void* stream);
 /* Same contract, always the all-FFMA exact kernel.  hpcs_knn_f32 picks, for 16 <= D <= 63 and
- * 128 <= N <= 4096, the tensor-core path (tcgen05 TF32 Gram tiles -> candidate lists -> exact fp32
+ * 128 <= N <= 16384, the tensor-core path (tcgen05 TF32 Gram tiles -> candidate lists -> exact fp32
  * re-rank with a proven-safe test and an exact redo of the rows that fail it); both return the
  * same bits, which the parity tests check against each other and against the oracle. */
 int hpcs_knn_ffma_f32(const float* x, int B, int D, int N, int k, int64_t* idx, float* val,

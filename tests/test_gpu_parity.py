@@ -61,9 +61,10 @@ def test_knn_bit_exact_vs_canonical_oracle(hb, B, D, N, k):
 
 @pytest.mark.parametrize("B,D,N,k,kind", [(2, 63, 128, 20, "randn"), (2, 63, 1024, 20, "randn"), (3, 32, 300, 10, "randn"),
                                           (1, 16, 128, 40, "randn"), (2, 63, 1024, 20, "clustered"), (2, 63, 512, 20, "dups"),
-                                          (2, 48, 640, 48, "randn"), (1, 63, 4096, 20, "randn"), (2, 63, 1000, 24, "offset")])
+                                          (2, 48, 640, 48, "randn"), (1, 63, 4096, 20, "randn"), (2, 63, 1000, 24, "offset"),
+                                          (1, 63, 8192, 20, "randn"), (1, 40, 16384, 10, "randn"), (1, 63, 8192, 20, "clustered")])
 def test_knn_tensor_core_path_bit_exact(hb, B, D, N, k, kind):
-    """hpcs_knn_f32 takes the tcgen05 path for 16 <= D <= 63, 128 <= N <= 4096, k <= 48: its indices AND value
+    """hpcs_knn_f32 takes the tcgen05 path for 16 <= D <= 63, 128 <= N <= 16384, k <= 48: its indices AND value
     bits must equal the canonical oracle and the all-FFMA kernel, including inputs built to defeat the
     TF32 candidate stage (near-duplicate clusters, exact duplicates, a large common offset)."""
     gen = torch.Generator().manual_seed(B * 977 + D * 13 + N + k)
@@ -83,7 +84,7 @@ def test_knn_tensor_core_path_bit_exact(hb, B, D, N, k, kind):
         assert torch.equal(got_i.cpu(), want_i) and torch.equal(got_v.cpu(), want_v)
     assert 0 <= stats["fallback_rows"] <= B * N
     if kind == "randn":
-        assert stats["fallback_rows"] <= B * N // 100          # the candidate stage decides almost every row itself
+        assert stats["fallback_rows"] <= B * N // 50           # the candidate stage decides almost every row itself (index bits cost key precision at large N)
 
 
 @pytest.mark.parametrize("B,N,k,kind", [(3, 1024, 20, "cloud"), (2, 1000, 32, "cloud"), (2, 33, 20, "cloud"), (2, 20, 20, "cloud"),
@@ -297,11 +298,13 @@ def test_edge_features_full_size_linearity(hb):
     assert torch.equal(y2, 2.0 * y1)                                            # scaling by 2 is exact in fp32
     xg = x.clone().requires_grad_(True)
     y = hb.get_graph_feature(xg, 20, idx=idx)
-    g = torch.randn_like(y)
+    g = torch.randn(y.shape, device=y.device, generator=torch.Generator(device=y.device).manual_seed(12))
     (gx,) = torch.autograd.grad(y, xg, g)
     lhs = (y.double() * g.double()).sum()
     rhs = (x.double() * gx.double()).sum()
-    assert abs(lhs - rhs) <= 1e-5 * abs(lhs)
+    # <y, g> is a sum of 86 M zero-mean terms and can itself be small, so the bar is relative to |y| |g| (1.2e8 here):
+    # fp32 rounding of the 2 M gradient sums gives ~1e-2 absolute, one dropped or doubled edge gives ~1
+    assert abs(lhs - rhs) <= 2e-9 * y.double().norm() * g.double().norm()
 
 
 # ------------------------------------------------------------------------------------------------

@@ -64,7 +64,7 @@ def main():
         i3, i63 = hb.knn(x3, k), hb.knn(x63, k)
         ok.append("knn3" if torch.equal(i3, hb.knn(x3, k, method="ffma")) else "KNN3-MISMATCH")
         ok.append("knn63" if torch.equal(i63, hb.knn(x63, k, method="ffma")) else "KNN63-MISMATCH")
-        path = "tcgen05" if N <= 4096 and k <= 48 else "ffma"
+        path = "tcgen05" if N <= 16384 and k <= 48 else "ffma"
         # edge features (C = 21): skip shapes whose output would not fit comfortably
         C = 21
         out_bytes = B * 2 * C * 3 * N * k * 4
