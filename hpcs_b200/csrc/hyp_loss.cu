@@ -127,16 +127,23 @@ hyp_triplet_kernel(const float* __restrict__ u, float* __restrict__ G, HypHeader
     float loss_acc = 0.f, gs_acc = 0.f;
     unsigned kept_acc = 0;
 
+    // the triplet indices of the NEXT batch are requested before the current one is processed: their (HBM) latency
+    // used to sit at the top of every iteration
+    auto load_idx = [&](int64_t t, unsigned& xa, unsigned& xp, unsigned& xn) {
+        xa = xp = xn = 0;
+        if (t < T0) {       // indices are clamped so a bad triplet cannot fault; the reference would raise instead
+            xa = (unsigned)min((unsigned long long)(long long)__ldg(a + t), (unsigned long long)(n - 1));
+            xp = (unsigned)min((unsigned long long)(long long)__ldg(p + t), (unsigned long long)(n - 1));
+            xn = (unsigned)min((unsigned long long)(long long)__ldg(ng + t), (unsigned long long)(n - 1));
+        }
+    };
+    unsigned na_ = 0, np_ = 0, nn_ = 0;
+    load_idx(warp_global * 32 + lane, na_, np_, nn_);
     for (int64_t base = warp_global * 32; base < T0; base += warps_total * 32) {
         const int64_t t = base + lane;
         const bool valid = t < T0;
-        // indices are clamped so a bad triplet cannot fault; the reference would raise instead
-        unsigned ia = 0, ip = 0, in_ = 0;
-        if (valid) {
-            ia = (unsigned)min((unsigned long long)(long long)__ldg(a + t), (unsigned long long)(n - 1));
-            ip = (unsigned)min((unsigned long long)(long long)__ldg(p + t), (unsigned long long)(n - 1));
-            in_ = (unsigned)min((unsigned long long)(long long)__ldg(ng + t), (unsigned long long)(n - 1));
-        }
+        const unsigned ia = na_, ip = np_, in_ = nn_;
+        load_idx(t + warps_total * 32, na_, np_, nn_);
         float c_ap = 0.f, c_an = 0.f, c_pn = 0.f;
         // the sampler emits all triplets of an anchor back to back (t_per_anchor of them), so consecutive slots
         // usually share the anchor row: it is loaded once per run, and (below) its gradient is summed in registers
