@@ -53,7 +53,7 @@ SIGNATURES = {
     "hpcs_linkage_workspace_bytes": (_Z, [_I, _I, _I, _I]),
     "hpcs_linkage_f64": (_I, [_P, _I, _I, _I, _I, _P, _P, _Z, _P]),
     "hpcs_fcluster_maxclust_i32": (_I, [_P, _I, _I, _P, _I, _I, _P, _P]),
-    "hpcs_cut_iou_scores_f64": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "hpcs_cut_scores_f64": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
 }
 
 

@@ -116,9 +116,13 @@ fcluster_maxclust_kernel(const double* __restrict__ Z_all, int N, const int* __r
 // jaccard_score; every true part takes its FIRST best cluster (torch.max); parts are applied in order, so a later part
 // overwrites an earlier one that chose the same cluster; score = agreements / (2N - agreements), which is what the
 // one-hot logical_and / logical_or ratio of the reference evaluates to.  k > n_true + extra is not scored (-1).
+// mode 1 ('ri', scores.py:154-159): sklearn's adjusted_rand_score from the same counts -- pair confusion matrix in
+// 64-bit integers (sum of squares, row / column weighted sums), one double division at the end, 1.0 when both
+// disagreement counts are zero.
 __global__ void __launch_bounds__(256)
 cut_iou_score_kernel(const int* __restrict__ labels_all, const int* __restrict__ ytrue_all, const int* __restrict__ n_true,
-                     const int* __restrict__ ks, int K, int N, int t_cap, int p_cap, int extra, double* __restrict__ scores) {
+                     const int* __restrict__ ks, int K, int N, int t_cap, int p_cap, int extra, int mode,
+                     double* __restrict__ scores) {
     extern __shared__ int cm[];
     int* C = cm;                          // [t_cap][p_cap]
     int* ct = C + t_cap * p_cap;          // [t_cap] part sizes
@@ -142,6 +146,21 @@ cut_iou_score_kernel(const int* __restrict__ labels_all, const int* __restrict__
         }
     }
     __syncthreads();
+    if (mode == 1) {
+        if (tid == 0) {
+            long long sumsq = 0, wc = 0, wk = 0;
+            for (int t = 0; t < T; ++t)
+                for (int c = 0; c < p_cap; ++c) {
+                    const long long v = C[t * p_cap + c];
+                    sumsq += v * v;
+                    wc += v * cp[c];
+                    wk += v * ct[t];
+                }
+            const long long n = N, tp = sumsq - n, fp = wc - sumsq, fn = wk - sumsq, tn = n * n - fp - fn - sumsq;
+            *out = (fn == 0 && fp == 0) ? 1.0 : (2.0 * (double)(tp * tn - fn * fp)) / (double)((tp + fn) * (fn + tn) + (tp + fp) * (fp + tn));
+        }
+        return;
+    }
     for (int t = tid; t < T; t += nthr) {
         float best = -1.f;
         int bj = 0;
@@ -178,14 +197,15 @@ extern "C" int hpcs_fcluster_maxclust_i32(const double* Z, int B, int N, const i
     return check_launch("fcluster_maxclust_kernel");
 }
 
-extern "C" int hpcs_cut_iou_scores_f64(const int32_t* labels, const int32_t* ytrue, const int32_t* n_true, const int* ks, int B,
-                                       int K, int N, int t_cap, int k_max, int extra, double* scores, void* stream) {
+extern "C" int hpcs_cut_scores_f64(const int32_t* labels, const int32_t* ytrue, const int32_t* n_true, const int* ks, int B,
+                                   int K, int N, int t_cap, int k_max, int extra, int index, double* scores, void* stream) {
     using namespace hpcs;
-    if (!labels || !ytrue || !n_true || !ks || !scores) return fail(HPCS_ERR_ARG, "cut_iou_scores: null pointer");
-    if (B <= 0 || K <= 0 || N <= 0 || t_cap <= 0 || k_max <= 0 || B > 65535) return fail(HPCS_ERR_ARG, "cut_iou_scores: bad arguments");
+    if (!labels || !ytrue || !n_true || !ks || !scores) return fail(HPCS_ERR_ARG, "cut_scores: null pointer");
+    if (B <= 0 || K <= 0 || N <= 0 || t_cap <= 0 || k_max <= 0 || B > 65535 || (index != 0 && index != 1)) return fail(HPCS_ERR_ARG, "cut_scores: bad arguments");
+    if (index == 1 && N > 40000) return fail(HPCS_ERR_ARG, "cut_scores: N=%d overflows the 64-bit pair counts of the Rand index", N);
     const size_t smem = ((size_t)t_cap * k_max + 2 * (size_t)t_cap + 2 * (size_t)k_max) * sizeof(int);
-    if (smem > 200 * 1024) return fail(HPCS_ERR_ARG, "cut_iou_scores: %d parts x %d clusters do not fit shared memory", t_cap, k_max);
+    if (smem > 200 * 1024) return fail(HPCS_ERR_ARG, "cut_scores: %d parts x %d clusters do not fit shared memory", t_cap, k_max);
     cudaFuncSetAttribute(cut_iou_score_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cut_iou_score_kernel<<<dim3(K, B), 256, smem, as_stream(stream)>>>(labels, ytrue, n_true, ks, K, N, t_cap, k_max, extra, scores);
+    cut_iou_score_kernel<<<dim3(K, B), 256, smem, as_stream(stream)>>>(labels, ytrue, n_true, ks, K, N, t_cap, k_max, extra, index, scores);
     return check_launch("cut_iou_score_kernel");
 }

@@ -89,13 +89,13 @@ def fcluster_maxclust(Z: torch.Tensor, ks) -> torch.Tensor:
 
 
 def get_optimal_k_batch(y: torch.Tensor, Z: torch.Tensor, index: str = "iou", extra: int = 4):
-    """``get_optimal_k(y[b], Z[b], 'iou')`` of the reference (hpcs/utils/scores.py:141-177; called per cloud on the host
+    """``get_optimal_k(y[b], Z[b], index)`` of the reference (hpcs/utils/scores.py:141-177; called per cloud on the host
     at base_hyp_hc.py:198) for a whole batch on the GPU: cut every dendrogram at k = 1 .. n_true+extra, score each cut
     against the ground-truth parts, keep the first best.  y[B,N] integer part labels (any ids), Z[B,N-1,4] fp64 on the
     device -> (best_pred[B,N] int32, 0-based cluster ids like the reference's ``fcluster(...) - 1``; best_k[B] int64;
     best_score[B] float64).  A cloud whose every score is 0 gets k = 0 and pred = -1 (the reference returns None)."""
-    if index != "iou":
-        raise NotImplementedError("only index='iou' (what base_hyp_hc.py:198 uses) runs on the GPU")
+    if index not in ("iou", "ri"):
+        raise ValueError("index must be 'iou' (base_hyp_hc.py:198) or 'ri' (adjusted Rand index, viz.py:489)")
     if y.dim() != 2 or Z.dim() != 3 or y.shape[0] != Z.shape[0] or y.shape[1] != Z.shape[1] + 1:
         raise ValueError(f"expected y[B,N] and Z[B,N-1,4], got {tuple(y.shape)} and {tuple(Z.shape)}")
     dev = _lib.require_cuda(Z, y)
@@ -114,9 +114,9 @@ def get_optimal_k_batch(y: torch.Tensor, Z: torch.Tensor, index: str = "iou", ex
     ks_dev = torch.tensor(ks, dtype=torch.int32, device=dev)
     scores = torch.empty((B, len(ks)), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
-        _lib.check(lib.hpcs_cut_iou_scores_f64(labels.data_ptr(), ytrue.data_ptr(), n_true.data_ptr(), ks_dev.data_ptr(), B,
-                                               len(ks), N, t_cap, max(ks), int(extra), scores.data_ptr(),
-                                               _lib.stream_ptr(dev)), "hpcs_cut_iou_scores_f64")
+        _lib.check(lib.hpcs_cut_scores_f64(labels.data_ptr(), ytrue.data_ptr(), n_true.data_ptr(), ks_dev.data_ptr(), B,
+                                           len(ks), N, t_cap, max(ks), int(extra), 0 if index == "iou" else 1,
+                                           scores.data_ptr(), _lib.stream_ptr(dev)), "hpcs_cut_scores_f64")
     best_score, best = scores.max(dim=1)                                  # first maximum, like the reference's strict '>'
     found = best_score > 0
     best_k = torch.where(found, best + 1, torch.zeros_like(best))

@@ -158,13 +158,14 @@ int hpcs_linkage_f64(const float* leaves, int B, int N, int D, int method, doubl
 int hpcs_fcluster_maxclust_i32(const double* Z, int B, int N, const int* ks, int K, int k_max, int32_t* labels,
                                void* stream);
 
-/* the 'iou' index of get_optimal_k   hpcs/utils/scores.py:152-171   (second half)
+/* the model-selection indices of get_optimal_k   hpcs/utils/scores.py:152-171   (second half)
  *   labels[B,K,N] from hpcs_fcluster_maxclust_i32 (1-based), ytrue[B,N] ground-truth parts remapped to 0..n_true[b]-1
- *   (scores.py:126-139), ks[K] device ints -> scores[B,K] fp64: float32 IoU matrix, first best cluster per part, later
- *   parts overwrite, agreements / (2N - agreements); -1 where k > n_true[b] + extra (the reference stops there).
+ *   (scores.py:126-139), ks[K] device ints -> scores[B,K] fp64; -1 where k > n_true[b] + extra (the reference stops there).
+ *   index 0 = 'iou' (base_hyp_hc.py:198): float32 IoU matrix, first best cluster per part, later parts overwrite,
+ *   agreements / (2N - agreements);  index 1 = 'ri': sklearn's adjusted_rand_score (pair counts in 64-bit integers).
  *   t_cap >= max n_true, k_max >= max ks (host copies, they size shared memory). */
-int hpcs_cut_iou_scores_f64(const int32_t* labels, const int32_t* ytrue, const int32_t* n_true, const int* ks, int B,
-                            int K, int N, int t_cap, int k_max, int extra, double* scores, void* stream);
+int hpcs_cut_scores_f64(const int32_t* labels, const int32_t* ytrue, const int32_t* n_true, const int* ks, int B, int K,
+                        int N, int t_cap, int k_max, int extra, int index, double* scores, void* stream);
 
 #ifdef __cplusplus
 }

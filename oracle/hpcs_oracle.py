@@ -454,7 +454,23 @@ def fcluster_maxclust_restated(Z: np.ndarray, k: int) -> np.ndarray:
     return T
 
 
-def get_optimal_k_restated(y: np.ndarray, Z: np.ndarray, extra: int = 4):
+def adjusted_rand_from_contingency(C: np.ndarray) -> float:
+    """sklearn.metrics.adjusted_rand_score (the reference's ``ri``) from the contingency table, in Python integers like
+    sklearn's pair_confusion_matrix + adjusted_rand_score."""
+    C = C.astype(object)
+    n = int(C.sum())
+    nk, nc = C.sum(1), C.sum(0)
+    sumsq = int((C * C).sum())
+    tp = sumsq - n
+    fp = int((C * nc[None, :]).sum()) - sumsq
+    fn = int((C * nk[:, None]).sum()) - sumsq
+    tn = n * n - fp - fn - sumsq
+    if fn == 0 and fp == 0:
+        return 1.0
+    return 2.0 * (tp * tn - fn * fp) / ((tp + fn) * (fn + tn) + (tp + fp) * (fp + tn))
+
+
+def get_optimal_k_restated(y: np.ndarray, Z: np.ndarray, extra: int = 4, index: str = "iou"):
     """get_optimal_k(y, Z, 'iou') of hpcs/utils/scores.py:141-177 restated on confusion counts (no sklearn): remap the
     labels to 0..T-1 (:126-139); for k = 1 .. T+extra cut the dendrogram (fcluster maxclust, :151), IoU of every
     (true part, cluster) pair stored in a float32 matrix (:153,158), each true part takes its first best cluster
@@ -473,6 +489,11 @@ def get_optimal_k_restated(y: np.ndarray, Z: np.ndarray, extra: int = 4):
         np.add.at(C, (yt, yp), 1)
         ct, cp = C.sum(1), C.sum(0)
         union = ct[:, None] + cp[None, :] - C
+        if index == "ri":                                         # scores.py:154-159: adjusted Rand index of the cut
+            score = adjusted_rand_from_contingency(C)
+            if score > best[2]:
+                best = (yp.astype(np.int32), k, score)
+            continue
         iou = np.where(union > 0, C / np.maximum(union, 1), 0.0).astype(np.float32)
         ind = iou.argmax(1)                                   # first maximum, like torch.max on CPU
         owner = np.full(P, -1)

@@ -38,7 +38,10 @@ def main():
         pred, k, score = get_optimal_k(y, Z, "iou")
         rec[f"y{ci}"], rec[f"Z{ci}"] = y.numpy(), Z
         rec[f"pred{ci}"], rec[f"k{ci}"], rec[f"score{ci}"] = np.asarray(pred), np.int64(k), np.float64(score)
-        print(ci, n, parts, method, "best k", k, "score", float(score))
+        rpred, rk, rscore = get_optimal_k(y, Z, "ri")       # adjusted Rand index variant (viz.py:489)
+        rec[f"ri_pred{ci}"] = np.asarray(rpred) if rpred is not None else np.full(n, -1, dtype=np.int32)
+        rec[f"ri_k{ci}"], rec[f"ri_score{ci}"] = np.int64(rk), np.float64(rscore)
+        print(ci, n, parts, method, "iou: best k", k, "score", float(score), "| ri: best k", rk, "score", float(rscore))
     np.savez_compressed(os.path.join(OUT, "optimal_k.npz"), n_cases=np.int64(len(cases)), **rec)
 
 

@@ -603,6 +603,10 @@ def test_get_optimal_k_batch_vs_reference_golden_and_oracle(hb):
         assert int(k[0]) == int(g[f"k{ci}"]), ci
         assert np.array_equal(pred[0].cpu().numpy(), g[f"pred{ci}"]), ci
         assert float(score[0]) == float(g[f"score{ci}"]), ci
+        pred, k, score = hb.get_optimal_k_batch(dev(y).unsqueeze(0), dev(Z).unsqueeze(0), index="ri")
+        assert int(k[0]) == int(g[f"ri_k{ci}"]) and float(score[0]) == float(g[f"ri_score{ci}"]), ci
+        if int(k[0]) > 0:
+            assert np.array_equal(pred[0].cpu().numpy(), g[f"ri_pred{ci}"]), ci
     gen = torch.Generator().manual_seed(23)
     B, N = 6, 400
     cen = torch.randn(6, 32, generator=gen)

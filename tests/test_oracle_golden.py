@@ -182,3 +182,7 @@ def test_get_optimal_k_restatement_matches_reference_golden():
         assert k == int(g[f"k{ci}"]), ci
         assert np.array_equal(pred, g[f"pred{ci}"]), ci
         assert score == float(g[f"score{ci}"]), ci
+        pred, k, score = O.get_optimal_k_restated(g[f"y{ci}"], g[f"Z{ci}"], index="ri")
+        assert k == int(g[f"ri_k{ci}"]) and score == float(g[f"ri_score{ci}"]), ci
+        if k > 0:
+            assert np.array_equal(pred, g[f"ri_pred{ci}"]), ci
