@@ -449,10 +449,11 @@ int hpcs_edge_feat_fwd_f32(const float* x, const int64_t* idx, int B, int C, int
     const size_t E = (size_t)N * k;
     const bool vec = (E % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) &&
                      ((reinterpret_cast<uintptr_t>(idx) & 15) == 0);
-    // enough CTAs for ~8 per SM, but at least 2048 vector groups each
+    // enough CTAs for ~8 per SM, but at least 512 vector groups each (a CTA restages its 3N coordinates; with C = 1
+    // and 2048 groups per CTA only 96 CTAs existed for 148 SMs)
     const size_t groups = vec ? E / 4 : E;
     int splits = (8 * sm_count() + B * C - 1) / (B * C);
-    const int max_splits = (int)((groups + 2047) / 2048);
+    const int max_splits = (int)((groups + 511) / 512);
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;
     dim3 grid(splits, C, B), block(256);
