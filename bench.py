@@ -533,24 +533,43 @@ def run_decode(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_per_step = ms.item() / args.steps
 
-    # end to end: embeddings from pinned host memory, Z back to pinned host memory (what fcluster consumes)
+    # end to end: embeddings from pinned host memory, Z back to pinned host memory (what fcluster consumes); two buffer
+    # sets on three streams, so the upload of step i+1 and the download of step i-1 overlap the decode of step i
     sampler.region = "e2e"
     x_pin = host.pin_memory()
-    z_pin = torch.empty(Z.shape, dtype=Z.dtype).pin_memory()
-    xd = torch.empty_like(x)
+    z_pin = [torch.empty(Z.shape, dtype=Z.dtype).pin_memory() for _ in range(2)]
+    xd = [torch.empty_like(x) for _ in range(2)]
+    zd = [None, None]
+    s_up, s_run, s_down = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    ev_up = [torch.cuda.Event() for _ in range(2)]
+    ev_run = [torch.cuda.Event() for _ in range(2)]
+    ev_down = [torch.cuda.Event() for _ in range(2)]
 
-    def e2e_step():
-        xd.copy_(x_pin, non_blocking=True)
-        z = hb.decode_linkage_batch(xd, scale, method)
-        z_pin.copy_(z, non_blocking=True)
+    def e2e_loop(n_steps):
+        for i in range(n_steps):
+            j = i % 2
+            with torch.cuda.stream(s_up):
+                s_up.wait_event(ev_run[j])                      # the previous decode of this set has read its input
+                xd[j].copy_(x_pin, non_blocking=True)
+                ev_up[j].record(s_up)
+            with torch.cuda.stream(s_run):
+                s_run.wait_event(ev_up[j])
+                s_run.wait_event(ev_down[j])                    # its previous result has left the device
+                zd[j] = hb.decode_linkage_batch(xd[j], scale, method)
+                ev_run[j].record(s_run)
+            with torch.cuda.stream(s_down):
+                s_down.wait_event(ev_run[j])
+                z_pin[j].copy_(zd[j], non_blocking=True)
+                zd[j].record_stream(s_down)
+                ev_down[j].record(s_down)
 
-    for _ in range(2):
-        e2e_step()
+    e2e_loop(4)
     barrier()
     te0, te1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     te0.record()
-    for _ in range(args.steps):
-        e2e_step()
+    e2e_loop(args.steps)
+    for s_ in (s_up, s_run, s_down):
+        torch.cuda.current_stream().wait_stream(s_)
     te1.record()
     barrier()
     clocks = sampler.stop()
@@ -562,7 +581,7 @@ def run_decode(args):
     pk = peaks()
     alg_bytes = 2.0 * B * N * (N - 1) / 2 * 8                          # fp64 condensed matrix written once, read once
     achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
-    zc = z_pin.numpy()
+    zc = z_pin[(args.steps - 1) % 2].numpy()
     line = {
         "metric": f"dendrograms/sec ({method}-linkage decode, {N} pts, 32-d)", "value": round(world * B / (ms_per_step * 1e-3), 1),
         "unit": "dendrograms/s", "n_gpus": world, "steps": args.steps, "warmup": warm, "ms_per_step": round(ms_per_step, 4),
@@ -572,7 +591,7 @@ def run_decode(args):
                    "l2": f"fp64 distance matrices {B * N * N * 8 / 1e6:.0f} MB per step vs 126 MB L2; no explicit flush",
                    "launch": "eager (one C-ABI call per step)"},
         "e2e": {"value": round(world * B / (ms_e.item() / args.steps * 1e-3), 1), "unit": "dendrograms/s",
-                "h2d_bytes_per_step": int(x_pin.numel() * 4), "d2h_bytes_per_step": int(z_pin.numel() * 8)},
+                "h2d_bytes_per_step": int(x_pin.numel() * 4), "d2h_bytes_per_step": int(z_pin[0].numel() * 8)},
         "gpu_launches": int(launches_per_step * args.steps), "clocks": clocks,
         "roofline": {"kernel": "pdist_cosine + linkage", "bound": "hbm", "achieved": round(achieved, 1), "peak": pk["hbm_gbs"],
                      "unit": "GB/s", "frac": round(achieved / pk["hbm_gbs"], 4), "traffic": None,
