@@ -318,6 +318,8 @@ def run_native(args):
     #            order, 131 KB, + 1 KB of per-label segments, both derived from the labels on the host) go up;
     #            the 1.64 M triplets are drawn on the GPU inside the step (hpcs_triplet_sample_i32);
     #   "host":  as the reference does it -- triplets sampled on the host beforehand and uploaded (int32) every step.
+    #   "points_only": like "device", but the layer inputs and embeddings (activations of device-resident layers in the real
+    #            model, synthetic stand-ins here) are not re-uploaded: the host->device traffic of an actual training step.
     pin = {k: host[k].pin_memory() for k in ("pts", "f1", "f2", "emb")}
     trip_pin = tuple(t.to(torch.int32).pin_memory() for t in trip_host)       # int32 indices: half the upload
     order_host, seg_host, T0_plan = hb.triplet_plan(host["labels"], T_PER_ANCHOR, 0.0)   # from the host-side labels, like the host sampler
@@ -333,14 +335,18 @@ def run_native(args):
 
     def run_e2e(variant):
         ups = dict(pin)
-        if variant == "device":
+        if variant in ("device", "points_only"):
             ups.update(order=order_pin, seg=seg_pin)
         else:
             ups.update(ta=trip_pin[0], tp=trip_pin[1], tn=trip_pin[2])
+        resident = {}
+        if variant == "points_only":                     # what a real step takes from the host: the clouds and the plan
+            for k in ("f1", "f2", "emb"):
+                resident[k] = ups.pop(k)
         h2d = sum(v.numel() * v.element_size() for v in ups.values())
 
         def step_of(inp):
-            if variant == "device":
+            if variant in ("device", "points_only"):
                 tr = hb.sample_triplets_device(None, seed=1234 + rank, plan=(inp["order"], inp["seg"], T0_plan))
             else:
                 tr = (inp["ta"], inp["tp"], inp["tn"])
@@ -351,6 +357,8 @@ def run_native(args):
             inp = {k: torch.empty_like(v, device=dev) for k, v in ups.items()}
             for k in ups:
                 inp[k].copy_(ups[k])
+            for k, v in resident.items():
+                inp[k] = d[k]
             if use_graph:
                 g_, outs = capture_fn(lambda: step_of(inp))
             else:
@@ -404,6 +412,7 @@ def run_native(args):
     sampler.region = "e2e"
     e2e_dev = run_e2e("device")
     e2e_host = run_e2e("host")
+    e2e_pts = run_e2e("points_only")
     clocks = sampler.stop()
 
     if rank != 0:
@@ -450,6 +459,9 @@ def run_native(args):
                 "d2h_bytes_per_step": e2e_dev["d2h_bytes_per_step"],
                 "inputs": "points, layer inputs, embeddings, sampling plan (label-sorted order + segments); triplets drawn on the GPU inside the step"},
         "e2e_host_sampled_triplets": {k: e2e_host[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")},
+        "e2e_points_only": dict({k: e2e_pts[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")},
+                                note="only what the reference's training step takes from the host goes up (point clouds + sampling plan); "
+                                     "the 63-d layer inputs and the embeddings, which device-resident layers produce there, stay in HBM"),
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
