@@ -40,7 +40,6 @@ def main():
     idx = hb.knn(x.view(B, 3 * C, N), K)
     g = torch.randn(B, 2 * C, 3, N, K, device=dev)
     bytes_ = g.numel() * 4 + idx.numel() * 8 + x.numel() * 4
-    os.environ["HPCS_BWD_NBUF"] = os.environ.get("NBUF", "2")
     prof = torch.zeros(8 * 320, dtype=torch.int64, device=dev)
     os.environ["HPCS_BWD_PROF_PTR"] = hex(prof.data_ptr())
     hgraph.edge_features_backward(g, x, idx)
@@ -53,12 +52,11 @@ def main():
     print("phase cycles per CTA (mean over %d CTAs), total %.0f:" % (pr.shape[0], tot))
     for i, nme in enumerate(names):
         print(f"   {nme:8s} {pr[:, i].mean().item():10.0f}  {100 * pr[:, i].mean().item() / tot:5.1f}%   max {pr[:, i].max().item():10.0f}")
-    for spec in sys.argv[1:] or ["81920", "16384", "8192", "4096", "2048", "1024"]:
-        chunk, _, mode = spec.partition(":")
-        os.environ["HPCS_BWD_CHUNK"] = chunk
-        os.environ["HPCS_BWD_MODE"] = mode or "0"
-        us = graph_time(lambda: hgraph.edge_features_backward(g, x, idx))
-        print(f"chunk {chunk:>6s} mode {mode or '0'}: {us:8.1f} us   {bytes_ / us / 1e3:7.1f} GB/s", flush=True)
+    us = graph_time(lambda: hgraph.edge_features_backward(g, x, idx))
+    print(f"backward (reverse-graph build + gather): {us:8.1f} us   {bytes_ / us / 1e3:7.1f} GB/s", flush=True)
+    rev = hgraph.build_reverse_graph(idx, overlap=False)
+    us = graph_time(lambda: hgraph.edge_features_backward(g, x, idx, prebuilt=rev))
+    print(f"gather alone (prebuilt reverse graph):   {us:8.1f} us   {bytes_ / us / 1e3:7.1f} GB/s", flush=True)
 
 
 if __name__ == "__main__":
