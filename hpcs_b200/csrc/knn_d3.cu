@@ -7,10 +7,11 @@
 // candidates (lane l holds candidates l, l+32, ...), so a cloud gives 32x the threads and selection becomes a
 // threshold problem:
 //   pass 1   every lane evaluates its N/32 canonical distances with packed FFMA2 (two candidates per instruction)
-//            and keeps them in registers, together with its maximum;
+//            and keeps their maximum;
 //   tau      the k-th largest of the 32 lane maxima (bitonic sort across the warp).  k lanes hold a value >= tau, so
 //            the k-th best distance of the row is >= tau: everything below tau is out, exactly;
-//   pass 2   the survivors (about 1.5 k of them, >= tau, ties included) are marked in a per-lane bit mask and appended
+//   pass 2   the distances are evaluated again (cheaper than holding N/32 registers per row: occupancy); the survivors
+//            (about 1.5 k of them, >= tau, ties included) are marked in a per-lane bit mask and appended
 //            to the row's list in shared memory at offsets from a warp scan of the per-lane counts;
 //   rank     each survivor counts the survivors that precede it in the canonical order (larger pd first, equal pd ->
 //            lower index); rank < k is its output slot.  No sort network, no insertion.
@@ -38,7 +39,7 @@ __device__ __forceinline__ bool d3_before(float v, int j, float ov, int oj) { re
 
 // S = candidate slots per lane (N <= 32 S), a power of two >= 2
 template <int S>
-__global__ void __launch_bounds__(kD3Warps * 32, S <= 32 ? 3 : 2)      // pd[S] + ~45 registers: 3 CTAs per SM up to N = 1024 (4 would spill pd[])
+__global__ void __launch_bounds__(kD3Warps * 32, S <= 32 ? 5 : 3)      // 48 registers: 40 warps per SM up to N = 1024
 knn_d3_kernel(const float* __restrict__ x, int N, int k, int64_t* __restrict__ idx, float* __restrict__ val) {
     constexpr int P = S / 2;                                        // candidate pairs per lane
     extern __shared__ __align__(16) unsigned char smraw[];
@@ -77,19 +78,21 @@ knn_d3_kernel(const float* __restrict__ x, int N, int k, int64_t* __restrict__ i
         const float2 qx2 = make_float2(qx, qx), qy2 = make_float2(qy, qy), qz2 = make_float2(qz, qz);
         const float2 two = make_float2(2.f, 2.f), nsq2 = make_float2(nsq_i, nsq_i), zero = make_float2(0.f, 0.f);
 
-        // ---- pass 1: distances into registers, lane maximum ----
-        float pd[S];
-        float lmax = -INFINITY;
-#pragma unroll
-        for (int p = 0; p < P; ++p) {
+        // ---- pass 1: lane maximum of the lane's distances.  The distances are NOT kept: pass 2 evaluates them again
+        //      (5 FFMA2 per pair, same bits) -- a register array of N/32 floats per row costs more in occupancy than the
+        //      second evaluation costs in issue slots.
+        auto pair_dist = [&](int p) -> float2 {
             const float4 a = cxy[p * 32 + lane], c = czs[p * 32 + lane];
             float2 acc = __ffma2_rn(qx2, make_float2(a.x, a.y), zero);
             acc = __ffma2_rn(qy2, make_float2(a.z, a.w), acc);
             acc = __ffma2_rn(qz2, make_float2(c.x, c.y), acc);
             const float2 t = __ffma2_rn(two, acc, nsq2);
-            const float2 d = __fadd2_rn(t, make_float2(c.z, c.w));
-            pd[2 * p] = d.x;
-            pd[2 * p + 1] = d.y;
+            return __fadd2_rn(t, make_float2(c.z, c.w));
+        };
+        float lmax = -INFINITY;
+#pragma unroll
+        for (int p = 0; p < P; ++p) {
+            const float2 d = pair_dist(p);
             lmax = fmaxf(lmax, fmaxf(d.x, d.y));
         }
         // ---- tau: k-th largest lane maximum (bitonic sort, descending across lanes) ----
@@ -112,9 +115,10 @@ knn_d3_kernel(const float* __restrict__ x, int N, int k, int64_t* __restrict__ i
         //      "precedes in the canonical order" is one unsigned 64-bit compare.
         unsigned mask = 0u, mask_hi = 0u;
 #pragma unroll
-        for (int s = 0; s < S; ++s) {
-            const unsigned bit = pd[s] >= tau ? 1u << (s & 31) : 0u;
-            if (s < 32) mask |= bit; else mask_hi |= bit;
+        for (int p = 0; p < P; ++p) {
+            const float2 d = pair_dist(p);
+            const unsigned bits = (d.x >= tau ? 1u : 0u) | (d.y >= tau ? 2u : 0u);
+            if (2 * p < 32) mask |= bits << ((2 * p) & 31); else mask_hi |= bits << ((2 * p) & 31);
         }
         const int cnt = __popc(mask) + __popc(mask_hi);
         int incl = cnt;
@@ -171,11 +175,15 @@ knn_d3_kernel(const float* __restrict__ x, int N, int k, int64_t* __restrict__ i
             for (int m = 0; m < k; ++m) {
                 float bv = -INFINITY;
                 int bj = 0x7fffffff;
+                for (int p = 0; p < P; ++p) {
+                    const float2 d = pair_dist(p);
 #pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    const int j = s * 32 + lane;
-                    const bool after = j < N && d3_before(cv, cj, pd[s], j);       // strictly after the last pick
-                    if (after && d3_before(pd[s], j, bv, bj)) { bv = pd[s]; bj = j; }
+                    for (int h = 0; h < 2; ++h) {
+                        const int j = (2 * p + h) * 32 + lane;
+                        const float v = h ? d.y : d.x;
+                        const bool after = j < N && d3_before(cv, cj, v, j);              // strictly after the last pick
+                        if (after && d3_before(v, j, bv, bj)) { bv = v; bj = j; }
+                    }
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
