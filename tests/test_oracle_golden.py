@@ -186,3 +186,46 @@ def test_get_optimal_k_restatement_matches_reference_golden():
         assert k == int(g[f"ri_k{ci}"]) and score == float(g[f"ri_score{ci}"]), ci
         if k > 0:
             assert np.array_equal(pred, g[f"ri_pred{ci}"]), ci
+
+
+def test_fcluster_and_optimal_k_restatements_randomised():
+    """Randomised sweep (seeded, no hypothesis shrinking needed): small dendrograms with many tied heights (integer
+    lattices), every k from 1 past N, single and complete linkage: restated cut == scipy.fcluster, and the IoU / ARI
+    model selection built on it == a direct evaluation with scipy + sklearn, the way the reference's get_optimal_k does."""
+    from scipy.cluster.hierarchy import fcluster, linkage
+    from sklearn.metrics import adjusted_rand_score, jaccard_score
+    rng = np.random.default_rng(123)
+    for trial in range(40):
+        n = int(rng.integers(3, 40))
+        pts = rng.integers(0, 4, size=(n, 2)).astype(np.float64) if trial % 2 else rng.standard_normal((n, 3))
+        Z = linkage(pts, method="single" if trial % 3 else "complete")
+        for k in range(1, n + 3):
+            assert np.array_equal(O.fcluster_maxclust_restated(Z, k), fcluster(Z, k, criterion="maxclust")), (trial, k)
+        y = rng.integers(0, 4, n) * 2 + 1
+        uniq = np.unique(y)
+        yt = np.searchsorted(uniq, y)
+        T = len(uniq)
+        best_iou, best_ri = (0, 0.0), (0, 0.0)
+        for k in range(1, T + 5):
+            yp = fcluster(Z, k, criterion="maxclust") - 1
+            P = len(np.unique(yp))
+            m = np.zeros((T, P), dtype=np.float32)
+            for i in range(T):
+                for j in range(P):
+                    m[i, j] = jaccard_score(yt == i, yp == j, zero_division=0)
+            ind = m.argmax(1)
+            remap = np.zeros_like(yp)
+            for i in range(T):
+                remap[yp == ind[i]] = i + 1
+            a = np.eye(T + 1)[yt + 1]
+            b = np.eye(T + 1)[remap]
+            s_iou = np.logical_and(a, b).sum() / np.logical_or(a, b).sum()
+            if s_iou > best_iou[1]:
+                best_iou = (k, s_iou)
+            s_ri = adjusted_rand_score(y, yp)
+            if s_ri > best_ri[1]:
+                best_ri = (k, s_ri)
+        _, k1, s1 = O.get_optimal_k_restated(y, Z)
+        _, k2, s2 = O.get_optimal_k_restated(y, Z, index="ri")
+        assert (k1, s1) == best_iou, (trial, (k1, s1), best_iou)
+        assert (k2, s2) == best_ri, (trial, (k2, s2), best_ri)
