@@ -624,6 +624,28 @@ def test_get_optimal_k_batch_vs_reference_golden_and_oracle(hb):
             assert np.array_equal(pred[b].cpu().numpy(), wp), (method, b)
 
 
+def test_cut_and_model_selection_with_tied_heights(hb):
+    """Integer-lattice points give dendrograms full of tied heights: the GPU cut must still equal scipy.fcluster for
+    every k, and get_optimal_k_batch (both indices) the oracle restatement, on scipy's own Z."""
+    from scipy.cluster.hierarchy import fcluster, linkage
+    rng = np.random.default_rng(77)
+    for trial in range(6):
+        n = int(rng.integers(5, 60))
+        pts = rng.integers(0, 4, size=(n, 2)).astype(np.float64)
+        Z = linkage(pts, method="single" if trial % 2 else "complete")
+        ks = list(range(1, n + 3))
+        got = hb.fcluster_maxclust(dev(torch.from_numpy(Z)), ks).cpu().numpy()
+        for i, k in enumerate(ks):
+            assert np.array_equal(got[i], fcluster(Z, k, criterion="maxclust")), (trial, k)
+        y = rng.integers(0, 4, n) * 3
+        for index in ("iou", "ri"):
+            pred, k, score = hb.get_optimal_k_batch(dev(torch.from_numpy(y)).unsqueeze(0), dev(torch.from_numpy(Z)).unsqueeze(0), index=index)
+            wp, wk, ws = O.get_optimal_k_restated(y, Z, index=index)
+            assert int(k[0]) == wk and float(score[0]) == ws, (trial, index)
+            if wk > 0:
+                assert np.array_equal(pred[0].cpu().numpy(), wp), (trial, index)
+
+
 @pytest.mark.parametrize("key", ["96", "200", "clu"])
 def test_linkage_vs_reference_golden(hb, golden, key):
     """Golden Z comes from the reference pipeline (torch-CPU normalize + project + scipy).  The leaves
