@@ -8,7 +8,7 @@ from .hyperbolic import hyp_lca, expmap0, ExpMap, normalize_project
 from .loss import (CosineSimilarity, RandomTripletMarginMiner, MetricHyperbolicLoss, CosFaceLoss,
                    get_balanced_random_triplet_indices, hyp_triplet_loss, filter_triplets,
                    sample_triplets_device, triplet_segments, triplet_plan)
-from .decode import decode_linkage, decode_linkage_batch, linkage_from_leaves, fcluster_maxclust, get_optimal_k_batch
+from .decode import decode_linkage, decode_linkage_batch, linkage_from_leaves, fcluster_maxclust, get_optimal_k_batch, get_optimal_k
 
 __all__ = [
     "knn", "get_graph_feature", "get_graph_feature_cross",
@@ -16,5 +16,5 @@ __all__ = [
     "CosineSimilarity", "RandomTripletMarginMiner", "MetricHyperbolicLoss", "CosFaceLoss",
     "get_balanced_random_triplet_indices", "hyp_triplet_loss", "filter_triplets",
     "sample_triplets_device", "triplet_segments", "triplet_plan",
-    "decode_linkage", "decode_linkage_batch", "linkage_from_leaves", "fcluster_maxclust", "get_optimal_k_batch",
+    "decode_linkage", "decode_linkage_batch", "linkage_from_leaves", "fcluster_maxclust", "get_optimal_k_batch", "get_optimal_k",
 ]

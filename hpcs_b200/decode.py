@@ -123,3 +123,22 @@ def get_optimal_k_batch(y: torch.Tensor, Z: torch.Tensor, index: str = "iou", ex
     pred = labels[torch.arange(B, device=dev), best] - 1
     pred = torch.where(found.view(B, 1), pred, torch.full_like(pred, -1))
     return pred, best_k, torch.where(found, best_score, torch.zeros_like(best_score))
+
+
+def get_optimal_k(y, linkage_matrix, index):
+    """Drop-in for ``hpcs.utils.scores.get_optimal_k`` (scores.py:141-177; called per cloud at base_hyp_hc.py:198 with
+    ``targets[i].cpu()`` and a numpy ``Z``): same arguments, same return types -- ``(best_pred: np.ndarray | None, best_k:
+    int, best_score: float)`` -- computed on the current CUDA device.  ``y`` and ``linkage_matrix`` may live on the host
+    (they are uploaded: 8 N + 32 N bytes) or on the device.  For a whole batch use :func:`get_optimal_k_batch`."""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    yt = torch.as_tensor(np.asarray(y.cpu()) if isinstance(y, torch.Tensor) and not y.is_cuda else y)
+    Zt = torch.as_tensor(linkage_matrix, dtype=torch.float64)
+    if yt.is_cuda:
+        dev = yt.device
+    elif Zt.is_cuda:
+        dev = Zt.device
+    pred, k, score = get_optimal_k_batch(yt.to(dev).reshape(1, -1), Zt.to(dev).unsqueeze(0), index=index)
+    k = int(k[0])
+    if k == 0:
+        return None, 0, 0.0
+    return pred[0].cpu().numpy(), k, float(score[0])

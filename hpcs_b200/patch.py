@@ -29,6 +29,8 @@ TARGETS = {
     ("hpcs.loss.ultrametric_loss", "MetricHyperbolicLoss"): loss.MetricHyperbolicLoss,
     ("hpcs.loss", "MetricHyperbolicLoss"): loss.MetricHyperbolicLoss,
     ("hpcs.models.base_hyp_hc", "MetricHyperbolicLoss"): loss.MetricHyperbolicLoss,
+    ("hpcs.utils.scores", "get_optimal_k"): decode.get_optimal_k,
+    ("hpcs.models.base_hyp_hc", "get_optimal_k"): decode.get_optimal_k,
 }
 
 

@@ -603,6 +603,9 @@ def test_get_optimal_k_batch_vs_reference_golden_and_oracle(hb):
         assert int(k[0]) == int(g[f"k{ci}"]), ci
         assert np.array_equal(pred[0].cpu().numpy(), g[f"pred{ci}"]), ci
         assert float(score[0]) == float(g[f"score{ci}"]), ci
+        dp, dk, ds = hb.get_optimal_k(y, g[f"Z{ci}"], "iou")                 # the drop-in: host torch labels, numpy Z, like base_hyp_hc.py:198
+        assert isinstance(dp, np.ndarray) and isinstance(dk, int) and isinstance(ds, float)
+        assert dk == int(g[f"k{ci}"]) and ds == float(g[f"score{ci}"]) and np.array_equal(dp, g[f"pred{ci}"]), ci
         pred, k, score = hb.get_optimal_k_batch(dev(y).unsqueeze(0), dev(Z).unsqueeze(0), index="ri")
         assert int(k[0]) == int(g[f"ri_k{ci}"]) and float(score[0]) == float(g[f"ri_score{ci}"]), ci
         if int(k[0]) > 0:
