@@ -19,7 +19,7 @@ _LOCK = threading.Lock()
 _LIB: Optional[ctypes.CDLL] = None
 _DEVICE_OK = set()
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # name -> (restype, argtypes); mirrors include/hpcs_b200.h one to one
 _P, _I, _L, _F, _Z = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float, _c.c_size_t

@@ -23,7 +23,9 @@
 extern "C" {
 #endif
 
-#define HPCS_ABI_VERSION 1
+/* 2: + hpcs_edge_rev_build, hpcs_edge_feat_bwd_prebuilt_f32, hpcs_triplet_sample_i32, hpcs_fcluster_maxclust_i32,
+ *    hpcs_cut_scores_f64 (additions only; every version-1 entry point is unchanged) */
+#define HPCS_ABI_VERSION 2
 
 enum {
     HPCS_OK = 0,
