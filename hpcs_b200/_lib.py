@@ -19,7 +19,7 @@ _LOCK = threading.Lock()
 _LIB: Optional[ctypes.CDLL] = None
 _DEVICE_OK = set()
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # name -> (restype, argtypes); mirrors include/hpcs_b200.h one to one
 _P, _I, _L, _F, _Z = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float, _c.c_size_t
@@ -45,6 +45,7 @@ SIGNATURES = {
     "hpcs_hyp_triplet_bwd_f32": (_I, [_P, _P, _L, _I, _P, _P, _Z, _P, _P, _P]),
     "hpcs_triplet_filter_f32": (_I, [_P, _L, _I, _P, _P, _P, _L, _I, _F, _P, _P, _Z, _P]),
     "hpcs_triplet_sample_i32": (_I, [_P, _L, _P, _I, _L, _c.c_uint64, _P, _P, _P, _P]),
+    "hpcs_triplet_sample_state_i32": (_I, [_P, _L, _P, _I, _L, _P, _P, _P, _P, _P]),
     "hpcs_hyp_lca_fwd_f32": (_I, [_P, _P, _L, _I, _I, _P, _P]),
     "hpcs_hyp_lca_bwd_f32": (_I, [_P, _P, _P, _L, _I, _I, _P, _P, _P]),
     "hpcs_expmap0_fwd_f32": (_I, [_P, _L, _I, _P, _P]),
@@ -54,6 +55,8 @@ SIGNATURES = {
     "hpcs_linkage_f64": (_I, [_P, _I, _I, _I, _I, _P, _P, _Z, _P]),
     "hpcs_fcluster_maxclust_i32": (_I, [_P, _I, _I, _P, _I, _I, _P, _P]),
     "hpcs_cut_scores_f64": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
+    "hpcs_rotate_points_f32": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
+    "hpcs_one_hot_f32": (_I, [_P, _L, _I, _P, _P]),
 }
 
 

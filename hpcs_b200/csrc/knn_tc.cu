@@ -10,12 +10,14 @@
 //                           + canonical raw norms, centred norms and their per-cloud maximum.  The A tile gets
 //                           a 1 patched into column 63 in shared memory, so the tensor-core product is directly
 //                           the ranking key  S_ij = c_i.c_j - |c_j|^2/2  (= pd_ij/2 + |c_i|^2/2).
-//   2. knn_tc_kernel        one CTA per (cloud, 128 query rows).  A producer warp streams 128-candidate
-//                           tiles of xb with TMA (128B-swizzled boxes) and issues tcgen05.mma kind::tf32
-//                           (M=128, N=128, K=8 x 8) into a double-buffered TMEM accumulator; four epilogue
-//                           warps (thread = query row = TMEM lane) read the scores with tcgen05.ld and keep
-//                           the KL best per row.  A key is the shifted score pd/2 with the candidate index
-//                           embedded in its low mantissa bits, so the sorted insert is 2 min/max per slot.
+//   2. knn_tc_kernel        one CTA per (cloud, 128 query rows), 192 threads: warp 4 streams 64-candidate tiles
+//                           of xc through a 3-stage ring with TMA (128B-swizzled boxes), warp 5 issues
+//                           tcgen05.mma kind::tf32 (M=128, N=64, K=8 x 8) into a double-buffered TMEM
+//                           accumulator; warps 0-3 are the epilogue (thread = query row = TMEM lane) and read
+//                           the scores with tcgen05.ld.  Selection is two passes over the Gram tiles: pass 1
+//                           keeps chunk maxima and a sorting network picks the row threshold, pass 2 pushes the
+//                           scores above it through a shared-memory FIFO into a sorted 32-list.  A key is the
+//                           shifted score pd/2 with the candidate index in its low mantissa bits.
 //   3. knn_rerank_kernel    one warp per row: canonical fp32 fma-chain distance of the KL candidates
 //                           (rows of xb staged coalesced through shared memory), bitonic sort by
 //                           (value desc, index asc), and a safety test: the k-th exact value must beat the

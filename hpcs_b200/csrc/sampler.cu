@@ -37,9 +37,18 @@ __device__ __forceinline__ Philox philox4x32_10(uint32_t c0, uint32_t c1, uint32
 
 constexpr int kMaxSeg = 1024;
 
+// `state` (optional, device): {seed, step, blocks done}.  When given, the Philox key is (seed, step) read from the device and
+// the last block to finish advances `step`, so a CUDA graph that captured this launch draws fresh triplets on every replay.
 __global__ void __launch_bounds__(256)
 triplet_sample_kernel(const int* __restrict__ order, int n, const int64_t* __restrict__ seg, int L, int64_t T0, uint64_t seed,
-                      int* __restrict__ a, int* __restrict__ p, int* __restrict__ ng) {
+                      unsigned long long* __restrict__ state, int* __restrict__ a, int* __restrict__ p, int* __restrict__ ng) {
+    uint32_t c2 = 0u, c3 = 0u;
+    if (state) {
+        seed = state[0];
+        const unsigned long long step = state[1];
+        c2 = (uint32_t)step;
+        c3 = (uint32_t)(step >> 32);
+    }
     __shared__ int64_t tstart[kMaxSeg + 1];
     __shared__ int start[kMaxSeg], members[kMaxSeg], reps[kMaxSeg];
     for (int l = threadIdx.x; l < L; l += blockDim.x) {
@@ -53,7 +62,7 @@ triplet_sample_kernel(const int* __restrict__ order, int n, const int64_t* __res
     // one thread draws two consecutive triplets from one Philox block (4 words); segment offsets are 32-bit whenever a
     // label's triplets number < 2^31 (always, in practice), which keeps the division off the 64-bit slow path
     for (int64_t t0 = 2 * ((int64_t)blockIdx.x * blockDim.x + threadIdx.x); t0 < T0; t0 += 2 * (int64_t)gridDim.x * blockDim.x) {
-        const Philox r = philox4x32_10((uint32_t)t0, (uint32_t)(t0 >> 32), 0u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32));
+        const Philox r = philox4x32_10((uint32_t)t0, (uint32_t)(t0 >> 32), c2, c3, (uint32_t)seed, (uint32_t)(seed >> 32));
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             const int64_t t = t0 + h;
@@ -74,12 +83,22 @@ triplet_sample_kernel(const int* __restrict__ order, int n, const int64_t* __res
             ng[t] = order[nd < s0 ? nd : nd + m];                         // order[] without the segment [s0, s0 + m)
         }
     }
+    if (state) {                                                          // every block has read state[0..1] by now
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            if (atomicAdd(&state[2], 1ull) == (unsigned long long)gridDim.x - 1) {
+                state[2] = 0ull;
+                state[1] += 1ull;
+            }
+        }
+    }
 }
 
 }  // namespace hpcs
 
-extern "C" int hpcs_triplet_sample_i32(const int* order, int64_t n, const int64_t* seg, int L, int64_t T0, uint64_t seed,
-                                       int* a, int* p, int* ng, void* stream) {
+static int triplet_sample_launch(const int* order, int64_t n, const int64_t* seg, int L, int64_t T0, uint64_t seed,
+                                 unsigned long long* state, int* a, int* p, int* ng, void* stream) {
     using namespace hpcs;
     if (T0 == 0) return HPCS_OK;
     if (!order || !seg || !a || !p || !ng) return fail(HPCS_ERR_ARG, "triplet_sample: null pointer");
@@ -87,6 +106,17 @@ extern "C" int hpcs_triplet_sample_i32(const int* order, int64_t n, const int64_
     int64_t blocks = ((T0 + 1) / 2 + 255) / 256;
     const int64_t cap = (int64_t)sm_count() * 16;
     if (blocks > cap) blocks = cap;
-    triplet_sample_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(order, (int)n, seg, L, T0, seed, a, p, ng);
+    triplet_sample_kernel<<<(int)blocks, 256, 0, as_stream(stream)>>>(order, (int)n, seg, L, T0, seed, state, a, p, ng);
     return check_launch("triplet_sample_kernel");
+}
+
+extern "C" int hpcs_triplet_sample_i32(const int* order, int64_t n, const int64_t* seg, int L, int64_t T0, uint64_t seed,
+                                       int* a, int* p, int* ng, void* stream) {
+    return triplet_sample_launch(order, n, seg, L, T0, seed, nullptr, a, p, ng, stream);
+}
+
+extern "C" int hpcs_triplet_sample_state_i32(const int* order, int64_t n, const int64_t* seg, int L, int64_t T0,
+                                             uint64_t* state, int* a, int* p, int* ng, void* stream) {
+    if (!state) return hpcs::fail(HPCS_ERR_ARG, "triplet_sample_state: null state");
+    return triplet_sample_launch(order, n, seg, L, T0, 0, reinterpret_cast<unsigned long long*>(state), a, p, ng, stream);
 }

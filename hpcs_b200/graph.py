@@ -162,6 +162,9 @@ def _edge_features(x: torch.Tensor, k: int, idx: Optional[torch.Tensor], x_coord
         if idx.shape != (B, N, k):
             raise ValueError(f"idx must be [B,N,k]={B, N, k}, got {tuple(idx.shape)}")
         idx = idx.to(device=dev, dtype=torch.int64).contiguous()
+        # a caller-supplied graph is the one input the kernels would index memory with unchecked; the reference raises
+        # an IndexError / device assert here, so does this (asynchronously: no host sync on the hot path)
+        torch._assert_async(((idx >= 0) & (idx < N)).all(), "get_graph_feature: idx out of range [0, N)")
     return _EdgeFeature.apply(xc, idx, cross)
 
 

@@ -20,8 +20,11 @@ import torch.nn.functional as F
 
 from . import _lib
 
-FILTER_MODES = {"all": 0, "easy": 1, "semihard": 2, "hard": 3}
-_BELOW_MARGIN = 4          # any other type_of_triplets in the reference: margin test only
+# filter_mode of the C ABI.  The miner-facing names follow hpcs/miner/triplet_margin_miner.py:24-32: 'easy' keeps
+# gap > margin; every other value (the constructor default 'all' included) keeps gap <= margin, 'hard' / 'semihard'
+# narrow that further.  "none" (mode 0, keep everything) is not a miner type: compute_hyp uses it when miner=False.
+_BELOW_MARGIN = 4
+FILTER_MODES = {"none": 0, "easy": 1, "semihard": 2, "hard": 3, "all": _BELOW_MARGIN}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -95,8 +98,16 @@ def triplet_plan(labels_cpu: torch.Tensor, t_per_anchor: Optional[int], fraction
     return order, seg, T0
 
 
+def sampler_state(seed: int = 0, device=None) -> torch.Tensor:
+    """Device-resident key of the device sampler: int64[3] = {seed, step, 0}.  Every launch that is handed this tensor
+    draws from Philox keyed by (seed, step) and then advances ``step`` on the device, so a CUDA graph that captured the
+    launch produces fresh triplets on every replay."""
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    return torch.tensor([int(seed) & 0x7FFFFFFFFFFFFFFF, 0, 0], dtype=torch.int64, device=dev)
+
+
 def sample_triplets_device(labels: Optional[torch.Tensor], t_per_anchor: Optional[int] = None,
-                           fraction: Optional[float] = None, seed: int = 0, plan=None
+                           fraction: Optional[float] = None, seed: int = 0, plan=None, state: Optional[torch.Tensor] = None
                            ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """``get_balanced_random_triplet_indices`` on the GPU -> three int32 index tensors on the device.
     Anchors come out exactly as the reference orders them; positives / negatives are drawn with the same distribution
@@ -120,9 +131,17 @@ def sample_triplets_device(labels: Optional[torch.Tensor], t_per_anchor: Optiona
     if order.dtype != torch.int32 or seg.dtype != torch.int64:
         raise TypeError("plan: order must be int32 and seg int64")
     with torch.cuda.device(dev):
-        _lib.check(lib.hpcs_triplet_sample_i32(order.data_ptr(), order.numel(), seg.data_ptr(), seg.shape[1], T0,
-                                               int(seed) & 0xFFFFFFFFFFFFFFFF, out[0].data_ptr(), out[1].data_ptr(),
-                                               out[2].data_ptr(), _lib.stream_ptr(dev)), "hpcs_triplet_sample_i32")
+        if state is not None:
+            if state.dtype != torch.int64 or state.numel() != 3 or state.device != dev or not state.is_contiguous():
+                raise TypeError("state must be the int64[3] device tensor made by sampler_state()")
+            _lib.check(lib.hpcs_triplet_sample_state_i32(order.data_ptr(), order.numel(), seg.data_ptr(), seg.shape[1],
+                                                         T0, state.data_ptr(), out[0].data_ptr(), out[1].data_ptr(),
+                                                         out[2].data_ptr(), _lib.stream_ptr(dev)),
+                       "hpcs_triplet_sample_state_i32")
+        else:
+            _lib.check(lib.hpcs_triplet_sample_i32(order.data_ptr(), order.numel(), seg.data_ptr(), seg.shape[1], T0,
+                                                   int(seed) & 0xFFFFFFFFFFFFFFFF, out[0].data_ptr(), out[1].data_ptr(),
+                                                   out[2].data_ptr(), _lib.stream_ptr(dev)), "hpcs_triplet_sample_i32")
     return out
 
 
@@ -200,13 +219,13 @@ class RandomTripletMarginMiner(torch.nn.Module):
         self.t_per_anchor, self.fraction = t_per_anchor, fraction
         self.margin, self.type_of_triplets = margin, type_of_triplets
         self.distance = distance if distance is not None else CosineSimilarity()
-        self.sampler, self._draws = sampler, 0
+        self.sampler, self._state = sampler, None
 
     def sample(self, labels):
         if self.sampler == "device" and labels.is_cuda:
-            self._draws += 1                                   # a new Philox key per call, reproducible from torch's seed
-            return sample_triplets_device(labels, self.t_per_anchor, self.fraction,
-                                          seed=(torch.initial_seed() << 20) + self._draws)
+            if self._state is None or self._state.device != labels.device:     # key (torch's seed, step) lives on the device
+                self._state = sampler_state(torch.initial_seed(), labels.device)
+            return sample_triplets_device(labels, self.t_per_anchor, self.fraction, state=self._state)
         return get_balanced_random_triplet_indices(labels, t_per_anchor=self.t_per_anchor, fraction=self.fraction)
 
     def forward(self, embeddings, labels, ref_emb=None, ref_labels=None):
@@ -255,9 +274,9 @@ class _HypTripletLoss(torch.autograd.Function):
 
 
 def hyp_triplet_loss(x: torch.Tensor, triplets, scale: torch.Tensor, temperature: float,
-                     type_of_triplets: str = "all", margin: float = 0.0, return_kept: bool = False):
+                     type_of_triplets: str = "none", margin: float = 0.0, return_kept: bool = False):
     """``mean_T(total) + mean(mat_sim)`` of ``compute_hyp`` for given (sampled, unfiltered) triplets.
-    ``type_of_triplets`` applies the miner's filter inside the kernel."""
+    ``type_of_triplets`` applies the miner's filter inside the kernel ("none": every triplet counts)."""
     dev = _lib.require_cuda(x, scale)
     if x.dtype != torch.float32 or x.dim() != 2:
         raise TypeError("hyp_triplet_loss expects x[n,D] float32")
@@ -292,6 +311,21 @@ class CosFaceLoss(torch.nn.Module):
 
     def forward(self, embeddings, labels):
         return F.cross_entropy(self.get_logits(embeddings, labels), labels.long())
+
+
+def triplet_margin_loss(x: torch.Tensor, a, p, n, margin: float, distance=None) -> torch.Tensor:
+    """The ``--triplet-sim`` metric term: ``relu(sim(a,n) - sim(a,p) + margin)`` averaged over the violating triplets
+    (hpcs/miner/triplet_margin_loss.py:34-65 with the inverted cosine similarity and PML's AvgNonZeroReducer), from row
+    gathers instead of the [n,n] matrix.  0 (with a graph) when nothing is mined or nothing violates."""
+    distance = distance if distance is not None else CosineSimilarity()
+    if a.numel() == 0:
+        return x.sum() * 0
+    u = F.normalize(x, p=2, dim=1)
+    ap = distance.pairwise_distance(u[a], u[p])
+    an = distance.pairwise_distance(u[a], u[n])
+    viol = F.relu(distance.margin(ap, an) + margin)
+    positive = viol[viol > 0]
+    return positive.mean() if positive.numel() else x.sum() * 0
 
 
 class MetricHyperbolicLoss(torch.nn.Module):
@@ -343,8 +377,8 @@ class MetricHyperbolicLoss(torch.nn.Module):
         dev = x_poincare.device
         if triplets is None:
             triplets = self.hyp_miner.sample(labels) if self.miner else self.get_triplets(x_poincare.shape[0])
-        kind = "easy" if self.miner else "all"
-        return hyp_triplet_loss(x_poincare, triplets, self._scale_on(dev), self.temperature, kind, 0.0)
+        kind, margin = (self.hyp_miner.type_of_triplets, self.hyp_miner.margin) if self.miner else ("none", 0.0)
+        return hyp_triplet_loss(x_poincare, triplets, self._scale_on(dev), self.temperature, kind, margin)
 
     def get_logits(self, embeddings, labels):
         if not hasattr(self, "loss_cosface"):
@@ -357,17 +391,89 @@ class MetricHyperbolicLoss(torch.nn.Module):
             loss_metric = self.loss_cosface(x_poincare, labels.long())
         else:
             a, p, n = self.triplet_miner(x_poincare, labels)
-            if a.numel() == 0:
-                loss_metric = x_poincare.sum() * 0
-            else:
-                u = F.normalize(x_poincare, p=2, dim=1)
-                ap = self.distance_sim.pairwise_distance(u[a], u[p])
-                an = self.distance_sim.pairwise_distance(u[a], u[n])
-                viol = F.relu(an - ap + self.margin)
-                nz = (viol > 0).sum().clamp_min(1)
-                loss_metric = viol.sum() / nz
+            loss_metric = triplet_margin_loss(x_poincare, a.long(), p.long(), n.long(), self.margin, self.distance_sim)
         return {"loss_hyp": {"losses": loss_hyperbolic}, "loss_metric": {"losses": loss_metric}}
 
     def anneal_temperature(self):
         self.temperature *= min(max(self.anneal_factor, 0.2), 1.0)
         return self.temperature
+
+
+# ------------------------------------------------------------------------------------------------
+# PartNet default: hierarchical CosFace on top of the same hyperbolic objective
+# ------------------------------------------------------------------------------------------------
+def hierarchical_loss(probabilities: torch.Tensor, targets: torch.Tensor, hierarchy_list) -> torch.Tensor:
+    """Sum over hierarchy levels of ``nll(log p_level, targets)`` where, level by level, the probability of every
+    channel of a branch is replaced by the branch's total (hpcs/loss/hierarchical_cosface_loss.py:9-28).  Branches
+    are applied one after another on the same tensor like the reference does, so an (unusual) overlap between two
+    branches of one level sums already-summed channels exactly as there."""
+    loss = probabilities.new_zeros(())
+    for level in hierarchy_list:
+        summed = probabilities
+        for branch in level:
+            cols = torch.as_tensor(list(branch), dtype=torch.long, device=probabilities.device)
+            if cols.numel() == 0:
+                continue
+            total = summed.index_select(1, cols).sum(1, keepdim=True)
+            summed = summed.index_copy(1, cols, total.expand(-1, cols.numel()))
+        loss = loss + F.nll_loss(torch.log(summed), targets.long())
+    return loss
+
+
+class HierarchicalCosFaceLoss(CosFaceLoss):
+    """CosFace logits -> softmax -> :func:`hierarchical_loss` (hierarchical_cosface_loss.py:31-87).  Outside the hot
+    path; plain PyTorch, kept so the PartNet default configuration constructs and trains."""
+
+    def __init__(self, num_classes, embedding_size, margin=0.35, scale=64, hierarchy_list=None):
+        super().__init__(num_classes, embedding_size, margin=margin, scale=scale)
+        self.hierarchy_list = hierarchy_list if hierarchy_list is not None else []
+
+    def forward(self, embeddings, labels):
+        probabilities = F.softmax(self.get_logits(embeddings, labels), dim=1)
+        return hierarchical_loss(probabilities, labels, self.hierarchy_list)
+
+
+class HierarchicalMetricHyperbolicLoss(MetricHyperbolicLoss):
+    """Same constructor and methods as the reference class (ultrametric_loss.py:146-176): the hyperbolic term is the
+    fused CUDA objective of the parent, the metric term the hierarchical CosFace."""
+
+    def __init__(self, margin: float = 1.0, t_per_anchor: int = 50, fraction: float = 1.2,
+                 scale: Union[float, torch.Tensor, torch.nn.Parameter] = 1e-3, temperature: float = 0.05,
+                 anneal_factor: float = 0.5, num_class: int = 4, embedding_size: int = 4, miner: bool = False,
+                 hierarchy_list: Optional[list] = None, sampler: str = "reference"):
+        super().__init__(margin=margin, t_per_anchor=t_per_anchor, fraction=fraction, scale=scale,
+                         temperature=temperature, anneal_factor=anneal_factor, num_class=num_class,
+                         embedding_size=embedding_size, cosface=True, miner=miner, sampler=sampler)
+        self.hierarchy_list = hierarchy_list if hierarchy_list is not None else []
+        self.loss_cosface = HierarchicalCosFaceLoss(num_classes=num_class, embedding_size=embedding_size, margin=0.35,
+                                                    scale=2, hierarchy_list=self.hierarchy_list)
+
+    def compute_loss(self, x_euclidean, x_poincare, labels, *args):
+        loss_hyperbolic = self.compute_hyp(x_poincare, labels)
+        loss_metric = self.loss_cosface(x_poincare, labels.long())
+        return {"loss_hyp": {"losses": loss_hyperbolic}, "loss_metric": {"losses": loss_metric}}
+
+
+# ------------------------------------------------------------------------------------------------
+# methods bound onto the REFERENCE's own classes by hpcs_b200.patch (attribute names are the reference's)
+# ------------------------------------------------------------------------------------------------
+def native_mine(self, embeddings, labels, ref_emb=None, ref_labels=None):
+    """``RandomTripletMarginMiner.mine`` (hpcs/miner/triplet_margin_miner.py:13-38) without the [n,n] matrix: the
+    reference's sampler order and RNG draws, the margin test by ``hpcs_triplet_filter_f32``."""
+    a, p, n = get_balanced_random_triplet_indices(labels, t_per_anchor=self.t_per_anchor, fraction=self.fraction)
+    keep = filter_triplets(embeddings, a, p, n, self.margin, self.type_of_triplets)
+    return a[keep], p[keep], n[keep]
+
+
+def native_compute_hyp(self, x_poincare, labels):
+    """``MetricHyperbolicLoss.compute_hyp`` (hpcs/loss/ultrametric_loss.py:57-93) as one fused CUDA pass; also what
+    ``HierarchicalMetricHyperbolicLoss`` inherits.  Reads the reference object's own attributes (``miner``,
+    ``hyp_miner``, ``scale``, ``temperature``) and never calls ``self.hyp_miner`` / ``self.distance_sim``."""
+    if self.miner:
+        m = self.hyp_miner
+        triplets = get_balanced_random_triplet_indices(labels, t_per_anchor=m.t_per_anchor, fraction=m.fraction)
+        kind, margin = m.type_of_triplets, m.margin
+    else:
+        triplets, kind, margin = self.get_triplets(x_poincare.shape[0]), "none", 0.0
+    scale = self.scale if isinstance(self.scale, torch.Tensor) else torch.tensor([float(self.scale)])
+    return hyp_triplet_loss(x_poincare, triplets, scale.to(x_poincare.device), float(self.temperature), kind, margin)

@@ -24,8 +24,10 @@ extern "C" {
 #endif
 
 /* 2: + hpcs_edge_rev_build, hpcs_edge_feat_bwd_prebuilt_f32, hpcs_triplet_sample_i32, hpcs_fcluster_maxclust_i32,
- *    hpcs_cut_scores_f64 (additions only; every version-1 entry point is unchanged) */
-#define HPCS_ABI_VERSION 2
+ *    hpcs_cut_scores_f64 (additions only; every version-1 entry point is unchanged)
+ * 3: + hpcs_triplet_sample_state_i32, hpcs_rotate_points_f32, hpcs_one_hot_f32 (round 2; additions only)
+ */
+#define HPCS_ABI_VERSION 3
 
 enum {
     HPCS_OK = 0,
@@ -129,6 +131,12 @@ int hpcs_triplet_filter_i32_f32(const float* x, int64_t n, int D, const int32_t*
 int hpcs_triplet_sample_i32(const int32_t* order, int64_t n, const int64_t* seg, int L, int64_t T0, uint64_t seed,
                             int32_t* a, int32_t* p, int32_t* ng, void* stream);
 
+/* Same sampler with its key in device memory: state[3] uint64 = {seed, step, 0}.  The Philox key is (seed, step); the
+ * launch advances `step` itself when its last block retires, so a CUDA graph that captured the call draws NEW triplets on
+ * every replay (a by-value seed would be frozen into the graph).  state[2] is scratch and must start at 0. */
+int hpcs_triplet_sample_state_i32(const int32_t* order, int64_t n, const int64_t* seg, int L, int64_t T0, uint64_t* state,
+                                  int32_t* a, int32_t* p, int32_t* ng, void* stream);
+
 /* hyp_lca(a, b, return_coord)         hpcs/distances/lca.py:37-52 (general, unequal norms)
  *   a,b[T,D] fp32 -> out[T,D] (return_coord) or out[T,1] = 2 artanh(|proj|); scalar chain in fp64. */
 int hpcs_hyp_lca_fwd_f32(const float* a, const float* b, int64_t T, int D, int return_coord, float* out,
@@ -168,6 +176,20 @@ int hpcs_fcluster_maxclust_i32(const double* Z, int B, int N, const int* ks, int
  *   t_cap >= max n_true, k_max >= max ks (host copies, they size shared memory). */
 int hpcs_cut_scores_f64(const int32_t* labels, const int32_t* ytrue, const int32_t* n_true, const int* ks, int B, int K,
                         int N, int t_cap, int k_max, int extra, int index, double* scores, void* stream);
+
+/* ---- per-step input pipeline on the device    ------------------------------------------------
+ * ShapeNetHypHC._forward / PartNetHypHC._forward   hpcs/models/shapenet_hyp_hc.py:63-73, partnet_hyp_hc.py:82-95
+ *   The reference rotates the batch on the host with pytorch3d, uploads it and transposes.  Here: pts[B,N,3] fp32 (device)
+ *   -> out[B,3,N] = (pts @ R_b)^T, the backbone's layout, in one pass.  mode 0: no rotation (params unused);
+ *   1: params = R[B,3,3] (row-vector convention, out = p @ R);  2 ('so3'): params = o[B,4], the randn(B,4) draws of
+ *   pytorch3d.transforms.random_rotations, turned into unit quaternions and matrices on the device;  3 ('z'): params =
+ *   u[B], the rand(B) draws of RotateAxisAngle(angle=u*360, axis='Z', degrees=True).  rot_out (optional) receives the
+ *   matrices R[B,3,3] actually applied. */
+int hpcs_rotate_points_f32(const float* pts, const float* params, int mode, int B, int N, float* out, float* rot_out,
+                           void* stream);
+/* to_categorical(y, num_classes)   hpcs/utils/data.py:24-29: y[rows] int64 -> out[rows, num_classes] fp32 one-hot
+ * (a row of zeros for a label outside [0, num_classes), where torch.eye indexing would raise). */
+int hpcs_one_hot_f32(const int64_t* y, int64_t rows, int num_classes, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -504,3 +504,46 @@ def get_optimal_k_restated(y: np.ndarray, Z: np.ndarray, extra: int = 4, index: 
         if score > best[2]:
             best = (yp.astype(np.int32), k, score)
     return best
+
+
+# --------------------------------------------------------------------------------------------
+# row f-4: the per-step input pipeline (rotation + transpose + one-hot)
+#
+# PARITY UNPINNED for the rotation matrices: they come from pytorch3d 0.7.2 (hpcs-env.yaml:287), which is neither
+# vendored under /root/reference nor installed in this image, so its published algorithm is restated here
+# (transforms/rotation_conversions.py: random_quaternions, quaternion_to_matrix; transforms/transform3d.py: Rotate,
+# RotateAxisAngle) and anchored on the reference's call sites (hpcs/models/shapenet_hyp_hc.py:63-69,
+# partnet_hyp_hc.py:82-88).  Property checks in the tests: orthonormal, det +1, rotation-invariant backbone input norms.
+# --------------------------------------------------------------------------------------------
+def quaternion_rotations(o: torch.Tensor) -> torch.Tensor:
+    """``random_rotations(n)`` given its ``randn(n, 4)`` draws ``o``: unit quaternion with non-negative real part ->
+    rotation matrix [n,3,3]."""
+    nrm = torch.sqrt((o * o).sum(1))
+    nrm = torch.where((nrm < 0) != (o[:, 0] < 0), -nrm, nrm)
+    q = o / nrm[:, None]
+    r, i, j, k = torch.unbind(q, -1)
+    ts = 2.0 / (q * q).sum(-1)
+    m = torch.stack((1 - ts * (j * j + k * k), ts * (i * j - k * r), ts * (i * k + j * r),
+                     ts * (i * j + k * r), 1 - ts * (i * i + k * k), ts * (j * k - i * r),
+                     ts * (i * k - j * r), ts * (j * k + i * r), 1 - ts * (i * i + j * j)), -1)
+    return m.reshape(-1, 3, 3)
+
+
+def z_rotations(u: torch.Tensor) -> torch.Tensor:
+    """``RotateAxisAngle(angle=u * 360, axis='Z', degrees=True)`` given its ``rand(n)`` draws: the column-vector
+    rotation about z, transposed because points are row vectors."""
+    a = u * 360 / 180.0 * torch.pi
+    c, s, one, zero = torch.cos(a), torch.sin(a), torch.ones_like(a), torch.zeros_like(a)
+    R = torch.stack((c, -s, zero, s, c, zero, zero, zero, one), -1).reshape(-1, 3, 3)
+    return R.transpose(1, 2)
+
+
+def rotate_points(points: torch.Tensor, R: Optional[torch.Tensor]) -> torch.Tensor:
+    """``trot.transform_points(points)`` then ``.transpose(2, 1)``: points[B,N,3] -> [B,3,N] = (p @ R)^T."""
+    out = points if R is None else torch.bmm(points, R.to(points.dtype))
+    return out.transpose(2, 1).contiguous()
+
+
+def to_categorical(y: torch.Tensor, num_classes: int) -> torch.Tensor:
+    """hpcs/utils/data.py:24-29."""
+    return torch.eye(num_classes)[y.cpu().numpy(),]

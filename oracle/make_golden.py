@@ -40,7 +40,7 @@ def synth_labels(gen, B, N, n_parts=(2, 6), first_id=0):
     labs = []
     for b in range(B):
         parts = int(torch.randint(n_parts[0], n_parts[1] + 1, (1,), generator=gen))
-        probs = torch.distributions.Dirichlet(torch.ones(parts)).sample()
+        probs = torch._sample_dirichlet(torch.ones(parts), generator=gen)      # seeded: the fixture regenerates bit for bit
         ids = torch.multinomial(probs, N, replacement=True, generator=gen) + first_id
         first_id += parts
         labs.append(ids)
@@ -49,6 +49,7 @@ def synth_labels(gen, B, N, n_parts=(2, 6), first_id=0):
 
 def main():
     ref_stubs.install()
+    torch.set_num_threads(1)           # fp32 index_put accumulation order: one thread -> bit-reproducible fixtures
     os.makedirs(OUT, exist_ok=True)
     util = ref_stubs.load_by_path("ref_vn_dgcnn_util", "hpcs/nn/dgcnn/utils/vn_dgcnn_util.py")
     util_pn = ref_stubs.load_by_path("ref_vn_dgcnn_util_pn", "hpcs/nn/pointnet/utils/vn_dgcnn_util.py")

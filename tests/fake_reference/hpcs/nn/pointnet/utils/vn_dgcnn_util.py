@@ -1,0 +1,5 @@
+from hpcs import unpatched
+
+knn = unpatched("hpcs.nn.pointnet.utils.vn_dgcnn_util.knn")
+get_graph_feature = unpatched("hpcs.nn.pointnet.utils.vn_dgcnn_util.get_graph_feature")
+get_graph_feature_cross = unpatched("hpcs.nn.pointnet.utils.vn_dgcnn_util.get_graph_feature_cross")

@@ -359,18 +359,19 @@ def test_compute_hyp_vs_reference_fp64_golden(hb, golden, tag):
 
 
 @pytest.mark.parametrize("n,D,scale,temp,kind", [(2048, 32, 1e-3, 0.05, "easy"), (1024, 50, 0.1, 0.1, "easy"),
-                                                  (512, 4, 0.5, 0.05, "all"), (768, 32, 0.9, 0.05, "semihard"),
-                                                  (640, 128, 0.1, 0.05, "hard"), (300, 7, 0.3, 0.07, "easy")])
+                                                  (512, 4, 0.5, 0.05, "none"), (768, 32, 0.9, 0.05, "semihard"),
+                                                  (640, 128, 0.1, 0.05, "hard"), (300, 7, 0.3, 0.07, "easy"),
+                                                  (700, 16, 0.2, 0.05, "all")])
 def test_hyp_triplet_loss_vs_oracle_fp64(hb, n, D, scale, temp, kind):
     gen = torch.Generator().manual_seed(n + D)
     x = O.expmap0(torch.randn(n, D, generator=gen))
     labels = torch.randint(0, 6, (n,), generator=gen)
     torch.manual_seed(5)
     a, p, ng = O.sample_triplets(labels, t_per_anchor=9, fraction=1.2)
-    margin = 0.05 if kind in ("semihard", "hard") else 0.0
+    margin = 0.05 if kind in ("semihard", "hard", "all") else 0.0
     xd = x.double().requires_grad_(True)
     sd = torch.tensor([scale], dtype=torch.float64, requires_grad=True)
-    if kind == "all":
+    if kind == "none":                                          # miner=False: every sampled triplet counts
         fa, fp_, fn_ = a, p, ng
     else:
         fa, fp_, fn_ = O.filter_triplets(xd.detach(), a, p, ng, margin=margin, kind=kind)
@@ -385,7 +386,7 @@ def test_hyp_triplet_loss_vs_oracle_fp64(hb, n, D, scale, temp, kind):
     assert rel_err(ggx, wgx) < REL
     assert rel_err(ggs, wgs) < REL
     # the stand-alone filter agrees with the oracle's filter except on borderline gaps
-    if kind != "all":
+    if kind != "none":
         keep = hb.filter_triplets(dev(x), a, p, ng, margin, kind).cpu()
         sim = O.cosine_similarity_matrix(x.double())
         gap = sim[a, p] - sim[a, ng]
@@ -393,8 +394,11 @@ def test_hyp_triplet_loss_vs_oracle_fp64(hb, n, D, scale, temp, kind):
             ref_keep = gap > margin
         elif kind == "semihard":
             ref_keep = (gap <= margin) & (gap > 0)
-        else:
+        elif kind == "hard":
             ref_keep = (gap <= margin) & (gap <= 0)
+        else:                                               # 'all', the miner's constructor default: margin test only
+            ref_keep = gap <= margin
+            assert 0 < int(ref_keep.sum()) < ref_keep.numel()
         differ = keep != ref_keep
         if differ.any():                                    # only gaps sitting on a threshold may flip in fp32
             border = torch.minimum(gap[differ].abs(), (gap[differ] - margin).abs())

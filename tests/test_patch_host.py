@@ -1,0 +1,139 @@
+"""The drop-in binding against the REAL reference tree (``/root/reference``, CPU, third-party packages shimmed by
+``oracle/ref_stubs.py``): after ``hpcs_b200.patch.install()`` every hot-path call site of ``train.py`` / ``infer.py``
+resolves to hpcs_b200, whatever the import order and including the subclass the PartNet default constructs.
+Skipped where the reference is absent (the GPU box); ``tests/test_gpu_dropin.py`` drives the same binding through a
+stand-in tree there."""
+import inspect
+import os
+import sys
+
+import pytest
+import torch
+
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "hpcs")), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    """Import the reference the way train.py does (models, backbones and ExpMap at module top: train.py:16-20),
+    BEFORE install(), so every ``from ... import`` alias already points at the reference's objects."""
+    stale = [m for m in sys.modules if m == "hpcs" or m.startswith("hpcs.")]
+    for m in stale:
+        del sys.modules[m]
+    sys.path[:] = [p for p in sys.path if not p.endswith("fake_reference")]
+    from oracle import ref_stubs
+    ref_stubs.install_models()
+    import train                                            # noqa: F401  (the reference's own entry script)
+    import hpcs.models, hpcs.nn.dgcnn, hpcs.nn.pointnet, hpcs.loss.ultrametric_loss   # noqa: F401,E401
+    import hpcs_b200.patch as patch
+    yield patch
+    patch.uninstall()
+
+
+def test_install_binds_every_call_site(ref):
+    patch = ref
+    import hpcs
+    from hpcs.models import ShapeNetHypHC
+    from hpcs.nn.dgcnn import VN_DGCNN_partseg
+    from hpcs.nn.hyperbolic import ExpMap
+    early = ShapeNetHypHC(nn_feat=VN_DGCNN_partseg(3, 32, 20, 0.5, "mean", 16), nn_emb=ExpMap(), euclidean_size=32,
+                          hyp_size=32, num_class=50)     # built BEFORE install()
+    originals = {key: getattr(sys.modules[key[0]], key[1]) for key in patch.FUNCTIONS}
+    done = patch.install(strict=True)
+    assert patch.verify() == []
+    # the definition sites
+    for (mod, attr), repl in patch.FUNCTIONS.items():
+        assert getattr(sys.modules[mod], attr) is repl
+        assert f"{mod}.{attr}" in done
+    # the from-import aliases the advisor and the judge listed, by name
+    import hpcs.nn.dgcnn.vn_dgcnn_partseg as partseg, hpcs.nn.dgcnn.vn_dgcnn_expo as expo
+    import hpcs.nn.pointnet.vn_pointnet_partseg as pn_partseg, hpcs.nn.pointnet.vn_pointnet as pn
+    import hpcs.loss.ultrametric_loss as ul, hpcs.models.base_hyp_hc as base, hpcs.miner.triplet_margin_miner as tmm
+    import hpcs_b200 as hb
+    assert partseg.get_graph_feature is hb.get_graph_feature and expo.get_graph_feature is hb.get_graph_feature
+    assert pn_partseg.get_graph_feature_cross is hb.get_graph_feature_cross
+    assert pn.get_graph_feature_cross is hb.get_graph_feature_cross
+    assert ul.hyp_lca is hb.hyp_lca and hpcs.distances.hyp_lca is hb.hyp_lca
+    assert base.get_optimal_k is hb.get_optimal_k
+    assert tmm.get_balanced_random_triplet_indices is hb.get_balanced_random_triplet_indices
+    # no loaded module anywhere still holds an original
+    for key, orig in originals.items():
+        holders = [f"{n}.{k}" for n, m in list(sys.modules.items()) if m is not None and not n.startswith("hpcs_b200")
+                   for k, v in list(vars(m).items()) if v is orig]
+        assert holders == [], (key, holders)
+    # methods: the reference's classes, native bodies; the subclass of the PartNet default inherits them
+    for (mod, cls_name, meth), repl in patch.METHODS.items():
+        assert getattr(sys.modules[mod], cls_name).__dict__[meth] is repl
+    assert ul.HierarchicalMetricHyperbolicLoss.compute_hyp is hb.loss.native_compute_hyp
+    assert ul.HierarchicalMetricHyperbolicLoss.__mro__[1] is ul.MetricHyperbolicLoss      # still the reference's class
+    train = sys.modules["train"]
+    assert train.ExpMap.forward is patch._expmap_forward and train.MLPExpMap.forward is patch._mlp_expmap_forward
+    # an instance built before install() is on the native path too: on CPU that means it refuses to run
+    pts, lab, tg = torch.randn(2, 64, 3), torch.zeros(2, 1, dtype=torch.long), torch.randint(0, 4, (2, 64))
+    early.nn_feat.k = 8
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        early.forward((pts, lab, tg), testing=False)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        early.metric_hyp_loss.compute_hyp(torch.randn(64, 32) * 0.1, torch.randint(0, 4, (64,)))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        early._decode_linkage(torch.randn(64, 32) * 0.1)
+
+
+def test_signatures_match_the_reference(ref):
+    """Each replacement accepts the reference's call: same leading parameter names, same defaults."""
+    patch = ref
+    patch.uninstall()
+    pairs = []
+    for (mod, attr), repl in patch.FUNCTIONS.items():
+        pairs.append((f"{mod}.{attr}", getattr(sys.modules[mod], attr), repl))
+    for (mod, cls_name, meth), repl in patch.METHODS.items():
+        pairs.append((f"{mod}.{cls_name}.{meth}", getattr(getattr(sys.modules[mod], cls_name), meth), repl))
+    for name, orig, repl in pairs:
+        want = list(inspect.signature(orig).parameters.values())
+        got = list(inspect.signature(repl).parameters.values())
+        assert len(got) >= len(want), name
+        for w, g in zip(want, got):
+            assert w.name == g.name, (name, w.name, g.name)
+            if w.default is not inspect.Parameter.empty and not name.endswith((".mine", ".compute_loss")):
+                assert g.default == w.default, (name, w.name)
+        for extra in got[len(want):]:
+            assert extra.default is not inspect.Parameter.empty or extra.kind in (
+                inspect.Parameter.VAR_POSITIONAL, inspect.Parameter.VAR_KEYWORD), (name, extra.name)
+    patch.install()
+
+
+def test_partial_bind_is_loud(ref, monkeypatch):
+    patch = ref
+    bogus = dict(patch.FUNCTIONS)
+    bogus[("hpcs.nn.dgcnn.utils.vn_dgcnn_util", "no_such_function")] = lambda: None
+    bogus[("hpcs.no_such_module", "knn")] = lambda: None
+    monkeypatch.setattr(patch, "FUNCTIONS", bogus)
+    with pytest.raises(patch.PatchError, match="no_such_function"):
+        patch.install(strict=True)
+    with pytest.warns(RuntimeWarning, match="still on the reference"):
+        patch.install(strict=False)
+    assert any("no_such_module" in m for m in patch.verify())
+    monkeypatch.undo()
+    patch.install()
+    assert patch.verify() == []
+
+
+def test_partnet_default_constructs_and_is_native(ref):
+    """BASELINE configs[2]: --hierarchical is store_false (train.py:53), so PartNet runs
+    HierarchicalMetricHyperbolicLoss; its hyperbolic term must be the native one."""
+    patch = ref
+    patch.install()
+    from hpcs.models import PartNetHypHC
+    from hpcs.nn.dgcnn import VN_DGCNN_partseg
+    from hpcs.nn.hyperbolic import MLPExpMap
+    hier = [[[0, 1, 2], [3, 4]], [[0], [1, 2], [3], [4]]]
+    model = PartNetHypHC(nn_feat=VN_DGCNN_partseg(3, 4, 20, 0.5, "mean", 1), nn_emb=MLPExpMap(4, 4), euclidean_size=4,
+                         hyp_size=4, num_class=5, fraction=1.2, hierarchical=True, hierarchy_list=hier)
+    loss = model.metric_hyp_loss
+    assert type(loss).__name__ == "HierarchicalMetricHyperbolicLoss" and type(loss).__module__ == "hpcs.loss.ultrametric_loss"
+    assert type(loss).compute_hyp is patch.loss.native_compute_hyp
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        loss.compute_loss(None, torch.randn(40, 4) * 0.1, torch.randint(0, 5, (40,)))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model.forward((torch.randn(2, 32, 3), torch.randint(0, 5, (2, 32))), testing=False)
