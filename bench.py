@@ -21,7 +21,10 @@ all-reduce of the `scale` gradient, the one trainable parameter on this path.
             timed region; the input gradients stay in HBM for the caller's backward.
 `roofline`: the single kernel with the largest share of the step (the persistent edge-backward gather); per-op
             figures, including that backward together with its reverse-graph build, under "ops".
-`--impl reference`: the oracle's restatement of the reference's PyTorch CPU path, on host cores.
+`peaks`   : pipe / cache peaks measured in this process by csrc/peaks.cu (fp32 FMA, ALU, fp64, TF32 tcgen05, L2
+            gathers) next to MEASURED_PEAKS.json's HBM figure: every entry of "ops" has a denominator.
+`decode`  : BASELINE configs[4] sub-record (single + complete linkage, 8 clouds per GPU = 64 on 8 GPUs, and 64 per GPU).
+`--impl reference`: the oracle's restatement of the reference's PyTorch CPU path, on host cores, same batch (32).
 """
 from __future__ import annotations
 
@@ -42,6 +45,13 @@ B_PER_GPU, N_PTS, K_NN, C_FEAT, D_EMB, T_PER_ANCHOR = 32, 1024, 20, 21, 32, 50
 SCALE, TEMPERATURE = 1e-3, 0.05
 METRIC = "point clouds/sec (1024 pts, k=20) fwd+bwd"
 UNIT = "clouds/s"
+# the one collective of a training step: all-reduce of the fp32 gradients -- VN_DGCNN_partseg's 1,303,850
+# parameters (out=32, 16 categories) + CosFace W[32,50] + scale
+GRAD_BUCKET_FLOATS = 1_303_850 + D_EMB * 50 + 1
+MIN_TIMED_MS = 250.0                   # the timed region replays the step until it lasts at least this long
+# thread-level fp32 instructions per mined triplet in hyp_triplet_kernel<8,1> (loss forward + gradient state), from the
+# ncu capture profiles/r01_g_ncu_full.md: 303.2 FFMA + 123.5 FADD + 140.4 FMUL per triplet at the bench shape
+LOSS_FLOP_PER_TRIPLET = 2 * 303.2 + 123.5 + 140.4
 
 
 # DRAM bytes per op from the committed `ncu --set full` capture (profiles/r01_d_ncu_full.md): read + written,
@@ -82,6 +92,20 @@ def synth_inputs(B, seed):
     return {"pts": pts, "f1": f1, "f2": f2, "emb": emb, "labels": labels}
 
 
+def clustered_features(B, seed, centres=6):
+    """[B, 63, N] 'backbone-like' features for the D=63 kNN: every cloud is a mixture of a few tight clusters (points of
+    one part have similar features after an EdgeConv layer), all clouds share a common offset of a few sigma and the
+    channels are correlated through a random low-rank mixing."""
+    gen = torch.Generator().manual_seed(seed)
+    D = 3 * C_FEAT
+    cen = torch.randn(B, centres, D, generator=gen)
+    which = torch.randint(0, centres, (B, N_PTS), generator=gen)
+    x = torch.gather(cen, 1, which.unsqueeze(-1).expand(-1, -1, D)) + 0.15 * torch.randn(B, N_PTS, D, generator=gen)
+    mix = torch.eye(D) + 0.3 * torch.randn(D, 8, generator=gen) @ torch.randn(8, D, generator=gen) / 8 ** 0.5
+    x = x @ mix + 2.0 * torch.randn(1, 1, D, generator=gen)
+    return x.transpose(1, 2).contiguous()
+
+
 def algorithmic_work(B):
     """Per-op algorithmic bytes / flops (DESIGN.md 'Kernels and rooflines')."""
     n = B * N_PTS
@@ -100,7 +124,11 @@ def algorithmic_work(B):
         "edge_fwd_c1": {"bytes": e1f}, "edge_bwd_c1": {"bytes": e1b},
         "edge_fwd_c21": {"bytes": e21f}, "edge_bwd_c21": {"bytes": e21b},
         "edge_bwd_gather_c21": {"bytes": e21b}, "edge_rev_build": {"bytes": B * E * 8},
-        "hyp_loss_fwd_bwd": {"flop": T0 * 2100.0, "bytes": T0 * 24.0 + 3 * n * D_EMB * 4},
+        "knn_d63_clustered": {"flop": B * N_PTS * N_PTS * (2 * 63 + 3.0), "bytes": B * (252 * N_PTS + 8 * E)},
+        # L2 traffic of the loss: three 128-byte rows gathered per mined triplet; HBM: 12 bytes of int32 indices per
+        # triplet in, table + gradient out.  flop: measured instruction mix (LOSS_FLOP_PER_TRIPLET)
+        "hyp_loss_fwd_bwd": {"flop": T0 * LOSS_FLOP_PER_TRIPLET, "l2_bytes": T0 * 3.0 * D_EMB * 4,
+                             "bytes": T0 * 24.0 + 3 * n * D_EMB * 4},
     }
 
 
@@ -184,6 +212,10 @@ def run_native(args):
     g2 = torch.randn(B, 2 * C_FEAT, 3, N_PTS, K_NN, device=dev, generator=gen)
     g3 = torch.randn(B, 2 * C_FEAT, 3, N_PTS, K_NN, device=dev, generator=gen)
 
+    # gradient bucket of a training step: the backbone / CosFace gradients are produced by layers outside this
+    # path, so their slots hold synthetic values; d loss / d scale, the one gradient this path produces, is the last slot
+    bucket = torch.randn(GRAD_BUCKET_FLOATS, device=dev, generator=gen) if world > 1 else None
+
     def loss_fwd_bwd(emb_in, tr):
         emb = emb_in.detach().requires_grad_(True)
         sc = scale.detach().requires_grad_(True)            # fresh leaves: keeps autograd on the capturing stream
@@ -195,7 +227,8 @@ def run_native(args):
         """The order a training step runs these ops in: the three layers' kNN + edge features (forward), the loss
         forward+backward on the embeddings, then the edge-feature backwards from the last layer to the first.  The
         all-reduce of d loss / d scale (the path's only parameter) is issued as soon as the loss backward has produced
-        it and overlaps the edge backwards."""
+        it and overlaps the edge backwards; it carries the whole 5.2 MB fp32 gradient bucket of the model (the reference's
+        DDP exchange), not just that scalar."""
         xs = [inp[k].detach().requires_grad_(True) for k in ("pts", "f1", "f2")]
         ys = []
         for x in xs:
@@ -203,11 +236,14 @@ def run_native(args):
             idx = hb.knn(x.detach().view(Bc, 3 * C, Np), K_NN)
             ys.append(hb.get_graph_feature(x, K_NN, idx=idx))
         loss, kept, ge, gs = loss_fwd_bwd(inp["emb"], tr)
-        work = dist.all_reduce(gs, op=dist.ReduceOp.SUM, async_op=True) if world > 1 else None
+        work = None
+        if world > 1:
+            bucket[-1:].copy_(gs.reshape(1))
+            work = dist.all_reduce(bucket, op=dist.ReduceOp.SUM, async_op=True)
         gxs = [torch.autograd.grad(y, x, g)[0] for y, x, g in zip(ys[::-1], xs[::-1], (g3, g2, g1))]
         if work is not None:
             work.wait()
-            gs = gs / world
+            gs = bucket[-1:] / world
         return loss, kept, gs, (gxs[2], gxs[1], gxs[0], ge)
 
     def barrier():
@@ -248,26 +284,28 @@ def run_native(args):
         def run_step():
             nonlocal out
             out = step(d, trip)
-    for _ in range(max(args.warmup, 3)):
+    R = max(1, args.batches_per_step)               # one timed "step" = R batches back to back (a >= 250 ms region)
+    for _ in range(max(args.warmup, 3) * R):
         run_step()
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0.record()
-    for _ in range(args.steps):
+    for _ in range(args.steps * R):
         run_step()
     t1.record()
     if sampler._nv is not None:
         sampler.sample()                                    # the replays are queued: the GPU is busy right now
     barrier()
     sampler.region = "ops"
-    launches = launches_per_step * args.steps
+    launches = launches_per_step * args.steps * R
     ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms_per_step = ms.item() / args.steps
-    value = world * B / (ms_per_step * 1e-3)
+    ms_per_step = ms.item() / args.steps                   # R batches
+    ms_per_batch = ms_per_step / R
+    value = world * B * R / (ms_per_step * 1e-3)
     loss_val, kept_val = float(out[0].detach()), int(out[1])
 
     # ---- per-op durations: every op of the step captured into its OWN CUDA graph and replayed K times
@@ -285,11 +323,11 @@ def run_native(args):
         torch.cuda.synchronize()
         s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s_.record()
-        for _ in range(args.steps):
+        for _ in range(args.steps * R):
             g_.replay()
         e_.record()
         torch.cuda.synchronize()
-        op_ms[name] = s_.elapsed_time(e_) / args.steps
+        op_ms[name] = s_.elapsed_time(e_) / (args.steps * R)
 
     with torch.no_grad():
         x3 = d["pts"].view(B, 3, N_PTS)
@@ -297,6 +335,15 @@ def run_native(args):
         idx3, idx63 = hb.knn(x3, K_NN), hb.knn(x63, K_NN)
         time_op("knn_d3", lambda: hb.knn(x3, K_NN), 1)
         time_op("knn_d63", lambda: hb.knn(x63, K_NN), 2)
+        # the same kNN on backbone-like features: a few tight clusters per cloud, off-centre, correlated channels (the
+        # N(0,1) features above are the tensor-core path's best case: no row needs the exact redo)
+        xclu = clustered_features(B, seed=100 + rank).to(dev)
+        knn_stats = {}
+        for tag, xin in (("gaussian", x63), ("clustered", xclu)):
+            st_ = {}
+            hb.knn(xin, K_NN, stats=st_)
+            knn_stats[tag] = st_.get("fallback_rows")
+        time_op("knn_d63_clustered", lambda: hb.knn(xclu, K_NN), 0)
         time_op("edge_fwd_c1", lambda: hgraph.edge_features_forward(d["pts"], idx3), 1)
         time_op("edge_fwd_c21", lambda: hgraph.edge_features_forward(d["f1"], idx63), 2)
         time_op("edge_bwd_c1", lambda: hgraph.edge_features_backward(g1, d["pts"], idx3), 1)
@@ -345,9 +392,11 @@ def run_native(args):
                 resident[k] = ups.pop(k)
         h2d = sum(v.numel() * v.element_size() for v in ups.values())
 
+        samp_state = hb.sampler_state(1234 + rank, dev)     # (seed, step) on the device: every replay draws new triplets
+
         def step_of(inp):
             if variant in ("device", "points_only"):
-                tr = hb.sample_triplets_device(None, seed=1234 + rank, plan=(inp["order"], inp["seg"], T0_plan))
+                tr = hb.sample_triplets_device(None, plan=(inp["order"], inp["seg"], T0_plan), state=samp_state)
             else:
                 tr = (inp["ta"], inp["tp"], inp["tn"])
             return step(inp, tr)
@@ -398,7 +447,7 @@ def run_native(args):
         barrier()
         te0, te1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         te0.record()
-        loop(args.steps)
+        loop(args.steps * R)
         for s_ in (s_up, s_run, s_down):
             torch.cuda.current_stream().wait_stream(s_)
         te1.record()
@@ -406,9 +455,15 @@ def run_native(args):
         ms_e = torch.tensor([te0.elapsed_time(te1)], device=dev)
         if world > 1:
             dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
-        return {"value": round(world * B / (ms_e.item() / args.steps * 1e-3), 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "loss": float(res_pin[(args.steps - 1) % 2][0])}
+        return {"value": round(world * B * R / (ms_e.item() / args.steps * 1e-3), 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d) * R,
+                "d2h_bytes_per_step": int(d2h) * R, "loss": float(res_pin[(args.steps * R - 1) % 2][0])}
 
+    sampler.region = "peaks"
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import peaks as peak_probes
+    probes = peak_probes.measure(dev)
+    decode_rec = decode_subrecord(hb, dev, rank) if not args.no_decode else None
+    barrier()
     sampler.region = "e2e"
     e2e_dev = run_e2e("device")
     e2e_host = run_e2e("host")
@@ -423,15 +478,34 @@ def run_native(args):
     for name, avg_ms in op_ms.items():
         n_launch, calls_per_step = op_launches[name]
         w = work[name]
+        sec = avg_ms * 1e-3
         ent = {"ms": round(avg_ms, 4), "calls_per_step": calls_per_step, "kernels_per_call": n_launch,
-               "share": round(avg_ms * calls_per_step / ms_per_step, 4)}
+               "share": round(avg_ms * calls_per_step / ms_per_batch, 4)}
         if name == "edge_rev_build":
-            ent.update(bound="latency (shared-memory atomics, prefix sums; one wave of 128 CTAs)", achieved=None, peak=None, unit=None)
+            # two passes over idx (read) + the reverse lists (written); the kernel is a latency chain, the HBM figure
+            # only says how far from a bandwidth limit it sits
+            ent.update(bound="latency (shared-memory atomics, prefix sums; one wave of 128 CTAs); HBM figure for scale",
+                       achieved=round(w["bytes"] / sec / 1e9, 1), peak=pk["hbm_gbs"], unit="GB/s")
         elif name.startswith("edge"):
-            ent.update(bound="hbm", achieved=round(w["bytes"] / (avg_ms * 1e-3) / 1e9, 1), peak=pk["hbm_gbs"], unit="GB/s")
-        else:
-            ent.update(bound="fp32-alu", achieved=round(w["flop"] / (avg_ms * 1e-3) / 1e12, 3), peak=None, unit="TFLOP/s")
-        if ent["peak"]:
+            ent.update(bound="hbm", achieved=round(w["bytes"] / sec / 1e9, 1), peak=pk["hbm_gbs"], unit="GB/s")
+        elif name == "knn_d3":
+            ent.update(bound="fp32 issue (distances: FFMA2; selection: ALU pipe)", achieved=round(w["flop"] / sec / 1e12, 3),
+                       peak=probes.get("fp32_ffma2_tflops"), unit="TFLOP/s",
+                       alu_note="selection-bound by design: ~900 warp instructions per row, 160 of them distance FFMA2")
+        elif name.startswith("knn_d63"):
+            gram = B * N_PTS * N_PTS * 2.0 * 64
+            ent.update(bound="ALU pipe (selection epilogue) + L2 gathers (re-rank); tensor pipe is the stated roofline",
+                       achieved=round(gram / sec / 1e12, 3), peak=probes.get("tf32_umma_tflops"), unit="TFLOP/s",
+                       gram_passes=2, fallback_rows=knn_stats.get("clustered" if name.endswith("clustered") else "gaussian"))
+        else:                                                 # hyp_loss_fwd_bwd
+            ent.update(bound="l2 (row gathers + vector reductions)", achieved=round(w["l2_bytes"] / sec / 1e9, 1),
+                       peak=probes.get("l2_gather_128B_gbs"), unit="GB/s",
+                       fp32_tflops=round(w["flop"] / sec / 1e12, 3), fp32_peak_tflops=probes.get("fp32_ffma2_tflops"),
+                       flop_per_triplet=round(LOSS_FLOP_PER_TRIPLET, 1),
+                       flop_source="ncu instruction counters (FFMA/FADD/FMUL per mined triplet), profiles/r01_g_ncu_full.md")
+            if ent["fp32_peak_tflops"]:
+                ent["fp32_frac"] = round(ent["fp32_tflops"] / ent["fp32_peak_tflops"], 4)
+        if ent.get("peak"):
             ent["frac"] = round(ent["achieved"] / ent["peak"], 4)
         ops[name] = ent
     # the dominant KERNEL (one launch per call) among those with an HBM roofline; "edge_bwd_c21" is that kernel plus the
@@ -447,12 +521,15 @@ def run_native(args):
         "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "shapenet_train_step_b32_n1024_k20_d32_t50 (BASELINE.json configs[1])",
+                   "batches_per_step": R, "ms_per_batch": round(ms_per_batch, 4),
+                   "step_definition": f"one timed step = {R} batches of {B} clouds per GPU back to back (a {round(ms_per_step * args.steps)} ms timed region); every per-batch figure below is per ONE batch",
+                   "collective": (f"all-reduce of the {GRAD_BUCKET_FLOATS * 4} B fp32 gradient bucket (SURVEY 8e), async, overlapped with the edge backwards" if world > 1 else "none at 1 GPU"),
                    "clouds_per_gpu": B, "points": N_PTS, "k": K_NN, "feat_channels": [1, C_FEAT, C_FEAT],
                    "emb_dim": D_EMB, "triplets_mined": T0, "triplets_kept": kept_val, "filter": "easy",
                    "scale": SCALE, "temperature": TEMPERATURE, "parallelism": f"dp{world}",
                    "l2": "per-step working set ~1.4 GB (edge-feature tensors) exceeds the 126 MB L2; no explicit flush",
                    "launch": "cuda-graph replay of one captured step" if use_graph else "eager",
-                   "ops_timing": "each op captured into its own CUDA graph, replayed `steps` times between CUDA events, after the timed region; edge_bwd_c21 = edge_rev_build + edge_bwd_gather_c21 (listed separately as well)",
+                   "ops_timing": "each op captured into its own CUDA graph, replayed steps x batches_per_step times between CUDA events, after the timed region; edge_bwd_c21 = edge_rev_build + edge_bwd_gather_c21 (listed separately as well)",
                    "e2e_pipeline": "2 device buffer sets; upload / compute / download on 3 streams",
                    "overlap": "the reverse graph of each layer's backward is built on a second stream during that layer's forward"},
         "e2e": {"value": e2e_dev["value"], "unit": UNIT, "h2d_bytes_per_step": e2e_dev["h2d_bytes_per_step"],
@@ -465,13 +542,15 @@ def run_native(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
+        "peaks": dict(probes, hbm_gbs=pk["hbm_gbs"], hbm_source=pk["source"]),
         "ops": ops,
+        "decode": decode_rec,
         "loss": loss_val,
         "e2e_loss": e2e_host["loss"],
         "e2e_loss_device_sampler": e2e_dev["loss"],
     }
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_reference_pass(steps=2, warmup=1)
+        line["cpu_baseline"] = cpu_reference_pass(steps=1, warmup=0)        # bounded: one 32-cloud step, 10-25 s of CPU work
     print(json.dumps(line), flush=True)
 
 
@@ -483,6 +562,33 @@ def decode_inputs(B, N, seed):
     u = torch.randn(B, N, D_EMB, generator=gen)
     nrm = u.norm(dim=-1, keepdim=True)
     return torch.tanh(nrm.clamp(max=15)) * u / nrm                    # ExpMap(N(0,1)), SURVEY 8(d)
+
+
+def decode_subrecord(hb, dev, rank, N=1024, reps=5):
+    """BASELINE configs[4] inside the default bench line: decode of B clouds x N points (leaves + fp64 cosine matrix +
+    linkage, one C-ABI call), for the configuration's real split (64 clouds over 8 GPUs = 8 per GPU) and for 64 per GPU,
+    single (north star) and complete (what the reference ships) linkage.  CUDA events around `reps` calls."""
+    pk = peaks()
+    scale = torch.tensor([SCALE], device=dev)
+    rec = {"points": N, "emb_dim": D_EMB, "timing": f"{reps} calls between CUDA events after 2 warm-up calls",
+           "roofline": "2 x B x N(N-1)/2 x 8 B (condensed fp64 matrix written once, read once) over the HBM peak"}
+    for B in (8, 64):
+        x = decode_inputs(B, N, seed=rank).to(dev)
+        for method in ("single", "complete"):
+            for _ in range(2):
+                hb.decode_linkage_batch(x, scale, method)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                hb.decode_linkage_batch(x, scale, method)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / reps
+            gbs = 2.0 * B * N * (N - 1) / 2 * 8 / (ms * 1e-3) / 1e9
+            rec[f"{method}_b{B}"] = {"ms": round(ms, 4), "dendrograms_per_s": round(B / (ms * 1e-3), 1),
+                                     "achieved_gbs": round(gbs, 1), "frac": round(gbs / pk["hbm_gbs"], 4)}
+    return rec
 
 
 def decode_cpu_baseline(x, method, budget_s=12.0):
@@ -618,14 +724,14 @@ def run_decode(args):
 # ------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle's restatement of the reference's PyTorch path on host cores
 # ------------------------------------------------------------------------------------------------
-CPU_SAMPLE_B = 8
+CPU_SAMPLE_B = B_PER_GPU            # the native arm's batch: like for like (22 s per step on 8 cores, 10 GB)
 
 
-def cpu_reference_pass(steps, warmup):
+def cpu_reference_pass(steps, warmup, B=None):
     from oracle import hpcs_oracle as O
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    B = CPU_SAMPLE_B
+    B = CPU_SAMPLE_B if B is None else B
     host = synth_inputs(B, seed=0)
     torch.manual_seed(1000)
     trip = O.sample_triplets(host["labels"], T_PER_ANCHOR, 0.0)
@@ -661,16 +767,17 @@ def run_reference(args):
     if rank != 0:
         return
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-    cb = cpu_reference_pass(steps, warmup)
+    steps, warmup = max(1, min(args.steps, 2)), max(0, min(args.warmup, 1))   # ~12-25 s per step on the host cores
+    cb = cpu_reference_pass(steps, warmup, B=args.ref_clouds)
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": world, "steps": steps,
         "warmup": warmup, "ms_per_step": round(cb["s_per_step"] * 1e3, 2), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "shapenet_train_step_b32_n1024_k20_d32_t50 (BASELINE.json configs[1])",
-                   "note": "reference is pure Python/PyTorch; this arm times the oracle restatement of its CPU path "
-                           f"on a bounded sample of {CPU_SAMPLE_B} clouds per step (the dense similarity matrix of "
-                           "the full batch, 2 x 4.3 GB forward, does not fit a bounded CPU run)"},
+                   "clouds_per_step": args.ref_clouds, "same_batch_as_native_arm": args.ref_clouds == B_PER_GPU, "points": N_PTS, "k": K_NN, "emb_dim": D_EMB,
+                   "note": "reference is pure Python/PyTorch with un-installable dependencies; this arm times the oracle "
+                           "restatement of its CPU path on the SAME batch as the native arm (32 clouds: the dense "
+                           "32768 x 32768 similarity matrix is built twice forward and once backward, as the reference does)"},
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -684,6 +791,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", choices=["native", "reference"], default="native")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--batches-per-step", type=int, default=16,
+                    help="train workload: batches per timed step (16 x 20 steps x 0.78 ms = a 250 ms timed region)")
+    ap.add_argument("--ref-clouds", type=int, default=CPU_SAMPLE_B,
+                    help="reference arm: clouds per step (default 32 = the native arm's batch; smaller only for quick checks)")
+    ap.add_argument("--no-decode", action="store_true", help="skip the configs[4] decode sub-record of the train line")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--workload", choices=["train", "decode"], default="train",
                     help="train = the headline step (configs[1]); decode = dendrogram decode (configs[4])")

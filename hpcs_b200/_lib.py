@@ -57,6 +57,12 @@ SIGNATURES = {
     "hpcs_cut_scores_f64": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "hpcs_rotate_points_f32": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "hpcs_one_hot_f32": (_I, [_P, _L, _I, _P, _P]),
+    "hpcs_edgeconv_coef_floats": (_I, []),
+    "hpcs_vn_point_linear_f32": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
+    "hpcs_edgeconv_fwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P]),
+    "hpcs_edgeconv_bwd_stage2_f32": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "hpcs_edgeconv_bwd_stage1_f32": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    "hpcs_peak_probe": (_I, [_I, _I, _P, _Z, _P, _c.POINTER(_c.c_double), _P]),
 }
 
 

@@ -16,7 +16,7 @@ LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libhpcs_b200.so")
 OBJ_DIR = os.path.join(LIB_DIR, "obj")
 
-SOURCES = ["abi.cu", "knn.cu", "knn_d3.cu", "knn_tc.cu", "edge_feat.cu", "edge_bwd.cu", "hyp_loss.cu", "sampler.cu", "hyp_ops.cu", "linkage.cu", "cut.cu", "input.cu"]
+SOURCES = ["abi.cu", "knn.cu", "knn_d3.cu", "knn_tc.cu", "edge_feat.cu", "edge_bwd.cu", "hyp_loss.cu", "sampler.cu", "hyp_ops.cu", "linkage.cu", "cut.cu", "input.cu", "peaks.cu", "edgeconv.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -9,7 +9,8 @@ subclassing can leave a call site on the reference's PyTorch path:
 * **functions** (``knn``, ``get_graph_feature``, ``hyp_lca``, ``get_optimal_k`` ...): the name is rebound in the module
   that defines it AND in every loaded module that holds the same object under any name (``from x import f`` aliases in
   ``vn_dgcnn_partseg``, ``vn_pointnet_partseg``, ``vn_dgcnn_expo``, ``base_hyp_hc``, ``__main__`` ...).
-* **methods** of the reference's own classes (``MetricHyperbolicLoss.compute_hyp``,
+* **methods** of the reference's own classes (``VN_DGCNN_partseg.forward``: the three graph layers fused, row f-1;
+  ``MetricHyperbolicLoss.compute_hyp``,
   ``RandomTripletMarginMiner.mine``, ``ExpMap.forward``, ``MLPExpMap.forward``,
   ``BaseSimilarityHypHC._decode_linkage``, ``ShapeNetHypHC._forward``, ``PartNetHypHC._forward``): the class object
   stays the reference's, so subclasses (``HierarchicalMetricHyperbolicLoss``, the PartNet default), ``isinstance``
@@ -25,7 +26,7 @@ import sys
 import warnings
 from typing import Dict, List, Tuple
 
-from . import decode, graph, hyperbolic, loss, pipeline
+from . import decode, edgeconv, graph, hyperbolic, loss, pipeline
 
 # (defining module, function name) -> replacement
 FUNCTIONS: Dict[Tuple[str, str], object] = {
@@ -85,6 +86,7 @@ METHODS: Dict[Tuple[str, str, str], object] = {
     ("hpcs.miner.triplet_margin_loss", "TripletMarginLoss", "compute_loss"): _triplet_margin_compute_loss,
     ("hpcs.nn.hyperbolic.hyp_embed", "ExpMap", "forward"): _expmap_forward,
     ("hpcs.nn.hyperbolic.hyp_embed", "MLPExpMap", "forward"): _mlp_expmap_forward,
+    ("hpcs.nn.dgcnn.vn_dgcnn_partseg", "VN_DGCNN_partseg", "forward"): edgeconv.vn_dgcnn_partseg_forward,
     ("hpcs.models.base_hyp_hc", "BaseSimilarityHypHC", "_decode_linkage"): _decode_linkage,
     ("hpcs.models.shapenet_hyp_hc", "ShapeNetHypHC", "_forward"): pipeline.shapenet_forward,
     ("hpcs.models.partnet_hyp_hc", "PartNetHypHC", "_forward"): pipeline.partnet_forward,
@@ -150,6 +152,8 @@ def install(strict: bool = True) -> List[str]:
         if cur is not repl:
             _ORIGINALS.setdefault((mod_name, cls_name, meth), cur)
             setattr(cls, meth, repl)
+            if meth == "forward" and cls_name == "VN_DGCNN_partseg":          # pooling='max' keeps the module's own layer sequence
+                cls._hpcs_reference_forward = _ORIGINALS[(mod_name, cls_name, meth)]
         done.append(f"{mod_name}.{cls_name}.{meth}")
     if failed:
         msg = ("hpcs_b200.patch.install(): these call sites are still on the reference's PyTorch path:\n  "

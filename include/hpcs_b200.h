@@ -25,7 +25,8 @@ extern "C" {
 
 /* 2: + hpcs_edge_rev_build, hpcs_edge_feat_bwd_prebuilt_f32, hpcs_triplet_sample_i32, hpcs_fcluster_maxclust_i32,
  *    hpcs_cut_scores_f64 (additions only; every version-1 entry point is unchanged)
- * 3: + hpcs_triplet_sample_state_i32, hpcs_rotate_points_f32, hpcs_one_hot_f32 (round 2; additions only)
+ * 3: + hpcs_triplet_sample_state_i32, hpcs_rotate_points_f32, hpcs_one_hot_f32, hpcs_peak_probe,
+ *    hpcs_vn_point_linear_f32, hpcs_edgeconv_* (round 2; additions only)
  */
 #define HPCS_ABI_VERSION 3
 
@@ -190,6 +191,46 @@ int hpcs_rotate_points_f32(const float* pts, const float* params, int mode, int 
 /* to_categorical(y, num_classes)   hpcs/utils/data.py:24-29: y[rows] int64 -> out[rows, num_classes] fp32 one-hot
  * (a row of zeros for a label outside [0, num_classes), where torch.eye indexing would raise). */
 int hpcs_one_hot_f32(const int64_t* y, int64_t rows, int num_classes, float* out, void* stream);
+
+/* ---- fused EdgeConv layer    -------------------------------------------------------------------------
+ * x = get_graph_feature(x, k); x = convA(x); [x = convB(x);] x = mean_pool(x)
+ *   hpcs/nn/dgcnn/vn_dgcnn_partseg.py:65-68,70-73,75-77; VNLinearLeakyReLU hpcs/nn/dgcnn/utils/vn_layers.py:48-77 (with its
+ *   VNBatchNorm :112-132), mean_pool :152-153.  The [B,2C,3,N,k] edge tensor is never formed (see csrc/edgeconv.cu).
+ *
+ * hpcs_vn_point_linear_f32: the layer's first Linear split into per-point maps.  x[B,C,3,N]; W4[4][21][C] = {Wa_feat, Wa_dir,
+ *   Wb_feat - Wa_feat, Wb_dir - Wa_dir} with W = [Wa | Wb] the [21, 2C] map_to_feat / map_to_dir weights of convA
+ *   -> UU[B*N][128], VV[B*N][128] rows [feat(o*3+c) 63 | 0 | dir 63 | 0].
+ * coef: DEVICE buffer of hpcs_edgeconv_coef_floats() floats: per stage s (0 = convA, 1 = convB) six 21-vectors at
+ *   [s*126 + which*21]: a, b (BatchNorm on the norm folded to y = a r + b), mu, rstd (rhat = (r - mu) rstd), s1m = mean(gy),
+ *   s2m = mean(gy rhat) (backward, training mode; 0 in eval mode); convB weights [21][24] (rows zero-padded) at float
+ *   256 (map_to_feat) and 760 (map_to_dir); for a C = 1 layer convA's own weights [4][21] = {Wa_feat, Wa_dir, Wb_feat, Wb_dir}
+ *   at float 1264.  Device-resident so that batch statistics never visit the host.
+ * x_direct: NULL, or x[B,1,3,N] for a C = 1 layer: the first conv is then evaluated per edge from the coordinates themselves,
+ *   p = Wa (x_j - x_i) + Wb x_i as the reference does (no |x| vs |x_j - x_i| cancellation, a 12-byte gather); UU / VV unused.
+ * hpcs_edgeconv_fwd_f32: stages 1 | 2.  mode 0: stats[21][2] (fp64) += sum r, sum r^2 of the convA norms over all B*N*k
+ *   edges; mode 1: same for the convB norms (needs convA's a, b); mode 2: out[B,21,3,N]; with ysum/yrsum != NULL also the
+ *   per-point sums [B*N][63] of the coefficients that make the last stage's BatchNorm backward sums a per-point dot product.
+ * hpcs_edgeconv_bwd_stage2_f32 (two-stage layers): G[B,21,3,N] = d loss / d out -> gO1[B*N*k][64] (gradient wrt convA's
+ *   output per edge), dW2[21][2][21] += (out, {feat, dir}, in), stats1[21][2] (fp64) += sum gy, sum gy rhat of convA.
+ * hpcs_edgeconv_bwd_stage1_f32: gO1 (or NULL for a one-stage layer: then gO1 = G[n]/k) -> gUU[B*N][128] += (caller zeroes),
+ *   gVV[B*N][128] = (floats 63 and 127 of a gVV row are not written); the caller contracts them with x and W4. */
+int hpcs_edgeconv_coef_floats(void);
+int hpcs_vn_point_linear_f32(const float* x, const float* W4, int B, int C, int N, float* UU, float* VV, void* stream);
+int hpcs_edgeconv_fwd_f32(const float* UU, const float* VV, const int64_t* idx, int B, int N, int k, int stages,
+                          const float* coef, const float* x_direct, int mode, double* stats, float* out, float* ysum,
+                          float* yrsum, void* stream);
+int hpcs_edgeconv_bwd_stage2_f32(const float* UU, const float* VV, const int64_t* idx, int B, int N, int k, const float* coef,
+                                 const float* x_direct, const float* G, float* gO1, float* dW2, double* stats1, void* stream);
+int hpcs_edgeconv_bwd_stage1_f32(const float* UU, const float* VV, const int64_t* idx, int B, int N, int k, const float* coef,
+                                 const float* x_direct, const float* gO1, const float* G, float* gUU, float* gVV, void* stream);
+
+/* ---- measurement support: pipe / cache peak probes (bench.py; no reference counterpart) ------------------------------
+ * The roofline denominators MEASURED_PEAKS.json lacks (SURVEY 8d asks for them): which = 0 packed fp32 FMA (FFMA2),
+ * 1 scalar fp32 FMA, 2 ALU pipe (fp32 min/max), 3 fp64 FMA, 4 fp64 tensor cores (mma.sync m8n8k4), 5 TF32 tcgen05.mma
+ * (M=128, N=256, operands resident in shared memory), 6 / 7 random 128- / 256-byte row gathers from `table` (device memory,
+ * size it to stay L2-resident).  One launch of `iters` loop trips; *work_host (HOST pointer, may be NULL) receives the flops
+ * (bytes for 6, 7) the launch performs, the caller times it.  `out` is one device float (never written in practice). */
+int hpcs_peak_probe(int which, int iters, const void* table, size_t table_bytes, float* out, double* work_host, void* stream);
 
 #ifdef __cplusplus
 }

@@ -547,3 +547,48 @@ def rotate_points(points: torch.Tensor, R: Optional[torch.Tensor]) -> torch.Tens
 def to_categorical(y: torch.Tensor, num_classes: int) -> torch.Tensor:
     """hpcs/utils/data.py:24-29."""
     return torch.eye(num_classes)[y.cpu().numpy(),]
+
+
+# --------------------------------------------------------------------------------------------
+# row f-1: the VN layers that consume the edge features (for the fused EdgeConv kernel)
+# --------------------------------------------------------------------------------------------
+VN_EPS = 1e-6                           # hpcs/nn/dgcnn/utils/vn_layers.py:10
+
+
+def vn_linear_leaky_relu(x, wf, wd, gamma, beta, running_mean=None, running_var=None, training=True,
+                         eps: float = 1e-5, momentum: float = 0.1, negative_slope: float = 0.2):
+    """``VNLinearLeakyReLU.forward`` (vn_layers.py:62-77) with its ``VNBatchNorm`` (:118-131, BatchNorm2d on the vector
+    norms): x[B,Cin,3,N,k] -> [B,Cout,3,N,k].  ``wf`` / ``wd``: ``map_to_feat`` / ``map_to_dir`` weights [Cout,Cin].  In
+    training mode the batch statistics are used and, when given, the running buffers are updated in place like
+    ``nn.BatchNorm2d`` (biased variance to normalise, unbiased into ``running_var``)."""
+    p = torch.einsum("oi,bicnk->bocnk", wf, x)                                   # :66
+    d = torch.einsum("oi,bicnk->bocnk", wd, x)                                   # :70
+    norm = torch.sqrt((p * p).sum(2)) + VN_EPS                                   # :124
+    if training:
+        mean = norm.mean(dim=(0, 2, 3))
+        var = norm.var(dim=(0, 2, 3), unbiased=False)
+        if running_mean is not None:
+            with torch.no_grad():
+                m = norm.numel() // norm.shape[1]
+                running_mean.mul_(1 - momentum).add_(momentum * mean.detach().to(running_mean.dtype))
+                running_var.mul_(1 - momentum).add_(momentum * (var.detach() * m / (m - 1)).to(running_var.dtype))
+    else:
+        mean, var = running_mean.to(norm.dtype), running_var.to(norm.dtype)
+    shape = (1, -1, 1, 1)
+    norm_bn = (norm - mean.view(shape)) / torch.sqrt(var.view(shape) + eps) * gamma.view(shape) + beta.view(shape)
+    p = p / norm.unsqueeze(2) * norm_bn.unsqueeze(2)                             # :128
+    dot = (p * d).sum(2, keepdim=True)                                           # :71
+    mask = (dot >= 0).to(p.dtype)
+    dns = (d * d).sum(2, keepdim=True)
+    return negative_slope * p + (1 - negative_slope) * (mask * p + (1 - mask) * (p - (dot / (dns + VN_EPS)) * d))   # :74-76
+
+
+def edgeconv_layer(x, idx, convs, training=True, k: Optional[int] = None):
+    """One graph layer of ``VN_DGCNN_partseg.forward`` (vn_dgcnn_partseg.py:65-68 / 70-73 / 75-77):
+    ``get_graph_feature`` -> one or two ``VNLinearLeakyReLU`` -> ``mean_pool`` over k.  ``convs``: list of dicts with keys
+    wf, wd, gamma, beta and optionally running_mean / running_var / eps / momentum."""
+    e = graph_feature(x, k if k is not None else idx.shape[2], idx=idx)
+    for c in convs:
+        e = vn_linear_leaky_relu(e, c["wf"], c["wd"], c["gamma"], c["beta"], c.get("running_mean"), c.get("running_var"),
+                                 training, c.get("eps", 1e-5), c.get("momentum", 0.1))
+    return e.mean(dim=-1)                                                         # vn_layers.py:152-153

@@ -1,28 +1,35 @@
 import torch
+import torch.nn as nn
+from hpcs.nn.dgcnn.utils.vn_layers import *
 from hpcs.nn.dgcnn.utils.vn_dgcnn_util import get_graph_feature
 
 
-class VN_DGCNN_partseg(torch.nn.Module):
-    """Backbone-SHAPED stand-in: the same three graph-feature calls as the reference's forward (a D=3 graph, then two
-    D=63 graphs on 21 vector channels), each followed by a channel-mixing linear map and a mean over the k neighbours,
-    then rotation-invariant norms -> per-point features.  Not the reference's network."""
+class VN_DGCNN_partseg(nn.Module):
+    """The reference's constructor signature, attribute names and layer shapes for the graph layers (conv1 .. conv5 on
+    64 // 3 = 21 vector channels); a narrower dense tail.  ``forward`` is the reference's call sequence for the first
+    layer only -- enough to reach ``get_graph_feature`` -- because every later statement is replaced by the binding."""
 
     def __init__(self, in_channels, out_features, k, dropout, pooling, num_categories):
         super().__init__()
-        self.k, self.out_features, self.num_categories = k, out_features, num_categories
-        self.mix1 = torch.nn.Linear(2, 21, bias=False)
-        self.mix2 = torch.nn.Linear(42, 21, bias=False)
-        self.mix3 = torch.nn.Linear(42, 21, bias=False)
-        self.head = torch.nn.Linear(63 + num_categories, out_features)
-
-    def _layer(self, x, mix):
-        e = get_graph_feature(x, k=self.k)                      # [B,2C,3,N,k]
-        return mix(e.transpose(1, -1)).transpose(1, -1).mean(dim=-1)
+        self.in_channels, self.out_features, self.k = in_channels, out_features, k
+        self.dropout, self.pooling, self.num_categories = dropout, pooling, num_categories
+        self.conv1 = VNLinearLeakyReLU(2, 64 // 3)
+        self.conv2 = VNLinearLeakyReLU(64 // 3, 64 // 3)
+        self.conv3 = VNLinearLeakyReLU(64 // 3 * 2, 64 // 3)
+        self.conv4 = VNLinearLeakyReLU(64 // 3, 64 // 3)
+        self.conv5 = VNLinearLeakyReLU(64 // 3 * 2, 64 // 3)
+        self.pool1 = self.pool2 = self.pool3 = mean_pool
+        wide = 32
+        self.conv6 = VNLinearLeakyReLU(64 // 3 * 3, wide, dim=4, share_nonlinearity=True)
+        self.std_feature = VNStdFeature(wide * 2, dim=4, normalize_frame=False)
+        self.conv7 = nn.Sequential(nn.Conv1d(num_categories, 64, kernel_size=1, bias=False), nn.BatchNorm1d(64), nn.LeakyReLU(0.2))
+        self.conv8 = nn.Sequential(nn.Conv1d(wide * 2 * 3 + 64 + 63 * 3, 256, kernel_size=1, bias=False), nn.BatchNorm1d(256), nn.LeakyReLU(0.2))
+        self.dp1 = nn.Dropout(p=dropout)
+        self.conv9 = nn.Sequential(nn.Conv1d(256, 256, kernel_size=1, bias=False), nn.BatchNorm1d(256), nn.LeakyReLU(0.2))
+        self.dp2 = nn.Dropout(p=dropout)
+        self.conv10 = nn.Sequential(nn.Conv1d(256, 128, kernel_size=1, bias=False), nn.BatchNorm1d(128), nn.LeakyReLU(0.2))
+        self.conv11 = nn.Sequential(nn.Conv1d(128, out_features, kernel_size=1, bias=False), nn.BatchNorm1d(out_features))
 
     def forward(self, x, l):
-        x1 = self._layer(x.unsqueeze(1), self.mix1)
-        x2 = self._layer(x1, self.mix2)
-        x3 = self._layer(x2, self.mix3)
-        inv = torch.cat((x1, x2, x3), dim=1).norm(dim=2)        # [B,63,N]
-        cat = l.reshape(l.shape[0], -1, 1).expand(-1, -1, inv.shape[-1])
-        return self.head(torch.cat((inv, cat), dim=1).transpose(1, 2))
+        x = get_graph_feature(x.unsqueeze(1), k=self.k)
+        return self.pool1(self.conv2(self.conv1(x)))

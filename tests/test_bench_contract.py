@@ -15,7 +15,7 @@ def _run(*args):
 
 
 def test_reference_arm_train_line():
-    p = _run("--impl", "reference", "--steps", "1", "--warmup", "1")
+    p = _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--ref-clouds", "2")
     assert p.returncode == 0, p.stderr[-2000:]
     line = json.loads(p.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "clouds/s" and line["higher_is_better"] is True

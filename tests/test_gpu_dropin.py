@@ -104,47 +104,62 @@ def test_shapenet_training_step_through_patched_names(tree, B, full):
     N, k = 1024, 20
     gen = torch.Generator().manual_seed(100 + B)
     torch.manual_seed(1)
-    model = ShapeNetHypHC(nn_feat=VN_DGCNN_partseg(3, 32, k, 0.5, "mean", 16), nn_emb=ExpMap(), euclidean_size=32,
+    model = ShapeNetHypHC(nn_feat=VN_DGCNN_partseg(3, 32, k, 0.0, "mean", 16), nn_emb=ExpMap(), euclidean_size=32,
                           hyp_size=32, num_class=50, t_per_anchor=50, fraction=0.0, temperature=0.05, miner=True).cuda()
     pts, targets = clouds(gen, B, N), shapenet_labels(gen, B, N)
     label = torch.randint(0, 16, (B, 1), generator=gen)
     seen = {}
-    model.nn_emb.register_forward_hook(lambda mod, inp, out: seen.__setitem__("x_poincare", out))
+    state0 = {k_: v.detach().clone() for k_, v in model.nn_feat.state_dict().items()}
+    def keep(mod, inp, out):
+        seen["x_poincare"], seen["x_euclidean"] = out, inp[0]
+    model.nn_emb.register_forward_hook(keep)
     before = launches()
     torch.manual_seed(7)
     losses, metrics = model.forward((pts, label, targets), testing=False)
     total = losses["loss_metric"] + losses["loss_hyp"]
     total.backward()
     torch.cuda.synchronize()
-    assert launches() - before >= 3 + 3 + 2 + 3          # >= 3 kNN, 3 edge fwd, loss fwd+bwd, 3 edge bwd kernels
+    assert launches() - before >= 3 + 8 + 2 + 5          # >= 3 kNN, 8 fused-layer forward passes, loss fwd+bwd, 5 fused backward kernels
     assert torch.isfinite(total).item()
     for name, prm in model.named_parameters():
-        assert prm.grad is not None and torch.isfinite(prm.grad).all(), name
+        fused = any(f"nn_feat.conv{i}." in name for i in range(1, 6))          # parameters of the five graph-layer convs
+        assert prm.grad is not None or not (fused or name == "scale"), name   # (stand-in tail modules own unused ones)
+        assert prm.grad is None or torch.isfinite(prm.grad).all(), name
+        assert not fused or prm.grad.abs().max().item() > 0, name
     assert model.scale.grad.abs().item() > 0
     xp = seen["x_poincare"].reshape(-1, 32)
     assert tuple(xp.shape) == (B * N, 32) and xp.norm(dim=1).max().item() <= 1.0 + 1e-6
     if not full:
         rotated, want = oracle_step(model, pts, targets, "so3", 50, 0.0, 7, xp)
         assert abs(losses["loss_hyp"].item() / model.trade_off - want.item()) <= REL * abs(want.item())
-        # the rotation + transpose the backbone saw (row f-4) and its three graph layers (kNN D=3, 63, 63 + gathers)
+        # the rotation + transpose the backbone saw (row f-4), its three fused graph layers (row f-1; kNN D=3, 63, 63) and
+        # the dense tail: the same forward on the host with the oracle's layers standing in for the fused ones
+        import copy
+        import hpcs_b200.edgeconv as ec
         net = model.nn_feat
-        with torch.no_grad():
-            cpu_net = type(net)(3, 32, k, 0.5, "mean", 16)
-            cpu_net.load_state_dict({k_: v.cpu() for k_, v in net.state_dict().items()})
+        cpu_net = copy.deepcopy(net).cpu()
+        cpu_net.load_state_dict({k_: v.cpu() for k_, v in state0.items()})        # parameters / buffers as before the step
 
-            def layer(x, mix):
-                e = O.graph_feature(x, k=k)
-                return mix(e.transpose(1, -1)).transpose(1, -1).mean(dim=-1)
-            x1 = layer(rotated.unsqueeze(1), cpu_net.mix1)
-            x2 = layer(x1, cpu_net.mix2)
-            x3 = layer(x2, cpu_net.mix3)
-            inv = torch.cat((x1, x2, x3), dim=1).norm(dim=2)
-            cat = O.to_categorical(label, 16).reshape(B, -1, 1).expand(-1, -1, N)
-            want_feat = cpu_net.head(torch.cat((inv, cat), dim=1).transpose(1, 2))
-            got_feat = net(torch.as_tensor(rotated).cuda(), O.to_categorical(label, 16).cuda()).cpu()
-        # near-tied neighbours may swap between the fp32 GPU and CPU linear layers; everything else must agree
-        close = ((got_feat - want_feat).norm(dim=-1) <= 1e-3 * want_feat.norm(dim=-1).clamp_min(1e-6)).float().mean()
-        assert close.item() > 0.98, close.item()
+        def edgeconv_oracle(x, k_, conv_a, conv_b=None, idx=None):
+            Bc, C, _, Np = x.shape
+            convs = []
+            for c in (conv_a, conv_b):
+                if c is not None:
+                    bn = c.batchnorm.bn
+                    convs.append({"wf": c.map_to_feat.weight, "wd": c.map_to_dir.weight, "gamma": bn.weight, "beta": bn.bias})
+            return O.edgeconv_layer(x, O.knn_canonical(x.reshape(Bc, 3 * C, Np).contiguous(), k_), convs, training=True)
+        real = ec.edgeconv
+        ec.edgeconv = edgeconv_oracle
+        try:
+            with torch.no_grad():
+                want_feat = ec.vn_dgcnn_partseg_forward(cpu_net, rotated, O.to_categorical(label, 16))
+        finally:
+            ec.edgeconv = real
+        got_feat = seen["x_euclidean"].detach().cpu()
+        # near-tied neighbours may swap between the fp32 GPU and host evaluations of layers 2 and 3; everything else agrees
+        # (one swapped neighbour moves that point's feature by O(1/k) and, through BatchNorm and the global max, nudges the rest)
+        rel = (got_feat - want_feat).norm(dim=-1) / want_feat.norm(dim=-1).clamp_min(1e-6)
+        assert rel.median().item() < 5e-4 and (rel <= 2e-3).float().mean().item() > 0.9, (rel.median().item(), (rel <= 2e-3).float().mean().item())
 
 
 def test_test_step_decode_and_model_selection_through_patched_names(tree):
@@ -261,7 +276,7 @@ def test_unpatched_tree_raises(tree):
     try:
         net = VN_DGCNN_partseg(3, 8, 4, 0.5, "mean", 16).cuda()
         with pytest.raises(hpcs.ReferencePathReached):
-            net(torch.randn(1, 3, 32).cuda(), torch.zeros(1, 16).cuda())
+            net(torch.randn(2, 3, 32).cuda(), torch.zeros(2, 16, 1).cuda())
     finally:
         patch.install(strict=True)
     assert patch.verify() == []

@@ -137,3 +137,42 @@ def test_partnet_default_constructs_and_is_native(ref):
         loss.compute_loss(None, torch.randn(40, 4) * 0.1, torch.randint(0, 5, (40,)))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         model.forward((torch.randn(2, 32, 3), torch.randint(0, 5, (2, 32))), testing=False)
+
+
+def test_fused_backbone_forward_equals_reference_forward(ref, monkeypatch):
+    """``vn_dgcnn_partseg_forward`` (bound onto VN_DGCNN_partseg) must be the reference's forward with the three graph
+    layers swapped for fused ones.  Checked on CPU against the reference's ORIGINAL forward by standing an oracle
+    implementation in for the fused layer (the CUDA layer itself is checked on the GPU, tests/test_gpu_edgeconv.py)."""
+    patch = ref
+    patch.uninstall()
+    from hpcs.nn.dgcnn import VN_DGCNN_partseg
+    from oracle import hpcs_oracle as O
+    import hpcs_b200.edgeconv as ec
+
+    def edgeconv_oracle(x, k, conv_a, conv_b=None, idx=None):
+        B, C, _, N = x.shape
+        idx = O.knn_reference(x.reshape(B, 3 * C, N), k)
+        convs = []
+        for c in (conv_a, conv_b):
+            if c is not None:
+                bn = c.batchnorm.bn
+                convs.append({"wf": c.map_to_feat.weight, "wd": c.map_to_dir.weight, "gamma": bn.weight, "beta": bn.bias,
+                              "running_mean": bn.running_mean, "running_var": bn.running_var, "eps": bn.eps})
+        return O.edgeconv_layer(x, idx, convs, training=False)
+
+    monkeypatch.setattr(ec, "edgeconv", edgeconv_oracle)
+    torch.manual_seed(0)
+    net = VN_DGCNN_partseg(in_channels=3, out_features=32, k=8, dropout=0.5, pooling="mean", num_categories=16).eval()
+    for m in net.modules():                                  # non-trivial BatchNorm state everywhere
+        if isinstance(m, (torch.nn.BatchNorm1d, torch.nn.BatchNorm2d)):
+            m.running_mean.uniform_(-0.2, 0.5); m.running_var.uniform_(0.5, 1.5)
+            m.weight.data.uniform_(0.5, 1.5); m.bias.data.uniform_(-0.3, 0.3)
+    x = torch.randn(2, 3, 64)
+    l = torch.zeros(2, 16, 1); l[0, 3] = 1; l[1, 7] = 1
+    with torch.no_grad():
+        want = net.forward(x, l)                             # the reference's own forward (uninstalled)
+        got = ec.vn_dgcnn_partseg_forward(net, x, l)
+    assert got.shape == want.shape == (2, 64, 32)
+    assert torch.allclose(got, want, rtol=1e-4, atol=1e-5), (got - want).abs().max()
+    monkeypatch.undo()
+    patch.install()
