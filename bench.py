@@ -463,6 +463,7 @@ def run_native(args):
     import peaks as peak_probes
     probes = peak_probes.measure(dev)
     decode_rec = decode_subrecord(hb, dev, rank) if not args.no_decode else None
+    edgeconv_rec = edgeconv_subrecord(hb, dev, B, rank) if not args.no_decode else None
     barrier()
     sampler.region = "e2e"
     e2e_dev = run_e2e("device")
@@ -545,6 +546,7 @@ def run_native(args):
         "peaks": dict(probes, hbm_gbs=pk["hbm_gbs"], hbm_source=pk["source"]),
         "ops": ops,
         "decode": decode_rec,
+        "edgeconv": edgeconv_rec,
         "loss": loss_val,
         "e2e_loss": e2e_host["loss"],
         "e2e_loss_device_sampler": e2e_dev["loss"],
@@ -588,6 +590,85 @@ def decode_subrecord(hb, dev, rank, N=1024, reps=5):
             gbs = 2.0 * B * N * (N - 1) / 2 * 8 / (ms * 1e-3) / 1e9
             rec[f"{method}_b{B}"] = {"ms": round(ms, 4), "dendrograms_per_s": round(B / (ms * 1e-3), 1),
                                      "achieved_gbs": round(gbs, 1), "frac": round(gbs / pk["hbm_gbs"], 4)}
+    return rec
+
+
+def edgeconv_subrecord(hb, dev, B, rank, reps=5):
+    """Row f-1 inside the default bench line: the three graph layers of VN_DGCNN_partseg at the bench shape, fused
+    (hpcs_b200.edgeconv: training-mode forward with its BatchNorm statistics passes, and forward+backward wrt the input and
+    every parameter) against the unfused composition on the same GPU (the native edge-feature kernel followed by the same
+    VN arithmetic as plain PyTorch ops over the [B,2C,3,N,k] tensor, which is what the reference's modules execute)."""
+    from hpcs_b200.edgeconv import edgeconv
+
+    class Conv(torch.nn.Module):                         # attribute layout of the reference's VNLinearLeakyReLU
+        def __init__(self, cin):
+            super().__init__()
+            self.negative_slope = 0.2
+            self.map_to_feat = torch.nn.Linear(cin, 21, bias=False)
+            self.map_to_dir = torch.nn.Linear(cin, 21, bias=False)
+            self.batchnorm = torch.nn.Module()
+            self.batchnorm.bn = torch.nn.BatchNorm2d(21)
+
+    def vn_torch(e, c):                                  # VNLinearLeakyReLU + VNBatchNorm (training mode) in plain PyTorch
+        bn = c.batchnorm.bn
+        p = c.map_to_feat(e.transpose(1, -1)).transpose(1, -1)
+        d = c.map_to_dir(e.transpose(1, -1)).transpose(1, -1)
+        norm = torch.norm(p, dim=2) + 1e-6
+        p = p / norm.unsqueeze(2) * torch.nn.functional.batch_norm(norm, None, None, bn.weight, bn.bias, True, 0.1, bn.eps).unsqueeze(2)
+        dot = (p * d).sum(2, keepdim=True)
+        mask = (dot >= 0).float()
+        return 0.2 * p + 0.8 * (mask * p + (1 - mask) * (p - (dot / ((d * d).sum(2, keepdim=True) + 1e-6)) * d))
+
+    def timed(fn, n):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    gen = torch.Generator(device=dev).manual_seed(50 + rank)
+    torch.manual_seed(50 + rank)
+    rec = {"timing": f"{reps} calls between CUDA events after 2 warm-up calls (eager launches, host overhead included)",
+           "unfused": "hpcs_b200.get_graph_feature + VNLinearLeakyReLU arithmetic as PyTorch ops (training-mode BatchNorm), fwd+bwd"}
+    tot_f = tot_u = 0.0
+    for tag, C, two in (("layer1_c1_conv1_conv2", 1, True), ("layer2_c21_conv3_conv4", C_FEAT, True), ("layer3_c21_conv5", C_FEAT, False)):
+        convs = [Conv(2 * C).to(dev).train()] + ([Conv(21).to(dev).train()] if two else [])
+        params = [p for c in convs for p in c.parameters()]
+        x = torch.randn(B, C, 3, N_PTS, device=dev, generator=gen)
+        gout = torch.randn(B, 21, 3, N_PTS, device=dev, generator=gen)
+        idx = hb.knn(x.view(B, 3 * C, N_PTS), K_NN)
+
+        def fused(bwd=True):
+            xr = x.detach().requires_grad_(bwd)
+            y = edgeconv(xr, K_NN, convs[0], convs[1] if two else None, idx=idx)
+            if bwd:
+                torch.autograd.grad((y * gout).sum(), [xr] + params)
+
+        def unfused():
+            xr = x.detach().requires_grad_(True)
+            e = hb.get_graph_feature(xr, K_NN, idx=idx)
+            for c in convs:
+                e = vn_torch(e, c)
+            torch.autograd.grad((e.mean(dim=-1) * gout).sum(), [xr] + params)
+        with torch.no_grad():
+            fwd_ms = timed(lambda: fused(False), reps)
+        torch.cuda.reset_peak_memory_stats(dev)
+        f_ms = timed(fused, reps)
+        f_mem = torch.cuda.max_memory_allocated(dev)
+        torch.cuda.reset_peak_memory_stats(dev)
+        u_ms = timed(unfused, 2)
+        u_mem = torch.cuda.max_memory_allocated(dev)
+        tot_f, tot_u = tot_f + f_ms, tot_u + u_ms
+        rec[tag] = {"fused_fwd_train_ms": round(fwd_ms, 4), "fused_fwd_bwd_ms": round(f_ms, 4), "unfused_fwd_bwd_ms": round(u_ms, 4),
+                    "speedup": round(u_ms / f_ms, 2), "fused_peak_mem_mb": round(f_mem / 1e6), "unfused_peak_mem_mb": round(u_mem / 1e6)}
+        del convs, params, x, gout, idx
+        torch.cuda.empty_cache()
+    rec["three_layers_fwd_bwd_ms"] = {"fused": round(tot_f, 4), "unfused": round(tot_u, 4), "speedup": round(tot_u / tot_f, 2)}
     return rec
 
 
@@ -795,7 +876,7 @@ def main():
                     help="train workload: batches per timed step (16 x 20 steps x 0.78 ms = a 250 ms timed region)")
     ap.add_argument("--ref-clouds", type=int, default=CPU_SAMPLE_B,
                     help="reference arm: clouds per step (default 32 = the native arm's batch; smaller only for quick checks)")
-    ap.add_argument("--no-decode", action="store_true", help="skip the configs[4] decode sub-record of the train line")
+    ap.add_argument("--no-decode", action="store_true", help="skip the sub-records of the train line (configs[4] decode, fused EdgeConv layers)")
     ap.add_argument("--no-graph", action="store_true", help="launch eagerly instead of replaying a CUDA graph")
     ap.add_argument("--workload", choices=["train", "decode"], default="train",
                     help="train = the headline step (configs[1]); decode = dendrogram decode (configs[4])")

@@ -120,9 +120,14 @@ struct ChanFwd {
 // One vector channel of VNLinearLeakyReLU after the Linear maps (vn_layers.py:66-77, 124-130):
 //   r = |p| + EPS;  q = p / r * bn(r);  dot = q.d;  o = q                       if dot >= 0
 //                                                    o = q - 0.8 dot/(|d|^2+EPS) d  otherwise
+__device__ __forceinline__ float vnorm(float p0, float p1, float p2) {
+    const float r2 = fmaf(p2, p2, fmaf(p1, p1, p0 * p0));
+    return r2 > 0.f ? r2 * rsqrtf(r2) : 0.f;              // MUFU.RSQ (2 ulp): no IEEE-sqrt slow path in the inner loops
+}
+
 __device__ __forceinline__ ChanFwd chan_fwd(float p0, float p1, float p2, float d0, float d1, float d2, float a, float b) {
     ChanFwd f;
-    f.nr = sqrtf(fmaf(p2, p2, fmaf(p1, p1, p0 * p0)));
+    f.nr = vnorm(p0, p1, p2);
     f.r = f.nr + kVnEps;
     f.s = a + __fdividef(b, f.r);
     f.q0 = p0 * f.s; f.q1 = p1 * f.s; f.q2 = p2 * f.s;
@@ -228,20 +233,28 @@ __global__ void __launch_bounds__(256) vn_point_linear_kernel(const float* __res
     }
 }
 
-// ---- per-edge helpers -------------------------------------------------------------------------------------------------
+// ---- per-edge machinery ---------------------------------------------------------------------------------------------
+// One thread per edge; a tile is P consecutive points x their k edges (P*k <= kMaxTileThreads), two CTAs per SM.
+// Shared memory of a CTA: packed coefficients | U rows of the tile's edges (cp.async, 528-byte stride: conflict-free 128-bit
+// reads of a thread's own row) | V rows of the tile's points | upstream-gradient rows (backward) | the k-reduction buffer.
+constexpr int kMaxTileThreads = 160;
+constexpr int kRowS = 132;              // shared-memory stride (floats) of a staged 128-float row
+constexpr int kGrp = 7;                 // channels per k-reduction round in the forward (21 floats per thread)
+constexpr int kRedS = 25;               // stride of the reduction buffer: up to 24 floats per thread and round, odd
+
 struct EdgeId {
     long long g;        // global point index b*N + n of the centre
     long long m;        // global point index of the neighbour
     long long b;        // cloud
     int n, mloc;        // centre / neighbour index inside the cloud
-    int pl;             // point slot inside the tile
+    int pl, j;          // point slot inside the tile, edge slot of the point
     bool valid;
 };
 
 __device__ __forceinline__ EdgeId edge_of(long long tile, int P, int k, long long BN, int N, const long long* __restrict__ idx) {
     EdgeId e;
     e.pl = threadIdx.x / k;
-    const int j = threadIdx.x - e.pl * k;
+    e.j = threadIdx.x - e.pl * k;
     e.g = tile * P + e.pl;
     e.valid = e.pl < P && e.g < BN;
     e.m = e.b = 0;
@@ -249,61 +262,126 @@ __device__ __forceinline__ EdgeId edge_of(long long tile, int P, int k, long lon
     if (e.valid) {
         e.b = e.g / N;
         e.n = (int)(e.g - e.b * N);
-        e.mloc = (int)idx[e.g * k + j];
+        e.mloc = (int)idx[e.g * k + e.j];
         e.m = e.b * N + e.mloc;
+    } else {
+        e.pl = 0;
     }
     return e;
 }
 
-// C = 1 layers: p = Wa (x_j - x_i) + Wb x_i straight from the coordinates x[B,1,3,N]
-__device__ __forceinline__ void load_pd_direct(const float* __restrict__ x, const float* ws, int N, const EdgeId& e, float (&P)[64],
-                                               float (&D)[64]) {
-    const float* xb = x + e.b * 3 * N;
-    float xi[3], dx[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        xi[c] = __ldg(xb + (size_t)c * N + e.n);
-        dx[c] = __ldg(xb + (size_t)c * N + e.mloc) - xi[c];
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+
+struct TileSmem {
+    float* ws;          // [kWFloats]
+    float* urows;       // [T][kRowS]   (not used by C = 1 layers)
+    float* vrows;       // [P][kRowS]
+    float* gs;          // [P][64] upstream gradient rows (backward)
+    float* red;         // [T][kRedS]
+    float* acc;         // backward accumulators
+};
+
+// urows: per-thread 528-byte slots (U rows; the backward kernels also stage their per-edge gradient rows there, so they carve
+// them for C = 1 layers too); vrows only when U/V rows are used; gs for the backward; red when the kernel reduces over k
+__device__ __forceinline__ TileSmem carve(float* base, int T, int P, bool urows, bool vrows, bool gs, bool red) {
+    TileSmem s;
+    s.ws = base;
+    s.urows = s.ws + kWFloats;
+    s.vrows = s.urows + (urows ? T * kRowS : 0);
+    s.gs = s.vrows + (vrows ? P * kRowS : 0);
+    s.red = s.gs + (gs ? P * 64 : 0);
+    s.acc = s.red + (red ? T * kRedS : 0);
+    return s;
+}
+
+static size_t tile_smem_bytes(int T, int P, bool urows, bool vrows, bool gs, bool red, int acc_floats) {
+    size_t f = kWFloats + (urows ? (size_t)T * kRowS : 0) + (vrows ? (size_t)P * kRowS : 0) + (gs ? (size_t)P * 64 : 0) +
+               (red ? (size_t)T * kRedS : 0) + acc_floats;
+    return f * sizeof(float);
+}
+
+// Stage the tile's inputs: every thread copies the 512-byte U row of its neighbour, the V rows of the tile's points are copied
+// cooperatively; threads without an edge zero their row so that everything downstream stays finite.
+template <bool DIRECT>
+__device__ __forceinline__ void stage_tile(const TileSmem& S, const float* __restrict__ UU, const float* __restrict__ VV, const EdgeId& e,
+                                           long long tile, int P, long long BN) {
+    if (DIRECT) return;
+    // warp-cooperative: 8 lanes copy one 128-byte line of one row, so an instruction touches 4 cache lines instead of the 32 a
+    // thread-per-row copy would (the L1 tag stage, not L2 bandwidth, limits a 32-line gather instruction)
+    const int lane = threadIdx.x & 31;
+    const long long mrow = e.valid ? e.m : -1;
+    float* wbase = S.urows + (threadIdx.x & ~31) * kRowS;
+#pragma unroll 8
+    for (int s = 0; s < 32; ++s) {
+        const int r = (lane >> 3) + 4 * (s >> 2), ch = (lane & 7) + 8 * (s & 3);
+        const long long m = __shfl_sync(kFull, mrow, r);
+        float* dst = wbase + r * kRowS + 4 * ch;
+        if (m >= 0) cp_async16(dst, UU + m * kRowF + 4 * ch);
+        else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-#pragma unroll
-    for (int o = 0; o < kVO; ++o) {
-        const float waf = ws[kOffW1 + o], wad = ws[kOffW1 + kVO + o], wbf = ws[kOffW1 + 2 * kVO + o], wbd = ws[kOffW1 + 3 * kVO + o];
+    for (int i = threadIdx.x; i < P * 32; i += blockDim.x) {
+        const int pl = i >> 5, q = i & 31;
+        const long long g = tile * P + pl;
+        if (g < BN) cp_async16(S.vrows + pl * kRowS + 4 * q, VV + g * kRowF + 4 * q);
+        else reinterpret_cast<float4*>(S.vrows + pl * kRowS)[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    cp_async_wait_all();
+}
+
+// Calls f(o, p0, p1, p2, d0, d1, d2) for the 21 channels of the first conv's Linear outputs of this thread's edge.
+template <bool DIRECT, typename F>
+__device__ __forceinline__ void stage1_inputs(const TileSmem& S, const float* __restrict__ x, int N, const EdgeId& e, F&& f) {
+    if (DIRECT) {                                        // p = Wa (x_j - x_i) + Wb x_i from the coordinates x[B,1,3,N]
+        const float* xb = x + e.b * 3 * N;
+        float xi[3], dx[3];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            P[3 * o + c] = fmaf(waf, dx[c], wbf * xi[c]);
-            D[3 * o + c] = fmaf(wad, dx[c], wbd * xi[c]);
+            xi[c] = e.valid ? __ldg(xb + (size_t)c * N + e.n) : 0.f;
+            dx[c] = e.valid ? __ldg(xb + (size_t)c * N + e.mloc) - xi[c] : 0.f;
+        }
+#pragma unroll
+        for (int o = 0; o < kVO; ++o) {
+            const float waf = S.ws[kOffW1 + o], wad = S.ws[kOffW1 + kVO + o], wbf = S.ws[kOffW1 + 2 * kVO + o], wbd = S.ws[kOffW1 + 3 * kVO + o];
+            f(o, fmaf(waf, dx[0], wbf * xi[0]), fmaf(waf, dx[1], wbf * xi[1]), fmaf(waf, dx[2], wbf * xi[2]),
+              fmaf(wad, dx[0], wbd * xi[0]), fmaf(wad, dx[1], wbd * xi[1]), fmaf(wad, dx[2], wbd * xi[2]));
+        }
+    } else {                                             // p = U[j] + V[i]: four channels (3 x 128 bits per half row) at a time
+        const float4* u = reinterpret_cast<const float4*>(S.urows + threadIdx.x * kRowS);
+        const float4* v = reinterpret_cast<const float4*>(S.vrows + e.pl * kRowS);
+#pragma unroll
+        for (int g4 = 0; g4 < 6; ++g4) {
+            float pp[12], dd[12];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                if (g4 < 5 || q == 0) {
+                    const float4 a = u[3 * g4 + q], b = v[3 * g4 + q], c = u[16 + 3 * g4 + q], d = v[16 + 3 * g4 + q];
+                    pp[4 * q] = a.x + b.x; pp[4 * q + 1] = a.y + b.y; pp[4 * q + 2] = a.z + b.z; pp[4 * q + 3] = a.w + b.w;
+                    dd[4 * q] = c.x + d.x; dd[4 * q + 1] = c.y + d.y; dd[4 * q + 2] = c.z + d.z; dd[4 * q + 3] = c.w + d.w;
+                }
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int o = 4 * g4 + jj;
+                if (o < kVO) f(o, pp[3 * jj], pp[3 * jj + 1], pp[3 * jj + 2], dd[3 * jj], dd[3 * jj + 1], dd[3 * jj + 2]);
+            }
         }
     }
-    P[63] = D[63] = 0.f;
 }
 
-// P = U[m] + V[g] (both halves): 32 + 32 128-bit loads, the V row is shared by the k threads of a point (L1)
-__device__ __forceinline__ void load_pd(const float* __restrict__ UU, const float* __restrict__ VV, const EdgeId& e, float (&P)[64],
-                                        float (&D)[64]) {
-    const float4* u = reinterpret_cast<const float4*>(UU + e.m * kRowF);
-    const float4* v = reinterpret_cast<const float4*>(VV + e.g * kRowF);
-#pragma unroll
-    for (int q = 0; q < 16; ++q) {
-        const float4 a = __ldg(u + q), c = __ldg(v + q);
-        P[4 * q] = a.x + c.x; P[4 * q + 1] = a.y + c.y; P[4 * q + 2] = a.z + c.z; P[4 * q + 3] = a.w + c.w;
-    }
-#pragma unroll
-    for (int q = 0; q < 16; ++q) {
-        const float4 a = __ldg(u + 16 + q), c = __ldg(v + 16 + q);
-        D[4 * q] = a.x + c.x; D[4 * q + 1] = a.y + c.y; D[4 * q + 2] = a.z + c.z; D[4 * q + 3] = a.w + c.w;
-    }
-}
-
-// sum over the k threads of every point of a tile, through shared memory: red[T][65] <- one 63-vector per thread
+// Sum over the k threads of every point: each thread has put `width` floats at red[tid*kRedS ..]; emit(pl, i, sum).
 template <typename Emit>
-__device__ __forceinline__ void reduce_over_k(float* red, int P, int k, bool point_major, Emit emit) {
+__device__ __forceinline__ void reduce_round(const TileSmem& S, int P, int k, int width, bool point_major, Emit emit) {
     __syncthreads();
-    for (int q = threadIdx.x; q < P * kVD; q += blockDim.x) {
-        const int pl = point_major ? q / kVD : q % P;
-        const int oc = point_major ? q % kVD : q / P;
+    for (int q = threadIdx.x; q < P * width; q += blockDim.x) {
+        const int pl = point_major ? q / width : q % P;
+        const int i = point_major ? q % width : q / P;
+        const float* src = S.red + pl * k * kRedS + i;
         float s = 0.f;
-        for (int j = 0; j < k; ++j) s += red[(pl * k + j) * kRedStride + oc];
-        emit(pl, oc, s);
+        for (int j = 0; j < k; ++j) s += src[j * kRedS];
+        emit(pl, i, s);
     }
     __syncthreads();
 }
@@ -320,11 +398,11 @@ struct FwdArgs {
 
 // MODE 0: statistics of the stage-1 norms; MODE 1: of the stage-2 norms; MODE 2: the layer's output (+ ysum / yrsum)
 template <int STAGES, int MODE, bool DIRECT>
-__global__ void __launch_bounds__(256, 1) edgeconv_fwd_kernel(const FwdArgs A) {
-    extern __shared__ float smem_f[];
-    float* ws = smem_f;                                  // packed coefficients
-    float* red = smem_f + kWFloats;                      // [T][65] k-reduction rows
-    stage_weights(ws, A.Wdev);
+__global__ void __launch_bounds__(kMaxTileThreads, 2) edgeconv_fwd_kernel(const FwdArgs A) {
+    extern __shared__ __align__(16) float smem_f[];
+    const TileSmem S = carve(smem_f, blockDim.x, A.P, !DIRECT, !DIRECT, false, true);
+    stage_weights(S.ws, A.Wdev);
+    const float* ws = S.ws;
     const long long ntiles = (A.BN + A.P - 1) / A.P;
     const int lane = threadIdx.x & 31;
     float sr[kVO], sr2[kVO];
@@ -332,117 +410,112 @@ __global__ void __launch_bounds__(256, 1) edgeconv_fwd_kernel(const FwdArgs A) {
 #pragma unroll
         for (int o = 0; o < kVO; ++o) sr[o] = sr2[o] = 0.f;
     }
+    const float inv_k = 1.0f / A.k;
+    float* myred = S.red + threadIdx.x * kRedS;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const EdgeId e = edge_of(tile, A.P, A.k, A.BN, A.N, A.idx);
-        float P[64], D[64];
-        if (e.valid) { if (DIRECT) load_pd_direct(A.x, ws, A.N, e, P, D); else load_pd(A.UU, A.VV, e, P, D); }
-        else {
-#pragma unroll
-            for (int i = 0; i < 64; ++i) P[i] = D[i] = 0.f;
-        }
-        float* myrow = red + threadIdx.x * kRedStride;
+        __syncthreads();                                   // the previous tile's rows are no longer read
+        stage_tile<DIRECT>(S, A.UU, A.VV, e, tile, A.P, A.BN);
+        __syncthreads();
         if (MODE == 0) {
-#pragma unroll
-            for (int o = 0; o < kVO; ++o) {
-                const float r = sqrtf(fmaf(P[3 * o + 2], P[3 * o + 2], fmaf(P[3 * o + 1], P[3 * o + 1], P[3 * o] * P[3 * o]))) + kVnEps;
+            stage1_inputs<DIRECT>(S, A.x, A.N, e, [&](int o, float p0, float p1, float p2, float, float, float) {
+                const float r = vnorm(p0, p1, p2) + kVnEps;
                 if (e.valid) { sr[o] += r; sr2[o] = fmaf(r, r, sr2[o]); }
-            }
-            continue;
-        }
-        // ---- stage 1 in place: P <- O1 (and, for a one-stage layer in MODE 2, its Y coefficients) -------------------------
-        if (STAGES == 1) {
-            float Ys[kVD], Yr[kVD];
-#pragma unroll
-            for (int o = 0; o < kVO; ++o) {
-                const ChanFwd f = chan_fwd(P[3 * o], P[3 * o + 1], P[3 * o + 2], D[3 * o], D[3 * o + 1], D[3 * o + 2], bn_coef(ws, 0, BN_A, o), bn_coef(ws, 0, BN_B, o));
-                if (A.ysum) {
-                    chan_y(f, P[3 * o], P[3 * o + 1], P[3 * o + 2], D[3 * o], D[3 * o + 1], D[3 * o + 2], Ys[3 * o], Ys[3 * o + 1], Ys[3 * o + 2]);
-                    const float rh = (f.r - bn_coef(ws, 0, BN_MU, o)) * bn_coef(ws, 0, BN_RSTD, o);
-                    Yr[3 * o] = Ys[3 * o] * rh; Yr[3 * o + 1] = Ys[3 * o + 1] * rh; Yr[3 * o + 2] = Ys[3 * o + 2] * rh;
-                }
-                P[3 * o] = f.o0; P[3 * o + 1] = f.o1; P[3 * o + 2] = f.o2;
-            }
-            const float inv_k = 1.0f / A.k;
-#pragma unroll
-            for (int i = 0; i < kVD; ++i) myrow[i] = e.valid ? P[i] : 0.f;
-            reduce_over_k(red, A.P, A.k, false, [&](int pl, int oc, float s) {
-                const long long g = tile * A.P + pl;
-                if (g < A.BN) A.out[((g / A.N) * kVD + oc) * A.N + g % A.N] = s * inv_k;
             });
-            if (A.ysum) {
-#pragma unroll
-                for (int i = 0; i < kVD; ++i) myrow[i] = e.valid ? Ys[i] : 0.f;
-                reduce_over_k(red, A.P, A.k, true, [&](int pl, int oc, float s) {
-                    const long long g = tile * A.P + pl;
-                    if (g < A.BN) A.ysum[g * kVD + oc] = s;
-                });
-#pragma unroll
-                for (int i = 0; i < kVD; ++i) myrow[i] = e.valid ? Yr[i] : 0.f;
-                reduce_over_k(red, A.P, A.k, true, [&](int pl, int oc, float s) {
-                    const long long g = tile * A.P + pl;
-                    if (g < A.BN) A.yrsum[g * kVD + oc] = s;
-                });
-            }
             continue;
         }
-#pragma unroll
-        for (int o = 0; o < kVO; ++o) {
-            const ChanFwd f = chan_fwd(P[3 * o], P[3 * o + 1], P[3 * o + 2], D[3 * o], D[3 * o + 1], D[3 * o + 2], bn_coef(ws, 0, BN_A, o), bn_coef(ws, 0, BN_B, o));
-            P[3 * o] = f.o0; P[3 * o + 1] = f.o1; P[3 * o + 2] = f.o2;
-        }
-        // ---- stage 2, one output channel at a time (weights are constant-bank operands) -----------------------------------
+        auto emit_out = [&](int c0) {
+            return [&, c0](int pl, int i, float s) {
+                const long long g = tile * A.P + pl;
+                if (g < A.BN) A.out[((g / A.N) * kVD + c0 + i) * A.N + g % A.N] = s * inv_k;
+            };
+        };
+        auto emit_rows = [&](float* dst, int c0) {
+            return [&, dst, c0](int pl, int i, float s) {
+                const long long g = tile * A.P + pl;
+                if (g < A.BN) dst[g * kVD + c0 + i] = s;
+            };
+        };
         const bool want_y = MODE == 2 && A.ysum != nullptr;
+        if (STAGES == 1) {
+            // one conv: outputs (and the BatchNorm-backward coefficients) leave in rounds of 4 channels
+            float ob[12], yb[12], rb[12];
+            stage1_inputs<DIRECT>(S, A.x, A.N, e, [&](int o, float p0, float p1, float p2, float d0, float d1, float d2) {
+                const ChanFwd f = chan_fwd(p0, p1, p2, d0, d1, d2, bn_coef(ws, 0, BN_A, o), bn_coef(ws, 0, BN_B, o));
+                const int jj = o & 3;
+                ob[3 * jj] = f.o0; ob[3 * jj + 1] = f.o1; ob[3 * jj + 2] = f.o2;
+                if (want_y) {
+                    chan_y(f, p0, p1, p2, d0, d1, d2, yb[3 * jj], yb[3 * jj + 1], yb[3 * jj + 2]);
+                    const float rh = (f.r - bn_coef(ws, 0, BN_MU, o)) * bn_coef(ws, 0, BN_RSTD, o);
+                    rb[3 * jj] = yb[3 * jj] * rh; rb[3 * jj + 1] = yb[3 * jj + 1] * rh; rb[3 * jj + 2] = yb[3 * jj + 2] * rh;
+                }
+                if (jj == 3 || o == kVO - 1) {
+                    const int c0 = 3 * (o - jj), width = 3 * (jj + 1);
 #pragma unroll
-        for (int o = 0; o < kVO; ++o) {
-            float p0, p1, p2, d0, d1, d2;
-            if (MODE == 1) {
-                mix_channel<false>(ws, o, P, p0, p1, p2, d0, d1, d2);
-                const float r = sqrtf(fmaf(p2, p2, fmaf(p1, p1, p0 * p0))) + kVnEps;
-                if (e.valid) { sr[o] += r; sr2[o] = fmaf(r, r, sr2[o]); }
-                continue;
-            }
-            mix_channel<true>(ws, o, P, p0, p1, p2, d0, d1, d2);
-            const ChanFwd f = chan_fwd(p0, p1, p2, d0, d1, d2, bn_coef(ws, 1, BN_A, o), bn_coef(ws, 1, BN_B, o));
-            myrow[3 * o] = e.valid ? f.o0 : 0.f; myrow[3 * o + 1] = e.valid ? f.o1 : 0.f; myrow[3 * o + 2] = e.valid ? f.o2 : 0.f;
-            if (want_y) {                                  // Y and Y*rhat parked in D (its stage-1 content is dead)
-                float y0, y1, y2;
-                chan_y(f, p0, p1, p2, d0, d1, d2, y0, y1, y2);
-                D[3 * o] = y0; D[3 * o + 1] = y1; D[3 * o + 2] = y2;
-                D[63] = 0.f;
-            }
-        }
-        if (MODE == 1) continue;
-        const float inv_k = 1.0f / A.k;
-        reduce_over_k(red, A.P, A.k, false, [&](int pl, int oc, float s) {
-            const long long g = tile * A.P + pl;
-            if (g < A.BN) A.out[((g / A.N) * kVD + oc) * A.N + g % A.N] = s * inv_k;
-        });
-        if (want_y) {
+                    for (int i = 0; i < 12; ++i) if (i < width) myred[i] = e.valid ? ob[i] : 0.f;
+                    reduce_round(S, A.P, A.k, width, false, emit_out(c0));
+                    if (want_y) {
 #pragma unroll
-            for (int i = 0; i < kVD; ++i) myrow[i] = e.valid ? D[i] : 0.f;
-            reduce_over_k(red, A.P, A.k, true, [&](int pl, int oc, float s) {
-                const long long g = tile * A.P + pl;
-                if (g < A.BN) A.ysum[g * kVD + oc] = s;
+                        for (int i = 0; i < 12; ++i) if (i < width) myred[i] = e.valid ? yb[i] : 0.f;
+                        reduce_round(S, A.P, A.k, width, true, emit_rows(A.ysum, c0));
+#pragma unroll
+                        for (int i = 0; i < 12; ++i) if (i < width) myred[i] = e.valid ? rb[i] : 0.f;
+                        reduce_round(S, A.P, A.k, width, true, emit_rows(A.yrsum, c0));
+                    }
+                }
             });
-            // rhat of stage 2 needs the norms again: recompute them from O1 (P) -- cheaper than 21 more live registers
+            continue;
+        }
+        // ---- two convs: stage 1 -> O1 in registers -----------------------------------------------------------------------
+        float X[64];
+        stage1_inputs<DIRECT>(S, A.x, A.N, e, [&](int o, float p0, float p1, float p2, float d0, float d1, float d2) {
+            const ChanFwd f = chan_fwd(p0, p1, p2, d0, d1, d2, bn_coef(ws, 0, BN_A, o), bn_coef(ws, 0, BN_B, o));
+            X[3 * o] = f.o0; X[3 * o + 1] = f.o1; X[3 * o + 2] = f.o2;
+        });
+        X[63] = 0.f;
+        if (MODE == 1) {
 #pragma unroll
             for (int o = 0; o < kVO; ++o) {
                 float p0, p1, p2, d0, d1, d2;
-                mix_channel<false>(ws, o, P, p0, p1, p2, d0, d1, d2);
-                const float r = sqrtf(fmaf(p2, p2, fmaf(p1, p1, p0 * p0))) + kVnEps;
-                const float rh = (r - bn_coef(ws, 1, BN_MU, o)) * bn_coef(ws, 1, BN_RSTD, o);
-                myrow[3 * o] = e.valid ? D[3 * o] * rh : 0.f; myrow[3 * o + 1] = e.valid ? D[3 * o + 1] * rh : 0.f;
-                myrow[3 * o + 2] = e.valid ? D[3 * o + 2] * rh : 0.f;
+                mix_channel<false>(ws, o, X, p0, p1, p2, d0, d1, d2);
+                const float r = vnorm(p0, p1, p2) + kVnEps;
+                if (e.valid) { sr[o] += r; sr2[o] = fmaf(r, r, sr2[o]); }
             }
-            reduce_over_k(red, A.P, A.k, true, [&](int pl, int oc, float s) {
-                const long long g = tile * A.P + pl;
-                if (g < A.BN) A.yrsum[g * kVD + oc] = s;
-            });
+            continue;
+        }
+        // ---- stage 2, kGrp output channels per k-reduction round (weights from shared memory, 128 bits at a time).  The rounds are
+        // a real loop: unrolling all 21 channels made the kernel 130 KB of straight-line code, and per-channel rounds (a ~330-
+        // instruction body) cost more in barriers than they save in instruction-cache misses (measured: 328 / 295 / 358 us)
+#pragma unroll 1
+        for (int g7 = 0; g7 < kVO / kGrp; ++g7) {
+            float yb[3 * kGrp], rb[3 * kGrp];
+#pragma unroll
+            for (int jj = 0; jj < kGrp; ++jj) {
+                const int o = g7 * kGrp + jj;
+                float p0, p1, p2, d0, d1, d2;
+                mix_channel<true>(ws, o, X, p0, p1, p2, d0, d1, d2);
+                const ChanFwd f = chan_fwd(p0, p1, p2, d0, d1, d2, bn_coef(ws, 1, BN_A, o), bn_coef(ws, 1, BN_B, o));
+                myred[3 * jj] = e.valid ? f.o0 : 0.f; myred[3 * jj + 1] = e.valid ? f.o1 : 0.f; myred[3 * jj + 2] = e.valid ? f.o2 : 0.f;
+                if (want_y) {
+                    chan_y(f, p0, p1, p2, d0, d1, d2, yb[3 * jj], yb[3 * jj + 1], yb[3 * jj + 2]);
+                    const float rh = (f.r - bn_coef(ws, 1, BN_MU, o)) * bn_coef(ws, 1, BN_RSTD, o);
+                    rb[3 * jj] = yb[3 * jj] * rh; rb[3 * jj + 1] = yb[3 * jj + 1] * rh; rb[3 * jj + 2] = yb[3 * jj + 2] * rh;
+                }
+            }
+            reduce_round(S, A.P, A.k, 3 * kGrp, false, emit_out(3 * kGrp * g7));
+            if (want_y) {
+#pragma unroll
+                for (int i = 0; i < 3 * kGrp; ++i) myred[i] = e.valid ? yb[i] : 0.f;
+                reduce_round(S, A.P, A.k, 3 * kGrp, true, emit_rows(A.ysum, 3 * kGrp * g7));
+#pragma unroll
+                for (int i = 0; i < 3 * kGrp; ++i) myred[i] = e.valid ? rb[i] : 0.f;
+                reduce_round(S, A.P, A.k, 3 * kGrp, true, emit_rows(A.yrsum, 3 * kGrp * g7));
+            }
         }
     }
     if (MODE != 2) {                                     // block reduction of the 42 partial sums, fp64 from the warp level up
         __syncthreads();
-        double* dsm = reinterpret_cast<double*>(red);
+        double* dsm = reinterpret_cast<double*>(S.red);
         const int warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
 #pragma unroll
         for (int o = 0; o < kVO; ++o) {
@@ -458,219 +531,213 @@ __global__ void __launch_bounds__(256, 1) edgeconv_fwd_kernel(const FwdArgs A) {
     }
 }
 
-// ---- backward, stage 2 (two-stage layers) -----------------------------------------------------------------------------
+// 16 values per lane -> lanes l and l+16 both receive the warp-wide sum of v[l]
+__device__ __forceinline__ float warp_transpose_sum16(float (&v)[16], int lane) {
+#pragma unroll
+    for (int s = 8; s >= 1; s >>= 1) {
+        const bool up = (lane & s) != 0;
+#pragma unroll
+        for (int j = 0; j < s; ++j) {
+            const float keep = up ? v[j + s] : v[j];
+            const float send = up ? v[j] : v[j + s];
+            v[j] = keep + __shfl_xor_sync(kFull, send, s);
+        }
+    }
+    return v[0] + __shfl_xor_sync(kFull, v[0], 16);
+}
+
+// ---- backward, stage 2 (two-conv layers) --------------------------------------------------------------------------------
 struct Bwd2Args {
     const float* UU; const float* VV; const long long* idx; const float* Wdev; const float* x;
     long long BN; int N; int k; int P;
     const float* G;         // [B,21,3,N] gradient of the layer output
-    float* gO1;             // [E][64] out: gradient wrt the stage-1 output of every edge
+    float* gO1;             // [E][64] out: gradient wrt the first conv's output of every edge
     float* dW2;             // [21][2][21] = [out o][half: feat, dir][in i] += (atomics at kernel end)
     double* stats1;         // [21][2] += sum gy1, sum gy1 rhat1
 };
+constexpr int kDwEntries = 2 * kVO * kVO;                 // 882
+constexpr int kDwRow = 48;                                // per output channel: 42 entries (half, in) padded to 3 groups of 16
+constexpr int kDwPad = kVO * kDwRow;                      // 1008
 
 template <bool DIRECT>
-__global__ void __launch_bounds__(256, 1) edgeconv_bwd2_kernel(const Bwd2Args A) {
-    extern __shared__ float smem_f[];
-    float* ws = smem_f;                                  // packed coefficients
-    float* red = smem_f + kWFloats;                      // Gs[P][63]
-    stage_weights(ws, A.Wdev);
+__global__ void __launch_bounds__(kMaxTileThreads, 2) edgeconv_bwd2_kernel(const Bwd2Args A) {
+    extern __shared__ __align__(16) float smem_f[];
+    const TileSmem S = carve(smem_f, blockDim.x, A.P, !DIRECT, !DIRECT, true, false);
+    float* dw_s = S.acc;                                 // [896] weight-gradient partial sums of this CTA
+    float* st_s = S.acc + kDwPad;                        // [42] stage-1 BatchNorm sums of this CTA
+    for (int i = threadIdx.x; i < kDwPad + 2 * kVO; i += blockDim.x) S.acc[i] = 0.f;
+    stage_weights(S.ws, A.Wdev);
+    const float* ws = S.ws;
     const long long ntiles = (A.BN + A.P - 1) / A.P;
     const int lane = threadIdx.x & 31;
-    constexpr int kGroups = (2 * kVO * kVO + 31) / 32;   // 28 groups of 32 weight-gradient entries
-    float dwacc[kGroups];
-#pragma unroll
-    for (int i = 0; i < kGroups; ++i) dwacc[i] = 0.f;
-    float s1[kVO], s2[kVO];
-#pragma unroll
-    for (int o = 0; o < kVO; ++o) s1[o] = s2[o] = 0.f;
     const float inv_k = 1.0f / A.k;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const EdgeId e = edge_of(tile, A.P, A.k, A.BN, A.N, A.idx);
         __syncthreads();
+        stage_tile<DIRECT>(S, A.UU, A.VV, e, tile, A.P, A.BN);
         for (int q = threadIdx.x; q < A.P * kVD; q += blockDim.x) {           // upstream gradient rows of the tile's points
             const int pl = q % A.P, oc = q / A.P;
             const long long g = tile * A.P + pl;
-            red[pl * kVD + oc] = g < A.BN ? A.G[((g / A.N) * kVD + oc) * A.N + g % A.N] * inv_k : 0.f;
+            S.gs[pl * 64 + oc] = g < A.BN ? A.G[((g / A.N) * kVD + oc) * A.N + g % A.N] * inv_k : 0.f;
         }
         __syncthreads();
-        const EdgeId e = edge_of(tile, A.P, A.k, A.BN, A.N, A.idx);
-        float P[64], D[64];
-        if (e.valid) { if (DIRECT) load_pd_direct(A.x, ws, A.N, e, P, D); else load_pd(A.UU, A.VV, e, P, D); }
-        else {
+        float X[64];                                                           // O1: output of the first conv
+        stage1_inputs<DIRECT>(S, A.x, A.N, e, [&](int o, float p0, float p1, float p2, float d0, float d1, float d2) {
+            const ChanFwd f = chan_fwd(p0, p1, p2, d0, d1, d2, bn_coef(ws, 0, BN_A, o), bn_coef(ws, 0, BN_B, o));
+            X[3 * o] = f.o0; X[3 * o + 1] = f.o1; X[3 * o + 2] = f.o2;
+        });
+        X[63] = 0.f;
+        float GO[64];                                                          // gO1 = W2^T g, accumulated over output channels
 #pragma unroll
-            for (int i = 0; i < 64; ++i) P[i] = D[i] = 0.f;
-        }
-#pragma unroll
-        for (int o = 0; o < kVO; ++o) {                                      // stage 1 forward: P <- O1
-            const ChanFwd f = chan_fwd(P[3 * o], P[3 * o + 1], P[3 * o + 2], D[3 * o], D[3 * o + 1], D[3 * o + 2], bn_coef(ws, 0, BN_A, o), bn_coef(ws, 0, BN_B, o));
-            P[3 * o] = f.o0; P[3 * o + 1] = f.o1; P[3 * o + 2] = f.o2;
-        }
-        float (&gO1)[64] = D;                                                 // D is dead: accumulate gO1 there
-#pragma unroll
-        for (int i = 0; i < 64; ++i) gO1[i] = 0.f;
-        const float* grow = red + (e.pl < A.P ? e.pl : 0) * kVD;
-        float stag[32];
-#pragma unroll
-        for (int o = 0; o < kVO; ++o) {
+        for (int i = 0; i < 64; ++i) GO[i] = 0.f;
+        const float* grow = S.gs + e.pl * 64;
+        float stag[16];
+#pragma unroll 1                                                               // a real loop: the body is ~700 instructions; unrolled 21 times
+        for (int o = 0; o < kVO; ++o) {                                        // it thrashes the instruction cache (1.56 ms; by 3: 1.16; 1: 0.91)
             float p0, p1, p2, d0, d1, d2;
-            mix_channel<true>(ws, o, P, p0, p1, p2, d0, d1, d2);
+            mix_channel<true>(ws, o, X, p0, p1, p2, d0, d1, d2);
             const ChanFwd f = chan_fwd(p0, p1, p2, d0, d1, d2, bn_coef(ws, 1, BN_A, o), bn_coef(ws, 1, BN_B, o));
-            const float g0 = e.valid ? grow[3 * o] : 0.f, g1 = e.valid ? grow[3 * o + 1] : 0.f, g2 = e.valid ? grow[3 * o + 2] : 0.f;
             float gp0, gp1, gp2, gd0, gd1, gd2, gy, rhat;
-            chan_bwd(f, p0, p1, p2, d0, d1, d2, g0, g1, g2, bn_coef(ws, 1, BN_A, o), bn_coef(ws, 1, BN_MU, o), bn_coef(ws, 1, BN_RSTD, o),
-                     bn_coef(ws, 1, BN_S1M, o), bn_coef(ws, 1, BN_S2M, o), gp0, gp1, gp2, gd0, gd1, gd2, gy, rhat);
+            chan_bwd(f, p0, p1, p2, d0, d1, d2, grow[3 * o], grow[3 * o + 1], grow[3 * o + 2], bn_coef(ws, 1, BN_A, o), bn_coef(ws, 1, BN_MU, o),
+                     bn_coef(ws, 1, BN_RSTD, o), bn_coef(ws, 1, BN_S1M, o), bn_coef(ws, 1, BN_S2M, o), gp0, gp1, gp2, gd0, gd1, gd2, gy, rhat);
             if (!e.valid) { gp0 = gp1 = gp2 = gd0 = gd1 = gd2 = 0.f; }
-            mix_channel_transposed(ws, o, gp0, gp1, gp2, gd0, gd1, gd2, D);       // gO1 += W2^T g
-            // weight gradient: entry q = (half h, out o, in i) <- sum over edges of g_h[o] . O1[i]; 32 entries at a time go
-            // through the warp transpose so that lane l ends up owning entry (group, l)
+            mix_channel_transposed(ws, o, gp0, gp1, gp2, gd0, gd1, gd2, GO);
+            // weight gradient: entry (out o, half h, in i) <- sum over edges of g_h[o] . O1[i]; the 42 entries of this output
+            // channel go through the warp transpose 16 at a time, after which lane l (< 16) owns entry 16*group + l of the row
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-#pragma unroll
-                for (int i = 0; i < kVO; ++i) {
-                    const int q = (o * 2 + h) * kVO + i;                     // visiting order: [out o][half h][in i]
-                    const float v = h == 0 ? fmaf(gp2, P[3 * i + 2], fmaf(gp1, P[3 * i + 1], gp0 * P[3 * i]))
-                                           : fmaf(gd2, P[3 * i + 2], fmaf(gd1, P[3 * i + 1], gd0 * P[3 * i]));
-                    stag[q & 31] = v;
-                    if ((q & 31) == 31) dwacc[q >> 5] += warp_transpose_sum(stag, lane);
+            for (int q = 0; q < kDwRow; ++q) {
+                const int h = q / kVO, i = q - h * kVO;
+                stag[q & 15] = q >= 2 * kVO ? 0.f
+                               : h == 0     ? fmaf(gp2, X[3 * i + 2], fmaf(gp1, X[3 * i + 1], gp0 * X[3 * i]))
+                                            : fmaf(gd2, X[3 * i + 2], fmaf(gd1, X[3 * i + 1], gd0 * X[3 * i]));
+                if ((q & 15) == 15) {
+                    const float tot = warp_transpose_sum16(stag, lane);
+                    if (lane < 16) atomicAdd(dw_s + o * kDwRow + (q & ~15) + lane, tot);
                 }
             }
         }
-        {                                                                     // the last, partial group of weight-gradient entries
-#pragma unroll
-            for (int j = (2 * kVO * kVO) & 31; j < 32; ++j) stag[j] = 0.f;
-            dwacc[kGroups - 1] += warp_transpose_sum(stag, lane);
-        }
-        if (e.valid) {
-            float4* dst = reinterpret_cast<float4*>(A.gO1 + (e.g * A.k + (threadIdx.x - e.pl * A.k)) * 64);
-#pragma unroll
-            for (int q = 0; q < 16; ++q) __stcs(dst + q, make_float4(gO1[4 * q], gO1[4 * q + 1], gO1[4 * q + 2], q == 15 ? 0.f : gO1[4 * q + 3]));
-        }
-        // stage-1 BatchNorm sums: gy1 = Y1 . gO1, needs the stage-1 inputs again (rows are L1 / L2 hits)
-        float Q[64], Dd[64];
-        if (e.valid) { if (DIRECT) load_pd_direct(A.x, ws, A.N, e, Q, Dd); else load_pd(A.UU, A.VV, e, Q, Dd); }
-        else {
-#pragma unroll
-            for (int i = 0; i < 64; ++i) Q[i] = Dd[i] = 0.f;
-        }
-#pragma unroll
-        for (int o = 0; o < kVO; ++o) {
-            const ChanFwd f = chan_fwd(Q[3 * o], Q[3 * o + 1], Q[3 * o + 2], Dd[3 * o], Dd[3 * o + 1], Dd[3 * o + 2], bn_coef(ws, 0, BN_A, o), bn_coef(ws, 0, BN_B, o));
+        // BatchNorm sums of the first conv: gy1 = Y1 . gO1 per channel (its inputs are still staged in shared memory)
+        stage1_inputs<DIRECT>(S, A.x, A.N, e, [&](int o, float p0, float p1, float p2, float d0, float d1, float d2) {
+            const ChanFwd f = chan_fwd(p0, p1, p2, d0, d1, d2, bn_coef(ws, 0, BN_A, o), bn_coef(ws, 0, BN_B, o));
             float y0, y1, y2;
-            chan_y(f, Q[3 * o], Q[3 * o + 1], Q[3 * o + 2], Dd[3 * o], Dd[3 * o + 1], Dd[3 * o + 2], y0, y1, y2);
-            const float gy = fmaf(y2, gO1[3 * o + 2], fmaf(y1, gO1[3 * o + 1], y0 * gO1[3 * o]));
-            if (e.valid) { s1[o] += gy; s2[o] = fmaf(gy, (f.r - bn_coef(ws, 0, BN_MU, o)) * bn_coef(ws, 0, BN_RSTD, o), s2[o]); }
+            chan_y(f, p0, p1, p2, d0, d1, d2, y0, y1, y2);
+            float gy = e.valid ? fmaf(y2, GO[3 * o + 2], fmaf(y1, GO[3 * o + 1], y0 * GO[3 * o])) : 0.f;
+            float gyr = gy * (f.r - bn_coef(ws, 0, BN_MU, o)) * bn_coef(ws, 0, BN_RSTD, o);
+            gy = warp_sum(gy);
+            gyr = warp_sum(gyr);
+            if (lane == 0) { atomicAdd(st_s + 2 * o, gy); atomicAdd(st_s + 2 * o + 1, gyr); }
+        });
+        // gO1 scratch layout [tile][16 chunks][T threads] of 16 bytes: thread-per-edge stores (here) and loads (stage-1 backward)
+        // are both fully coalesced, 512 contiguous bytes per warp instruction
+        if (e.valid) {
+            float4* dst = reinterpret_cast<float4*>(A.gO1) + tile * 16 * blockDim.x + threadIdx.x;
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+                __stcs(dst + (size_t)q * blockDim.x, make_float4(GO[4 * q], GO[4 * q + 1], GO[4 * q + 2], q == 15 ? 0.f : GO[4 * q + 3]));
         }
     }
-    // flush: weight-gradient entries (lane l of every warp owns entry 32*group + l) and the 42 BatchNorm sums
-#pragma unroll
-    for (int gi = 0; gi < kGroups; ++gi) {
-        const int q = gi * 32 + lane;
-        if (q < 2 * kVO * kVO) atomicAdd(A.dW2 + q, dwacc[gi]);
-    }
     __syncthreads();
-    double* dsm = reinterpret_cast<double*>(red);
-    const int warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-#pragma unroll
-    for (int o = 0; o < kVO; ++o) {
-        const double a = warp_sum((double)s1[o]), b = warp_sum((double)s2[o]);
-        if (lane == 0) { dsm[(warp * kVO + o) * 2] = a; dsm[(warp * kVO + o) * 2 + 1] = b; }
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * kVO; i += blockDim.x) {
-        double s = 0.;
-        for (int w = 0; w < nw; ++w) s += dsm[w * 2 * kVO + i];
-        atomicAdd(A.stats1 + i, s);
-    }
+    for (int i = threadIdx.x; i < kDwEntries; i += blockDim.x) atomicAdd(A.dW2 + i, dw_s[(i / (2 * kVO)) * kDwRow + i % (2 * kVO)]);
+    for (int i = threadIdx.x; i < 2 * kVO; i += blockDim.x) atomicAdd(A.stats1 + i, (double)st_s[i]);
 }
 
 // ---- backward, stage 1 ------------------------------------------------------------------------------------------------------
 struct Bwd1Args {
     const float* UU; const float* VV; const long long* idx; const float* Wdev; const float* x;
     long long BN; int N; int k; int P;
-    const float* gO1;       // [E][64] (two-stage layers) or nullptr: then gO1 = G[n]/k (one-stage layers)
+    const float* gO1;       // [E][64] (two-conv layers) or nullptr: then gO1 = G[n]/k (one-conv layers)
     const float* G;         // [B,21,3,N]
     float* gUU;             // [B*N][128] += (vector reductions; zeroed by the caller)
     float* gVV;             // [B*N][128]  = sum over the k edges of the point
 };
 
 template <bool DIRECT>
-__global__ void __launch_bounds__(256, 1) edgeconv_bwd1_kernel(const Bwd1Args A) {
-    extern __shared__ float smem_f[];
-    float* ws = smem_f;                                  // packed coefficients
-    float* red = smem_f + kWFloats;                      // [T][65] reduction rows, then Gs[P][63] behind them
-    float* Gs = red + blockDim.x * kRedStride;
-    stage_weights(ws, A.Wdev);
+__global__ void __launch_bounds__(kMaxTileThreads, 2) edgeconv_bwd1_kernel(const Bwd1Args A) {
+    extern __shared__ __align__(16) float smem_f[];
+    const TileSmem S = carve(smem_f, blockDim.x, A.P, true, !DIRECT, true, true);
+    stage_weights(S.ws, A.Wdev);
+    const float* ws = S.ws;
     const long long ntiles = (A.BN + A.P - 1) / A.P;
     const float inv_k = 1.0f / A.k;
+    const int lane = threadIdx.x & 31;
+    float* myred = S.red + threadIdx.x * kRedS;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const EdgeId e = edge_of(tile, A.P, A.k, A.BN, A.N, A.idx);
+        __syncthreads();
+        stage_tile<DIRECT>(S, A.UU, A.VV, e, tile, A.P, A.BN);
         if (!A.gO1) {
-            __syncthreads();
             for (int q = threadIdx.x; q < A.P * kVD; q += blockDim.x) {
                 const int pl = q % A.P, oc = q / A.P;
                 const long long g = tile * A.P + pl;
-                Gs[pl * kVD + oc] = g < A.BN ? A.G[((g / A.N) * kVD + oc) * A.N + g % A.N] * inv_k : 0.f;
+                S.gs[pl * 64 + oc] = g < A.BN ? A.G[((g / A.N) * kVD + oc) * A.N + g % A.N] * inv_k : 0.f;
             }
-            __syncthreads();
         }
-        const EdgeId e = edge_of(tile, A.P, A.k, A.BN, A.N, A.idx);
-        float P[64], D[64];
-        if (e.valid) { if (DIRECT) load_pd_direct(A.x, ws, A.N, e, P, D); else load_pd(A.UU, A.VV, e, P, D); }
-        else {
-#pragma unroll
-            for (int i = 0; i < 64; ++i) P[i] = D[i] = 0.f;
-        }
-        const float4* gsrc = A.gO1 ? reinterpret_cast<const float4*>(A.gO1 + (e.g * A.k + (threadIdx.x - e.pl * A.k)) * 64) : nullptr;
-        const float* grow = Gs + (e.pl < A.P ? e.pl : 0) * kVD;
-        float gO[64];
-        if (gsrc && e.valid) {
+        __syncthreads();
+        float GO[64];
+        if (A.gO1) {                                                          // chunk-major scratch: coalesced (see edgeconv_bwd2_kernel)
+            const float4* gsrc = reinterpret_cast<const float4*>(A.gO1) + tile * 16 * blockDim.x + threadIdx.x;
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
-                const float4 v = __ldcs(gsrc + q);
-                gO[4 * q] = v.x; gO[4 * q + 1] = v.y; gO[4 * q + 2] = v.z; gO[4 * q + 3] = v.w;
+                const float4 v = e.valid ? __ldcs(gsrc + (size_t)q * blockDim.x) : make_float4(0.f, 0.f, 0.f, 0.f);
+                GO[4 * q] = v.x; GO[4 * q + 1] = v.y; GO[4 * q + 2] = v.z; GO[4 * q + 3] = v.w;
             }
         } else {
+            const float* grow = S.gs + e.pl * 64;
 #pragma unroll
-            for (int i = 0; i < kVD; ++i) gO[i] = (e.valid && !gsrc) ? grow[i] : 0.f;
-            gO[63] = 0.f;
+            for (int i = 0; i < kVD; ++i) GO[i] = e.valid ? grow[i] : 0.f;
+            GO[63] = 0.f;
         }
-#pragma unroll
-        for (int o = 0; o < kVO; ++o) {
-            const float p0 = P[3 * o], p1 = P[3 * o + 1], p2 = P[3 * o + 2], d0 = D[3 * o], d1 = D[3 * o + 1], d2 = D[3 * o + 2];
+        float4* slot = reinterpret_cast<float4*>(S.urows + threadIdx.x * kRowS);   // own row: its inputs are consumed group by group,
+        float pb[12], db[12];                                                       // the gradient row (gP | gD) replaces them in place
+        stage1_inputs<DIRECT>(S, A.x, A.N, e, [&](int o, float p0, float p1, float p2, float d0, float d1, float d2) {
             const ChanFwd f = chan_fwd(p0, p1, p2, d0, d1, d2, bn_coef(ws, 0, BN_A, o), bn_coef(ws, 0, BN_B, o));
+            const int jj = o & 3;
             float gy, rhat;
-            chan_bwd(f, p0, p1, p2, d0, d1, d2, gO[3 * o], gO[3 * o + 1], gO[3 * o + 2], bn_coef(ws, 0, BN_A, o), bn_coef(ws, 0, BN_MU, o),
-                     bn_coef(ws, 0, BN_RSTD, o), bn_coef(ws, 0, BN_S1M, o), bn_coef(ws, 0, BN_S2M, o), P[3 * o], P[3 * o + 1], P[3 * o + 2], D[3 * o], D[3 * o + 1], D[3 * o + 2], gy, rhat);
-        }
-        P[63] = D[63] = 0.f;
-        if (e.valid) {                                                        // neighbour half: gU[m] += (gP | gD)
-            float4* dst = reinterpret_cast<float4*>(A.gUU + e.m * kRowF);
+            chan_bwd(f, p0, p1, p2, d0, d1, d2, GO[3 * o], GO[3 * o + 1], GO[3 * o + 2], bn_coef(ws, 0, BN_A, o), bn_coef(ws, 0, BN_MU, o),
+                     bn_coef(ws, 0, BN_RSTD, o), bn_coef(ws, 0, BN_S1M, o), bn_coef(ws, 0, BN_S2M, o), pb[3 * jj], pb[3 * jj + 1], pb[3 * jj + 2],
+                     db[3 * jj], db[3 * jj + 1], db[3 * jj + 2], gy, rhat);
+            if (jj == 3 || o == kVO - 1) {                                    // four channels = 3 x 128 bits of each half row
+                const int g4 = o >> 2, nq = jj == 3 ? 3 : 1;
+                if (jj != 3) { pb[3] = db[3] = 0.f; }
 #pragma unroll
-            for (int q = 0; q < 16; ++q) atomicAdd(dst + q, make_float4(P[4 * q], P[4 * q + 1], P[4 * q + 2], P[4 * q + 3]));
+                for (int q = 0; q < 3; ++q) {
+                    if (q < nq) {                                             // neighbour half, parked for the scatter below
+                        slot[3 * g4 + q] = make_float4(pb[4 * q], pb[4 * q + 1], pb[4 * q + 2], pb[4 * q + 3]);
+                        slot[16 + 3 * g4 + q] = make_float4(db[4 * q], db[4 * q + 1], db[4 * q + 2], db[4 * q + 3]);
+                    }
+                }
+                const int width = 4 * nq;                                     // centre half: gV[g] = sum over the point's k edges
 #pragma unroll
-            for (int q = 0; q < 16; ++q) atomicAdd(dst + 16 + q, make_float4(D[4 * q], D[4 * q + 1], D[4 * q + 2], D[4 * q + 3]));
-        }
-        float* myrow = red + threadIdx.x * kRedStride;                        // centre half: gV[g] = sum over its k edges
-#pragma unroll
-        for (int i = 0; i < kVD; ++i) myrow[i] = e.valid ? P[i] : 0.f;
-        reduce_over_k(red, A.P, A.k, true, [&](int pl, int oc, float s) {
-            const long long g = tile * A.P + pl;
-            if (g < A.BN) A.gVV[g * kRowF + oc] = s;
+                for (int i = 0; i < 12; ++i) if (i < width) { myred[i] = e.valid ? pb[i] : 0.f; myred[12 + i] = e.valid ? db[i] : 0.f; }
+                reduce_round(S, A.P, A.k, 24, true, [&](int pl, int i, float s) {
+                    const long long g = tile * A.P + pl;
+                    const int half = i / 12, w = i - 12 * half;
+                    if (g < A.BN && w < width) A.gVV[g * kRowF + 64 * half + 12 * g4 + w] = s;
+                });
+            }
         });
-#pragma unroll
-        for (int i = 0; i < kVD; ++i) myrow[i] = e.valid ? D[i] : 0.f;
-        reduce_over_k(red, A.P, A.k, true, [&](int pl, int oc, float s) {
-            const long long g = tile * A.P + pl;
-            if (g < A.BN) A.gVV[g * kRowF + 64 + oc] = s;
-        });
+        // neighbour half: gU[m] += (gP | gD), warp-cooperative like the gather -- 8 lanes add one 128-byte line of one row, so the
+        // 128-bit reductions of an instruction land in 4 lines instead of 32
+        {
+            __syncwarp();
+            const long long mrow = e.valid ? e.m : -1;
+            const float* wbase = S.urows + (threadIdx.x & ~31) * kRowS;
+#pragma unroll 8
+            for (int s = 0; s < 32; ++s) {
+                const int r = (lane >> 3) + 4 * (s >> 2), ch = (lane & 7) + 8 * (s & 3);
+                const long long m = __shfl_sync(kFull, mrow, r);
+                if (m >= 0) atomicAdd(reinterpret_cast<float4*>(A.gUU + m * kRowF) + ch, *reinterpret_cast<const float4*>(wbase + r * kRowS + 4 * ch));
+            }
+        }
     }
 }
 
-static int tile_threads(int P, int k) { return (P * k + 31) / 32 * 32; }   // whole warps: the kernels shuffle
-
 static int tile_points(int k) {
-    int P = 256 / k;
+    int P = kMaxTileThreads / k;
     if (P > 32) P = 32;
     return P < 1 ? 1 : P;
 }
+static int tile_threads(int P, int k) { return (P * k + 31) / 32 * 32; }   // whole warps: the kernels shuffle
 
 static int edge_grid(long long BN, int P) {
     const long long tiles = (BN + P - 1) / P;
@@ -702,17 +769,24 @@ static void opt_in_smem(K kernel, size_t smem) {
 
 extern "C" int hpcs_edgeconv_coef_floats(void) { return kWFloats; }
 
+extern "C" size_t hpcs_edgeconv_scratch_floats(int B, int N, int k) {
+    if (B <= 0 || N <= 0 || k <= 0 || k > kMaxTileThreads) return 0;
+    const int P = tile_points(k);
+    const long long tiles = ((long long)B * N + P - 1) / P;
+    return (size_t)tiles * tile_threads(P, k) * 64;
+}
+
 extern "C" int hpcs_edgeconv_fwd_f32(const float* UU, const float* VV, const int64_t* idx, int B, int N, int k, int stages,
                                      const float* coef, const float* x_direct, int mode, double* stats, float* out, float* ysum,
                                      float* yrsum, void* stream) {
     if (!idx || !coef || (!x_direct && (!UU || !VV))) return fail(HPCS_ERR_ARG, "edgeconv_fwd: null pointer");
-    if (B <= 0 || N <= 0 || k <= 0 || k > 256 || (stages != 1 && stages != 2) || mode < 0 || mode > 2 || (mode == 1 && stages == 1))
+    if (B <= 0 || N <= 0 || k <= 0 || k > kMaxTileThreads || (stages != 1 && stages != 2) || mode < 0 || mode > 2 || (mode == 1 && stages == 1))
         return fail(HPCS_ERR_ARG, "edgeconv_fwd: bad arguments B=%d N=%d k=%d stages=%d mode=%d", B, N, k, stages, mode);
     if ((mode != 2 && !stats) || (mode == 2 && !out) || ((ysum == nullptr) != (yrsum == nullptr)))
         return fail(HPCS_ERR_ARG, "edgeconv_fwd: output pointers do not match mode %d", mode);
     FwdArgs A{UU, VV, reinterpret_cast<const long long*>(idx), coef, x_direct, (long long)B * N, N, k, tile_points(k), stats, out, ysum, yrsum};
     const int T = tile_threads(A.P, k);
-    const size_t smem = sizeof(float) * ((size_t)kWFloats + (size_t)T * kRedStride) + 64;
+    const size_t smem = tile_smem_bytes(T, A.P, x_direct == nullptr, x_direct == nullptr, false, true, 0);
     const int grid = edge_grid(A.BN, A.P);
     cudaStream_t st = as_stream(stream);
 #define HPCS_LAUNCH_FWD(S, M)                                                      \
@@ -739,15 +813,17 @@ extern "C" int hpcs_edgeconv_bwd_stage2_f32(const float* UU, const float* VV, co
                                             double* stats1, void* stream) {
     if (!idx || !coef || !G || !gO1 || !dW2 || !stats1 || (!x_direct && (!UU || !VV)))
         return fail(HPCS_ERR_ARG, "edgeconv_bwd_stage2: null pointer");
-    if (B <= 0 || N <= 0 || k <= 0 || k > 256) return fail(HPCS_ERR_ARG, "edgeconv_bwd_stage2: bad shape");
+    if (B <= 0 || N <= 0 || k <= 0 || k > kMaxTileThreads) return fail(HPCS_ERR_ARG, "edgeconv_bwd_stage2: bad shape");
     Bwd2Args A{UU, VV, reinterpret_cast<const long long*>(idx), coef, x_direct, (long long)B * N, N, k, tile_points(k), G, gO1, dW2, stats1};
     const int T = tile_threads(A.P, k);
-    size_t tail = sizeof(float) * (size_t)A.P * kVD;
-    const size_t tail_red = sizeof(double) * 2 * kVO * ((T + 31) / 32);
-    if (tail < tail_red) tail = tail_red;
-    const size_t smem = sizeof(float) * kWFloats + tail;
-    if (x_direct) edgeconv_bwd2_kernel<true><<<edge_grid(A.BN, A.P), T, smem, as_stream(stream)>>>(A);
-    else edgeconv_bwd2_kernel<false><<<edge_grid(A.BN, A.P), T, smem, as_stream(stream)>>>(A);
+    const size_t smem = tile_smem_bytes(T, A.P, x_direct == nullptr, x_direct == nullptr, true, false, kDwPad + 2 * kVO + 2);
+    if (x_direct) {
+        opt_in_smem(edgeconv_bwd2_kernel<true>, smem);
+        edgeconv_bwd2_kernel<true><<<edge_grid(A.BN, A.P), T, smem, as_stream(stream)>>>(A);
+    } else {
+        opt_in_smem(edgeconv_bwd2_kernel<false>, smem);
+        edgeconv_bwd2_kernel<false><<<edge_grid(A.BN, A.P), T, smem, as_stream(stream)>>>(A);
+    }
     return check_launch("edgeconv_bwd2_kernel");
 }
 
@@ -756,10 +832,10 @@ extern "C" int hpcs_edgeconv_bwd_stage1_f32(const float* UU, const float* VV, co
                                             float* gUU, float* gVV, void* stream) {
     if (!idx || !coef || !gUU || !gVV || (!gO1 && !G) || (!x_direct && (!UU || !VV)))
         return fail(HPCS_ERR_ARG, "edgeconv_bwd_stage1: null pointer");
-    if (B <= 0 || N <= 0 || k <= 0 || k > 256) return fail(HPCS_ERR_ARG, "edgeconv_bwd_stage1: bad shape");
+    if (B <= 0 || N <= 0 || k <= 0 || k > kMaxTileThreads) return fail(HPCS_ERR_ARG, "edgeconv_bwd_stage1: bad shape");
     Bwd1Args A{UU, VV, reinterpret_cast<const long long*>(idx), coef, x_direct, (long long)B * N, N, k, tile_points(k), gO1, G, gUU, gVV};
     const int T = tile_threads(A.P, k);
-    const size_t smem = sizeof(float) * ((size_t)kWFloats + (size_t)T * kRedStride + (size_t)A.P * kVD);
+    const size_t smem = tile_smem_bytes(T, A.P, true, x_direct == nullptr, true, true, 0);
     if (x_direct) {
         opt_in_smem(edgeconv_bwd1_kernel<true>, smem);
         edgeconv_bwd1_kernel<true><<<edge_grid(A.BN, A.P), T, smem, as_stream(stream)>>>(A);

@@ -120,7 +120,7 @@ class _EdgeConv(torch.autograd.Function):
         gO1 = None
         with torch.cuda.device(dev):
             if stages == 2:
-                gO1 = torch.empty((B * N * k, 64), dtype=torch.float32, device=dev)
+                gO1 = torch.empty(lib.hpcs_edgeconv_scratch_floats(B, N, k), dtype=torch.float32, device=dev)
                 dW2 = torch.zeros((VO, 2, VO), dtype=torch.float32, device=dev)
                 stats1 = torch.zeros((VO, 2), dtype=torch.float64, device=dev)
                 _lib.check(lib.hpcs_edgeconv_bwd_stage2_f32(_lib.ptr(UU), _lib.ptr(VV), idx.data_ptr(), B, N, k, coef.data_ptr(),

@@ -210,11 +210,12 @@ int hpcs_one_hot_f32(const int64_t* y, int64_t rows, int num_classes, float* out
  * hpcs_edgeconv_fwd_f32: stages 1 | 2.  mode 0: stats[21][2] (fp64) += sum r, sum r^2 of the convA norms over all B*N*k
  *   edges; mode 1: same for the convB norms (needs convA's a, b); mode 2: out[B,21,3,N]; with ysum/yrsum != NULL also the
  *   per-point sums [B*N][63] of the coefficients that make the last stage's BatchNorm backward sums a per-point dot product.
- * hpcs_edgeconv_bwd_stage2_f32 (two-stage layers): G[B,21,3,N] = d loss / d out -> gO1[B*N*k][64] (gradient wrt convA's
- *   output per edge), dW2[21][2][21] += (out, {feat, dir}, in), stats1[21][2] (fp64) += sum gy, sum gy rhat of convA.
+ * hpcs_edgeconv_bwd_stage2_f32 (two-stage layers): G[B,21,3,N] = d loss / d out -> gO1 (scratch of hpcs_edgeconv_scratch_floats
+ *   floats, private tile-major layout: the gradient wrt convA's output per edge), dW2[21][2][21] += (out, {feat, dir}, in), stats1[21][2] (fp64) += sum gy, sum gy rhat of convA.
  * hpcs_edgeconv_bwd_stage1_f32: gO1 (or NULL for a one-stage layer: then gO1 = G[n]/k) -> gUU[B*N][128] += (caller zeroes),
  *   gVV[B*N][128] = (floats 63 and 127 of a gVV row are not written); the caller contracts them with x and W4. */
 int hpcs_edgeconv_coef_floats(void);
+size_t hpcs_edgeconv_scratch_floats(int B, int N, int k);   /* floats of the gO1 scratch between the two backward kernels */
 int hpcs_vn_point_linear_f32(const float* x, const float* W4, int B, int C, int N, float* UU, float* VV, void* stream);
 int hpcs_edgeconv_fwd_f32(const float* UU, const float* VV, const int64_t* idx, int B, int N, int k, int stages,
                           const float* coef, const float* x_direct, int mode, double* stats, float* out, float* ysum,
