@@ -52,6 +52,7 @@ SIGNATURES = {
     "hpcs_expmap0_bwd_f32": (_I, [_P, _P, _L, _I, _P, _P]),
     "hpcs_leaves_f32": (_I, [_P, _L, _I, _P, _P, _P]),
     "hpcs_linkage_workspace_bytes": (_Z, [_I, _I, _I, _I]),
+    "hpcs_linkage_debug_counters_offset": (_Z, [_I, _I, _I]),
     "hpcs_linkage_f64": (_I, [_P, _I, _I, _I, _I, _P, _P, _Z, _P]),
     "hpcs_fcluster_maxclust_i32": (_I, [_P, _I, _I, _P, _I, _I, _P, _P]),
     "hpcs_cut_scores_f64": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),

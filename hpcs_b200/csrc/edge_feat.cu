@@ -298,6 +298,32 @@ edge_rev_build_kernel(const int64_t* __restrict__ idx, int N, int k, int* __rest
 // STAGED: the gdiff plane is copied to shared memory (+ a zero at [E] for the ELL sentinel) and, when
 // rows are float4-aligned, the per-float4 partial row sums of (gctr - gdiff) are formed during that same
 // coalesced pass, so both planes are read from HBM exactly once with 128-bit loads.
+// Clouds too large for the per-cloud reverse graph to be built in shared memory (N above ~11000: BASELINE configs[3] goes to
+// 16384): plain scatter.  One thread per point walks its k edges in one (cloud, channel, component) plane pair; the centre
+// part of the gradient is a private row sum, the neighbour part goes out as fp32 reductions on gx (L2 resident: 3C planes of
+// N floats per cloud), which the caller zeroes.  Summation order is whatever the atomics give: results agree to rounding.
+__global__ void __launch_bounds__(256)
+edge_feat_bwd_scatter_kernel(const float* __restrict__ gout, const int64_t* __restrict__ idx, int C, int N, int k,
+                             float* __restrict__ gx) {
+    const int b = blockIdx.z, ch = blockIdx.y;              // ch = c*3 + a
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const size_t E = (size_t)N * k;
+    const float* gb = gout + (size_t)b * 2 * C * 3 * E;
+    const float* g_diff = gb + (size_t)ch * E + (size_t)n * k;
+    const float* g_ctr = gb + ((size_t)C * 3 + ch) * E + (size_t)n * k;
+    const int64_t* row = idx + ((size_t)b * N + n) * k;
+    float* out = gx + ((size_t)b * 3 * C + ch) * N;
+    float self = 0.f;
+    for (int j = 0; j < k; ++j) {
+        const float gd = __ldg(g_diff + j);
+        self += __ldg(g_ctr + j) - gd;
+        const long long m = row[j];
+        if (m >= 0 && m < N) atomicAdd(out + m, gd);
+    }
+    atomicAdd(out + n, self);
+}
+
 template <bool STAGED, bool CROSS>
 __global__ void __launch_bounds__(1024)
 edge_feat_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ x, const int64_t* __restrict__ idx,
@@ -518,7 +544,13 @@ int hpcs_edge_feat_bwd_f32(const float* gout, const float* x, const int64_t* idx
         auto smem_for = [&](int w) { return ((size_t)w * N + (size_t)N + (N + 1) + (N + 2) + N + G + (G + 1)) * sizeof(int); };
         while (nw > 1 && ((size_t)nw * N * sizeof(int) > 128 * 1024 || smem_for(nw) > 220 * 1024)) nw >>= 1;
         const size_t smem = smem_for(nw);
-        if (smem > 220 * 1024) return fail(HPCS_ERR_ARG, "edge_feat_bwd: N=%d too large (max ~11000)", N);
+        if (smem > 220 * 1024) {                             // the reverse graph of one cloud does not fit: scatter with reductions
+            if (cross) return fail(HPCS_ERR_ARG, "edge_feat_bwd: cross features with N=%d (max ~11000)", N);
+            cudaError_t ce = cudaMemsetAsync(gx, 0, sizeof(float) * (size_t)B * 3 * C * N, st);
+            if (ce != cudaSuccess) return fail(HPCS_ERR_CUDA, "edge_feat_bwd: memset: %s", cudaGetErrorString(ce));
+            edge_feat_bwd_scatter_kernel<<<dim3((N + 255) / 256, 3 * C, B), 256, 0, st>>>(gout, idx, C, N, k, gx);
+            return check_launch("edge_feat_bwd_scatter_kernel");
+        }
         cudaFuncSetAttribute(edge_rev_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         edge_rev_build_kernel<<<B, nw * 32, smem, st>>>(idx, N, k, wsi);
         int rc = check_launch("edge_rev_build_kernel");

@@ -18,6 +18,8 @@
 // same merge order as single linkage over hyperbolic similarity (SURVEY.md Finding 2).
 #include <float.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace hpcs {
@@ -74,8 +76,9 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
 template <int PF>
 __global__ void __launch_bounds__(256, 2)
 pdist_mma_kernel(const float* __restrict__ leaves, const double* __restrict__ norms, int N, int D, unsigned d_magic,
-                 double* __restrict__ dm) {
+                 double* __restrict__ dm, const int* __restrict__ gate) {
     extern __shared__ __align__(16) double sm[];
+    if (gate && gate[blockIdx.y] == 0) return;           // exact redo of flagged clouds only (complete linkage, tied distances)
     const int P = D >> 1, S = (P + 3) >> 2;      // feature pairs; slice steps of 4 pairs
     const int rows = 8 * S + 1;                   // staged feature rows (+ the tail row)
     double* as = sm;                              // [rows][kPLD]
@@ -248,7 +251,8 @@ __global__ void __launch_bounds__(1024)
 linkage_kernel(double* dm_all, size_t dm_stride, int pitch, const int* __restrict__ nd_all, int nd_slot,
                const int* __restrict__ rep_all, int rep_stride, int N, int NP2, int* __restrict__ recx_all,
                int* __restrict__ recy_all, double* __restrict__ rech_all, double* __restrict__ Z_all,
-               int* __restrict__ tie_flag, const int* __restrict__ gate) {
+               int* __restrict__ tie_flag, const int* __restrict__ gate, const int* __restrict__ alive_in,
+               const int* __restrict__ rec0_in) {
     extern __shared__ __align__(16) unsigned char raw[];
     __shared__ uint4 scratch[64];
     __shared__ int tie_s;
@@ -257,7 +261,9 @@ linkage_kernel(double* dm_all, size_t dm_stride, int pitch, const int* __restric
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int M = N - 1;
     const int n_nodes = nd_all ? nd_all[b * 8 + nd_slot] : N;       // nodes of the (contracted) matrix
-    const int rec0 = N - n_nodes;                                   // merges already recorded
+    // merges already recorded: single linkage after Boruvka rounds (contracted matrix), or complete linkage after the
+    // parallel reciprocal-nearest-neighbour rounds (same matrix, alive_in marks the clusters that are left)
+    const int rec0 = rec0_in ? rec0_in[b] : N - n_nodes;
     const int* rep = rep_all ? rep_all + (size_t)b * rep_stride : nullptr;
     double* dm = dm_all + (size_t)b * dm_stride;          // mutated by METHOD 1: plain loads only
     int* recx = recx_all + (size_t)b * N;
@@ -274,7 +280,8 @@ linkage_kernel(double* dm_all, size_t dm_stride, int pitch, const int* __restric
 
     unsigned alive = 0u, phase = 0u;
 #pragma unroll
-    for (int c = 0; c < CPT; ++c) if (tid + c * nthr < n_nodes) alive |= 1u << c;
+    for (int c = 0; c < CPT; ++c)
+        if (tid + c * nthr < n_nodes && (!alive_in || alive_in[(size_t)b * N + tid + c * nthr])) alive |= 1u << c;
     auto drop = [&](int col) {                                       // the owner of `col` clears its flag
         const int c = col / nthr;
         if (col - c * nthr == tid) alive &= ~(1u << c);
@@ -323,7 +330,7 @@ linkage_kernel(double* dm_all, size_t dm_stride, int pitch, const int* __restric
         // nearest-neighbour chain with the 'complete' update (scipy's nn_chain), matrix updated in place
         int* chain = reinterpret_cast<int*>(regC);                    // [N]
         int len = 0, x = 0, prev = -1;
-        for (int k = 0; k < M; ++k) {
+        for (int k = rec0_in ? rec0 : 0; k < M; ++k) {
             if (len == 0) {
                 x = first_alive();
                 prev = -1;
@@ -420,7 +427,7 @@ linkage_kernel(double* dm_all, size_t dm_stride, int pitch, const int* __restric
         if (i + 1 < M && A[i] == A[i + 1]) tie_s = 1;                // equal heights: merge order is not unique
     }
     __syncthreads();
-    if (tie_flag && tid == 0) tie_flag[b] = tie_s;
+    if (tie_flag && tid == 0) tie_flag[b] = (rec0_in ? tie_flag[b] : 0) | tie_s;   // (the parallel rounds may have flagged it already)
     // ---- union-find relabel (scipy `label`): ids of the two clusters a merge joins, size of the union --------------
     // The forest lives on the N leaves with union by size, one packed record per leaf {parent, size, cluster id} so
     // that a find that lands on a root has everything after ONE 16-byte load; the cluster id is the leaf id, or N + i
@@ -698,6 +705,207 @@ boruvka_contract_kernel(const double* __restrict__ in_all, size_t in_stride, int
     if (threadIdx.x == 0) { rmw_all[(size_t)b * N + A] = key_value(r); rmj_all[(size_t)b * N + A] = r.idx; }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Complete linkage, parallel: rounds of reciprocal nearest neighbours.
+// ------------------------------------------------------------------------------------------------
+// scipy's nn_chain (what linkage(method='complete') runs, and what linkage_kernel<1> walks step by step) is ~4N dependent
+// row passes.  Complete linkage is reducible: if A and B are each other's nearest neighbours they are merged by the greedy
+// algorithm no matter what happens elsewhere, so ALL reciprocal pairs of a round can merge at once; the Lance-Williams
+// update d(C, A u B) = max(d(C,A), d(C,B)) only ever grows entries, so a cluster whose nearest neighbour was not merged
+// keeps it.  When no two candidate distances of a row tie exactly the nearest neighbours are unique, the hierarchy is the
+// greedy one, and after the stable sort by height + union-find relabel (the tail of linkage_kernel) Z equals scipy's bit
+// for bit.  A row minimum attained twice (duplicate points) flags the cloud; flagged clouds are redone by the serial kernel
+// on a recomputed matrix, in the same call.
+// One thread-block CLUSTER of 8 CTAs per cloud, the whole decode of a cloud in one launch: phases are separated by cluster
+// barriers (release / acquire at cluster scope), shared mutable state is read with L2 loads.  A round:
+//   1. row minima (lexicographic (distance, index)) of the rows whose nearest neighbour was invalidated -- warp per row;
+//   2. reciprocal pairs (x < y): merge record (x, y, d), partner[] marks both ends;
+//   3. row x <- max(row x, row y) (row x is dead after the round: it is the scratch that makes phase 4 race-free);
+//   4. row y and column y <- the scratch; an entry between two clusters merged in this round takes the max over the partner's
+//      scratch entries; rows whose nearest neighbour was x or y are marked for phase 1; x leaves the alive set.
+// Rounds run until one cluster is left or a round finds no pair (NaN rows); linkage_kernel<1> then finishes whatever is
+// left from the alive mask and does the sort + relabel.  About a third of the clusters merge per round on embeddings.
+constexpr int kClusterCtas = 8;
+constexpr int kRoundThreads = 512;
+constexpr int kRoundMaxN = 8192;          // alive / partner snapshots of a cloud live in shared memory
+constexpr int kRoundMlp = 16;             // independent 64-bit loads a lane keeps in flight (the phases are L2-latency chains otherwise)
+
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned cluster_cta_rank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+
+// stop_frac: the rounds stop after a round that merged fewer than stop_frac pairs (a round costs four cluster barriers and a few L2
+// latencies, ~10 us; the serial kernel ~5 us per merge)
+template <int CS>                                      // CTAs per cluster: 8, or 16 (non-portable size) when few clouds are decoded
+__global__ void __launch_bounds__(kRoundThreads)
+complete_rounds_kernel(double* dm_all, int N, int stop_frac, int* __restrict__ alive_all, int* __restrict__ nn_all,
+                       double* __restrict__ nnd_all, int* __restrict__ partner_all, int* __restrict__ rescan_all,
+                       int2* __restrict__ pairs_all, int* __restrict__ cnt_all /*[B][16]: pair counters of even / odd rounds, records, rounds, 6 phase timers (us)*/,
+                       int* __restrict__ recx_all, int* __restrict__ recy_all, double* __restrict__ rech_all, int* __restrict__ tie_all) {
+    __shared__ unsigned char alive_s[kRoundMaxN];      // bit 0: alive, bit 1: needs a new nearest neighbour
+    __shared__ int partner_s[kRoundMaxN];
+    const int b = blockIdx.y;
+    const int rank = (int)cluster_cta_rank();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NW = CS * (kRoundThreads / 32), NT = CS * kRoundThreads;
+    const int gw = rank * (kRoundThreads / 32) + warp, gt = rank * kRoundThreads + threadIdx.x;
+    double* dm = dm_all + (size_t)b * N * N;
+    int* alive = alive_all + (size_t)b * N;
+    int* nn = nn_all + (size_t)b * N;
+    double* nnd = nnd_all + (size_t)b * N;
+    int* partner = partner_all + (size_t)b * N;
+    int* rescan = rescan_all + (size_t)b * N;
+    int2* pairs = pairs_all + (size_t)b * (N / 2 + 1);
+    int* cnt = cnt_all + b * 16;
+    unsigned long long t_mark = 0, t_acc[6] = {0, 0, 0, 0, 0, 0};
+    auto tick = [&](int slot) {
+        if (gt == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (slot >= 0) t_acc[slot] += t - t_mark;
+            t_mark = t;
+        }
+    };
+    int* recx = recx_all + (size_t)b * N;
+    int* recy = recy_all + (size_t)b * N;
+    double* rech = rech_all + (size_t)b * N;
+    for (int i = gt; i < N; i += NT) { alive[i] = 1; rescan[i] = 1; partner[i] = -1; }
+    if (gt == 0) { cnt[0] = cnt[1] = cnt[2] = cnt[3] = 0; tie_all[b] = 0; }
+    cluster_sync_all();
+    int nrec = 0, n_alive = N, round = 0;
+    tick(-1);
+    for (; n_alive > 1; ++round) {
+        for (int i = threadIdx.x; i < N; i += kRoundThreads)                    // this round's alive set and rescan marks
+            alive_s[i] = (unsigned char)((__ldcg(alive + i) ? 1 : 0) | (__ldcg(rescan + i) ? 2 : 0));
+        __syncthreads();
+        tick(0);
+        // ---- 1. nearest neighbour of every row that needs one: warp per row, 8 independent 64-bit loads per lane in flight ----
+        if (gt == 0) cnt[(round + 1) & 1] = 0;
+        for (int i = gw; i < N; i += NW) {
+            if (alive_s[i] != 3) continue;                                      // warp-uniform: alive and marked
+            const double* row = dm + (size_t)i * N;
+            double bv = INFINITY;
+            int bi = kNoIdx;
+            bool tied = false;
+            for (int c0 = lane; c0 < N; c0 += 32 * kRoundMlp) {
+                double v[kRoundMlp];
+#pragma unroll
+                for (int u = 0; u < kRoundMlp; ++u) { const int c = c0 + 32 * u; v[u] = c < N ? __ldcg(row + c) : INFINITY; }
+#pragma unroll
+                for (int u = 0; u < kRoundMlp; ++u) {
+                    const int c = c0 + 32 * u;
+                    if (c < N && c != i && (alive_s[c] & 1)) {
+                        if (v[u] < bv) { bv = v[u]; bi = c; tied = false; }
+                        else if (v[u] == bv) tied = true;
+                    }
+                }
+            }
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(bv);
+            LexKey k{(unsigned)(bits >> 32), (unsigned)bits, bi};
+            const LexKey mine = k;
+            warp_lexmin(k);
+            const bool at_min = mine.hi == k.hi && mine.lo == k.lo && mine.idx != kNoIdx;
+            const bool any_tie = __any_sync(kFull, at_min && (tied || mine.idx != k.idx));
+            if (lane == 0) {
+                nn[i] = k.idx;
+                nnd[i] = key_value(k);
+                rescan[i] = 0;
+                if (any_tie) tie_all[b] = 1;
+            }
+        }
+        tick(1);
+        cluster_sync_all();
+        tick(5);
+        // ---- 2. reciprocal pairs ----------------------------------------------------------------------------------------------
+        for (int i = gt; i < N; i += NT) {
+            if (!(alive_s[i] & 1)) continue;
+            const int j = __ldcg(nn + i);
+            const bool mutual = j != kNoIdx && (alive_s[j] & 1) && __ldcg(nn + j) == i;
+            partner[i] = mutual ? j : -1;
+            if (mutual && i < j) {
+                const int s = atomicAdd(cnt + (round & 1), 1);
+                pairs[s] = make_int2(i, j);
+                recx[nrec + s] = i;
+                recy[nrec + s] = j;
+                rech[nrec + s] = __ldcg(nnd + i);
+            }
+        }
+        tick(2);
+        cluster_sync_all();
+        tick(5);
+        const int np = __ldcg(cnt + (round & 1));
+        if (np == 0) break;                                                     // uniform over the cluster: nothing mergeable is left
+        for (int i = threadIdx.x; i < N; i += kRoundThreads) partner_s[i] = (alive_s[i] & 1) ? __ldcg(partner + i) : -2;   // -2: not alive
+        __syncthreads();
+        // ---- 3. scratch: row x <- max(row x, row y), every column (dead ones are never read again).  Work items are (pair, chunk
+        // of 32 * kRoundMlp columns) so that late rounds with few pairs still spread over all warps of the cluster ------------------
+        const int nchunk = (N + 32 * kRoundMlp - 1) / (32 * kRoundMlp);
+        for (int item = gw; item < np * nchunk; item += NW) {
+            const int p = item / nchunk, c0 = (item - p * nchunk) * 32 * kRoundMlp + lane;
+            const int2 xy = __ldcg(pairs + p);
+            double* rx = dm + (size_t)xy.x * N;
+            const double* ry = dm + (size_t)xy.y * N;
+            double a[kRoundMlp], bb[kRoundMlp];
+#pragma unroll
+            for (int u = 0; u < kRoundMlp; ++u) { const int c = c0 + 32 * u; a[u] = c < N ? __ldcg(rx + c) : 0.0; bb[u] = c < N ? __ldcg(ry + c) : 0.0; }
+#pragma unroll
+            for (int u = 0; u < kRoundMlp; ++u) { const int c = c0 + 32 * u; if (c < N) rx[c] = fmax(a[u], bb[u]); }
+        }
+        tick(3);
+        cluster_sync_all();
+        tick(5);
+        // ---- 4. row y, column y, invalidations -----------------------------------------------------------------------------------
+        for (int item = gw; item < np * nchunk; item += NW) {
+            const int p = item / nchunk, q = item - p * nchunk, c0 = q * 32 * kRoundMlp + lane;
+            const int2 xy = __ldcg(pairs + p);
+            const double* rx = dm + (size_t)xy.x * N;
+            double* ry = dm + (size_t)xy.y * N;
+            double v[kRoundMlp];
+            int nc[kRoundMlp];
+#pragma unroll
+            for (int u = 0; u < kRoundMlp; ++u) {
+                const int c = c0 + 32 * u;
+                v[u] = c < N ? __ldcg(rx + c) : 0.0;
+                nc[u] = c < N ? __ldcg(nn + c) : -1;
+            }
+#pragma unroll
+            for (int u = 0; u < kRoundMlp; ++u) {
+                const int c = c0 + 32 * u;
+                if (c >= N || c == xy.x || c == xy.y) continue;
+                const int pc = partner_s[c];
+                if (pc == -1) {                                                 // an unmerged cluster
+                    ry[c] = v[u];
+                    dm[(size_t)c * N + xy.y] = v[u];
+                    if (nc[u] == xy.x || nc[u] == xy.y) rescan[c] = 1;
+                } else if (pc >= 0 && c > pc) {                                 // the surviving end of another pair of this round
+                    ry[c] = fmax(v[u], __ldcg(rx + pc));
+                }
+            }
+            if (q == 0 && lane == 0) { alive[xy.x] = 0; rescan[xy.y] = 1; }
+        }
+        nrec += np;
+        n_alive -= np;
+        tick(4);
+        cluster_sync_all();
+        tick(5);
+        if (np < stop_frac) { ++round; break; }                                 // hardly anything reciprocal is left: the serial chain finishes
+    }
+    if (gt == 0) {
+        cnt[2] = nrec; cnt[3] = round;
+        for (int q = 0; q < 6; ++q) cnt[4 + q] = (int)(t_acc[q] / 1000);       // microseconds per phase (6 = barriers), diagnostics
+    }
+}
+
+__global__ void gather_rec0_kernel(const int* __restrict__ cnt, int B, int* __restrict__ rec0) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < B) rec0[b] = cnt[16 * b + 2];
+}
+
 static int next_pow2(int v) {
     int p = 1;
     while (p < v) p <<= 1;
@@ -716,8 +924,23 @@ struct LinkWs {
     int pitch[kMaxRounds + 1];        // row pitch (= node capacity) of matrix r
     size_t off_m[kMaxRounds + 1], off_recx, off_recy, off_rech, off_rmw, off_rmj, off_memb, off_moff, off_nd, off_tie, off_norm;
     size_t off_rep[kMaxRounds + 1];
+    bool par_complete;                // complete linkage by parallel reciprocal-nearest-neighbour rounds (N >= 64)
+    size_t off_alive, off_nn, off_nnd, off_partner, off_rescan, off_pairs, off_cnt;
     size_t total;
 };
+
+// Complete linkage: the parallel rounds pay when the GPU is not already full of independent clouds -- one serial CTA per cloud
+// keeps B SMs busy, so from B ~ a quarter of the SMs up the serial kernel is as fast or faster.  Measured (ms per call, serial ->
+// rounds): N = 1024: B = 8 3.08 -> 1.08, B = 32 3.66 -> 2.76, B = 64 4.02 -> 5.14; N = 4096: B = 8 24.8 -> 10.7, B = 64 35.1 -> 57.2;
+// N = 8192, B = 16: 93 -> 77.  A round costs four cluster barriers (~3 us each with the skew between CTAs) and a few L2 latencies.
+static bool use_parallel_complete(int B, int N) {
+    if (N < 64 || N > kRoundMaxN) return false;
+    if (const char* force = getenv("HPCS_COMPLETE_LINKAGE")) {                  // measurement switch: "serial" | "rounds"
+        if (force[0] == 's') return false;
+        if (force[0] == 'r') return true;
+    }
+    return B * 4 <= sm_count();
+}
 
 static LinkWs link_ws(int B, int N, int method) {
     LinkWs L{};
@@ -740,6 +963,17 @@ static LinkWs link_ws(int B, int N, int method) {
         L.off_tie = take((size_t)B * sizeof(int));
         for (int r = 1; r <= L.rounds; ++r) L.off_rep[r] = take((size_t)B * L.pitch[r] * sizeof(int));
     }
+    L.par_complete = method == 1 && use_parallel_complete(B, N);
+    if (L.par_complete) {
+        L.off_alive = take((size_t)B * N * sizeof(int));
+        L.off_nn = take((size_t)B * N * sizeof(int));
+        L.off_nnd = take((size_t)B * N * sizeof(double));
+        L.off_partner = take((size_t)B * N * sizeof(int));
+        L.off_rescan = take((size_t)B * N * sizeof(int));
+        L.off_pairs = take((size_t)B * (N / 2 + 1) * sizeof(int2));
+        L.off_cnt = take((size_t)B * 16 * sizeof(int));
+        L.off_tie = take((size_t)B * sizeof(int));
+    }
     L.total = off;
     return L;
 }
@@ -747,10 +981,11 @@ static LinkWs link_ws(int B, int N, int method) {
 template <int METHOD>
 static void launch_linkage(int cpt, int B, int threads, size_t smem, cudaStream_t st, double* dm, size_t dm_stride, int pitch,
                            const int* nd, int nd_slot, const int* rep, int rep_stride, int N, int NP2, int* recx, int* recy,
-                           double* rech, double* Z, int* tie_flag, const int* gate) {
+                           double* rech, double* Z, int* tie_flag, const int* gate, const int* alive_in = nullptr,
+                           const int* rec0_in = nullptr) {
     auto go = [&](auto kern) {
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        kern<<<B, threads, smem, st>>>(dm, dm_stride, pitch, nd, nd_slot, rep, rep_stride, N, NP2, recx, recy, rech, Z, tie_flag, gate);
+        kern<<<B, threads, smem, st>>>(dm, dm_stride, pitch, nd, nd_slot, rep, rep_stride, N, NP2, recx, recy, rech, Z, tie_flag, gate, alive_in, rec0_in);
     };
     if (cpt == 1) go(linkage_kernel<METHOD, 1>);
     else if (cpt == 2) go(linkage_kernel<METHOD, 2>);
@@ -761,6 +996,13 @@ static void launch_linkage(int cpt, int B, int threads, size_t smem, cudaStream_
 }  // namespace hpcs
 
 extern "C" {
+
+/* diagnostics (tools/decode_rounds.py): byte offset of the per-cloud round counters [B][16] in the workspace, 0 if the parallel
+ * complete-linkage path does not apply */
+size_t hpcs_linkage_debug_counters_offset(int B, int N, int method) {
+    const hpcs::LinkWs L = hpcs::link_ws(B, N, method);
+    return L.par_complete ? L.off_cnt : 0;
+}
 
 size_t hpcs_linkage_workspace_bytes(int B, int N, int D, int method) {
     (void)D;
@@ -796,9 +1038,10 @@ int hpcs_linkage_f64(const float* leaves, int B, int N, int D, int method, doubl
         const size_t smem_mma = ((size_t)2 * S8 * kPLD + 2 * kPT) * sizeof(double);
         if (smem_mma > 200 * 1024) return fail(HPCS_ERR_ARG, "linkage: D=%d too large", D);
         const unsigned d_magic = 0xFFFFFFFFu / (unsigned)D + 1u;                 // e / D == umulhi(e, magic) for e < 2^16
+        const int* pdist_gate = nullptr;
         auto go = [&](auto kern) {
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_mma);
-            kern<<<dim3(T, B), 256, smem_mma, st>>>(leaves, norms, N, D, d_magic, dm);
+            kern<<<dim3(T, B), 256, smem_mma, st>>>(leaves, norms, N, D, d_magic, dm, pdist_gate);
         };
         if (D <= 32) go(pdist_mma_kernel<8>);
         else if (D <= 64) go(pdist_mma_kernel<16>);
@@ -809,6 +1052,58 @@ int hpcs_linkage_f64(const float* leaves, int B, int N, int D, int method, doubl
     const int cpt0 = N <= 512 ? 1 : N <= 2048 ? 2 : N <= 4096 ? 4 : 8;
     const int threads0 = ((N + cpt0 - 1) / cpt0 + 31) / 32 * 32;
     const size_t stride0 = (size_t)N * N;
+    if (L.par_complete) {
+        // ---- complete linkage: parallel reciprocal-nearest-neighbour rounds (one 8-CTA cluster per cloud), the serial kernel for
+        // whatever is left + sort + relabel, and an exact serial redo (on a recomputed matrix) of clouds with tied distances ----
+        int* alive = reinterpret_cast<int*>(w + L.off_alive);
+        int* cnt = reinterpret_cast<int*>(w + L.off_cnt);
+        int* tie = reinterpret_cast<int*>(w + L.off_tie);
+        cudaLaunchConfig_t cfg = {};
+        const int cs = kClusterCtas;                                            // (16-CTA clusters measured slower: 1.70 vs 1.24 ms at B = 8)
+        cfg.gridDim = dim3(cs, B);
+        cfg.blockDim = dim3(kRoundThreads);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cs;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t ce;
+        int* nn_p = reinterpret_cast<int*>(w + L.off_nn);
+        double* nnd_p = reinterpret_cast<double*>(w + L.off_nnd);
+        int* partner_p = reinterpret_cast<int*>(w + L.off_partner);
+        int* rescan_p = reinterpret_cast<int*>(w + L.off_rescan);
+        int2* pairs_p = reinterpret_cast<int2*>(w + L.off_pairs);
+        if (cs == 16) {
+            cudaFuncSetAttribute(complete_rounds_kernel<16>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            ce = cudaLaunchKernelEx(&cfg, complete_rounds_kernel<16>, dm, N, 3, alive, nn_p, nnd_p, partner_p, rescan_p, pairs_p, cnt, recx, recy, rech, tie);
+        } else {
+            ce = cudaLaunchKernelEx(&cfg, complete_rounds_kernel<8>, dm, N, 3, alive, nn_p, nnd_p, partner_p, rescan_p, pairs_p, cnt, recx, recy, rech, tie);
+        }
+        if (ce != cudaSuccess) return fail(HPCS_ERR_CUDA, "complete_rounds_kernel: %s", cudaGetErrorString(ce));
+        if ((rc = check_launch("complete_rounds_kernel"))) return rc;
+        // rec0 of cloud b lives at cnt[4 b + 2]: hand the kernel a strided view by pointing at element 2 with stride 4 ... the
+        // kernel indexes rec0_in[b], so compact it first (B ints)
+        int* rec0 = reinterpret_cast<int*>(w + L.off_partner);                   // partner[] is dead after the rounds
+        gather_rec0_kernel<<<(B + 255) / 256, 256, 0, st>>>(cnt, B, rec0);
+        if ((rc = check_launch("gather_rec0_kernel"))) return rc;
+        launch_linkage<1>(cpt0, B, threads0, smem_link, st, dm, stride0, N, nullptr, 0, nullptr, 0, N, NP2, recx, recy, rech, Z, tie, nullptr, alive, rec0);
+        if ((rc = check_launch("linkage_kernel"))) return rc;
+        {
+            const int S8 = 8 * ((D / 2 + 3) / 4) + 1;
+            const size_t smem_mma = ((size_t)2 * S8 * kPLD + 2 * kPT) * sizeof(double);
+            const unsigned d_magic = 0xFFFFFFFFu / (unsigned)D + 1u;
+            if (D <= 32) pdist_mma_kernel<8><<<dim3(T, B), 256, smem_mma, st>>>(leaves, norms, N, D, d_magic, dm, tie);
+            else if (D <= 64) pdist_mma_kernel<16><<<dim3(T, B), 256, smem_mma, st>>>(leaves, norms, N, D, d_magic, dm, tie);
+            else pdist_mma_kernel<0><<<dim3(T, B), 256, smem_mma, st>>>(leaves, norms, N, D, d_magic, dm, tie);
+            if ((rc = check_launch("pdist_mma_kernel(redo)"))) return rc;
+        }
+        launch_linkage<1>(cpt0, B, threads0, smem_link, st, dm, stride0, N, nullptr, 0, nullptr, 0, N, NP2, recx, recy, rech, Z, nullptr, tie);
+        return check_launch("linkage_kernel(redo)");
+    }
     if (L.rounds == 0) {
         if (method == 0) launch_linkage<0>(cpt0, B, threads0, smem_link, st, dm, stride0, N, nullptr, 0, nullptr, 0, N, NP2, recx, recy, rech, Z, nullptr, nullptr);
         else launch_linkage<1>(cpt0, B, threads0, smem_link, st, dm, stride0, N, nullptr, 0, nullptr, 0, N, NP2, recx, recy, rech, Z, nullptr, nullptr);

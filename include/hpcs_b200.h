@@ -158,6 +158,10 @@ int hpcs_expmap0_bwd_f32(const float* gy, const float* u, int64_t rows, int D, f
  *   cloud; the B clouds are processed by one launch sequence. */
 int hpcs_leaves_f32(const float* x, int64_t rows, int D, const float* scale, float* leaves, void* stream);
 size_t hpcs_linkage_workspace_bytes(int B, int N, int D, int method);
+/* diagnostics: byte offset, inside the workspace, of the [B][16] int counters the parallel complete-linkage rounds leave behind
+ * ({-, -, merges, rounds, microseconds in: snapshot, row minima, pairing, scratch rows, row/column update, barriers}); 0 when
+ * that path does not apply to the shape */
+size_t hpcs_linkage_debug_counters_offset(int B, int N, int method);
 int hpcs_linkage_f64(const float* leaves, int B, int N, int D, int method, double* Z,
                      void* ws, size_t ws_bytes, void* stream);
 

@@ -221,6 +221,25 @@ def test_edge_backward_persistent_gather(hb, B, C, N, k, dups):
         assert torch.equal(got, hgraph.edge_features_backward(gout, x, idx))
 
 
+@pytest.mark.parametrize("B,C,N,k", [(1, 2, 16384, 40), (2, 1, 12000, 10), (1, 21, 16384, 20)])
+def test_edge_backward_beyond_the_shared_memory_reverse_graph(hb, B, C, N, k):
+    """BASELINE configs[3] reaches N=16384, k=40: the per-cloud reverse graph no longer fits shared memory (N > ~11000), the
+    backward scatters with fp32 reductions instead (round 1 returned HPCS_ERR_ARG here).  Also the kNN + forward at that size."""
+    gen = torch.Generator(device="cuda").manual_seed(N + k)
+    x = torch.randn(B, C, 3, N, device="cuda", generator=gen)
+    idx = hb.knn(x.view(B, 3 * C, N), k)
+    assert tuple(idx.shape) == (B, N, k) and int(idx.min()) >= 0 and int(idx.max()) < N
+    from hpcs_b200 import graph as hgraph
+    gout = torch.randn(B, 2 * C, 3, N, k, device="cuda", generator=gen)
+    got = hgraph.edge_features_backward(gout, x, idx)
+    want = _edge_bwd_reference_fp64(gout, idx, C)
+    assert rel_err(got, want) < 1e-5
+    xr = x.clone().requires_grad_(True)                                      # and through autograd / the public function
+    out = hb.get_graph_feature(xr, k, idx=idx)
+    (g2,) = torch.autograd.grad(out, xr, gout)
+    assert rel_err(g2, want) < 1e-5
+
+
 def test_edge_backward_prebuilt_reverse_graph_and_graph_capture(hb):
     """The autograd path builds the reverse graph during the forward, on a second stream (hpcs_edge_rev_build), and the
     backward only gathers (hpcs_edge_feat_bwd_prebuilt_f32): same bits as the one-call backward, also when the whole
@@ -567,6 +586,34 @@ def test_linkage_boruvka_path_ties_and_clusters(hb):
         Z, leaves = hb.decode_linkage_batch(dev(xs), scale, "single", return_leaves=True)
         for b in range(2):
             _check_Z(Z[b].cpu().numpy(), linkage(leaves[b].cpu().numpy(), method="single", metric="cosine"))
+
+
+def test_complete_linkage_parallel_rounds_ties_clusters_sizes(hb):
+    """Complete linkage (what the reference ships) runs parallel reciprocal-nearest-neighbour rounds from N = 64 up; clouds with
+    exactly tied distances (duplicate points) are flagged by the rounds and redone by the serial NN-chain kernel on a recomputed
+    matrix.  Z must equal scipy's bit for bit either way: tied clouds next to clean ones, clustered embeddings (few, large
+    merges at the top), sizes around the threshold and around the 8-CTA work split, N = 2048 and 4096."""
+    from scipy.cluster.hierarchy import linkage
+    gen = torch.Generator().manual_seed(23)
+    cen = torch.randn(6, 32, generator=gen)
+    x = O.expmap0(cen[torch.randint(0, 6, (5, 500), generator=gen)] + 0.15 * torch.randn(5, 500, 32, generator=gen))
+    x[1, 10] = x[1, 3]; x[1, 377] = x[1, 3]; x[1, 50] = x[1, 51]              # cloud 1: exact distance ties
+    x[3, 200:230] = x[3, 100:130]                                            # cloud 3: thirty duplicate pairs
+    x[4] = x[4, torch.randint(0, 500, (500,), generator=gen)]                # cloud 4: sampled with replacement, like the datasets
+    scale = dev(torch.tensor([0.2]))
+    Z, leaves = hb.decode_linkage_batch(dev(x), scale, "complete", return_leaves=True)
+    for b in range(5):
+        _check_Z(Z[b].cpu().numpy(), linkage(leaves[b].cpu().numpy(), method="complete", metric="cosine"))
+    for n, B in ((63, 2), (64, 3), (65, 2), (255, 2), (513, 2), (2048, 2), (4096, 1)):
+        xs = O.expmap0(torch.randn(B, n, 32, generator=gen))
+        Z, leaves = hb.decode_linkage_batch(dev(xs), scale, "complete", return_leaves=True)
+        for b in range(B):
+            _check_Z(Z[b].cpu().numpy(), linkage(leaves[b].cpu().numpy(), method="complete", metric="cosine"))
+    # a degenerate cloud: a zero row has NaN cosine distances; the call must still return (no hang)
+    xz = O.expmap0(torch.randn(1, 100, 32, generator=gen))
+    xz[0, 7] = 0
+    Zz = hb.decode_linkage_batch(dev(xz), scale, "complete")
+    assert Zz.shape == (1, 99, 4)
 
 
 def test_fcluster_maxclust_matches_scipy(hb):
