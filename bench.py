@@ -54,10 +54,10 @@ MIN_TIMED_MS = 250.0                   # the timed region replays the step until
 LOSS_FLOP_PER_TRIPLET = 2 * 303.2 + 123.5 + 140.4
 
 
-# DRAM bytes per op from the committed `ncu --set full` capture (profiles/r01_d_ncu_full.md): read + written,
-# summed over the op's kernels (edge bwd = reverse-graph build 5.3 MB + gather 332.9 + 9.8 MB; edge fwd 13.5 + 273.0 MB,
-# below the algorithmic 343.8 MB because the tail of the output is still in L2 when the kernel ends)
-NCU_TRAFFIC_BYTES = {"edge_bwd_c21": 348.0e6, "edge_bwd_gather_c21": 343.9e6, "edge_fwd_c21": 288.1e6}
+# DRAM bytes per op from the committed `ncu --set full` capture (profiles/r02_ncu_full.md): read + written per launch
+# (edge bwd gather 333.0 + 8.8..11.2 MB; edge fwd 13.5 + 272.5 MB, below the algorithmic 343.8 MB because the tail of the
+# output is still in L2 when the kernel ends; + the reverse-graph build 5.3 MB for the two-kernel backward)
+NCU_TRAFFIC_BYTES = {"edge_bwd_c21": 348.3e6, "edge_bwd_gather_c21": 343.0e6, "edge_fwd_c21": 286.0e6}
 
 
 def peaks():
@@ -368,6 +368,10 @@ def run_native(args):
     #   "points_only": like "device", but the layer inputs and embeddings (activations of device-resident layers in the real
     #            model, synthetic stand-ins here) are not re-uploaded: the host->device traffic of an actual training step.
     pin = {k: host[k].pin_memory() for k in ("pts", "f1", "f2", "emb")}
+    # what the data loader hands a training step: un-rotated clouds [B,N,3] and (drawn on the host like the reference does) the
+    # randn(B,4) of the SO(3) rotation; the rotation + transpose run on the device (row f-4)
+    raw_pin = host["pts"].view(B, 3, N_PTS).transpose(1, 2).contiguous().pin_memory()
+    rot_pin = torch.randn(B, 4, generator=torch.Generator().manual_seed(77 + rank)).pin_memory()
     trip_pin = tuple(t.to(torch.int32).pin_memory() for t in trip_host)       # int32 indices: half the upload
     order_host, seg_host, T0_plan = hb.triplet_plan(host["labels"], T_PER_ANCHOR, 0.0)   # from the host-side labels, like the host sampler
     order_pin, seg_pin = order_host.pin_memory(), seg_host.pin_memory()
@@ -387,14 +391,18 @@ def run_native(args):
         else:
             ups.update(ta=trip_pin[0], tp=trip_pin[1], tn=trip_pin[2])
         resident = {}
-        if variant == "points_only":                     # what a real step takes from the host: the clouds and the plan
+        if variant == "points_only":                     # what a real step takes from the host: the clouds, the rotation draws, the plan
             for k in ("f1", "f2", "emb"):
                 resident[k] = ups.pop(k)
+            ups.pop("pts")
+            ups.update(pts_raw=raw_pin, rot=rot_pin)
         h2d = sum(v.numel() * v.element_size() for v in ups.values())
 
         samp_state = hb.sampler_state(1234 + rank, dev)     # (seed, step) on the device: every replay draws new triplets
 
         def step_of(inp):
+            if variant == "points_only":                 # rotate + transpose on the device, then the step proper
+                inp = dict(inp, pts=hb.rotate_points(inp["pts_raw"], "so3", inp["rot"]).view(B, 1, 3, N_PTS))
             if variant in ("device", "points_only"):
                 tr = hb.sample_triplets_device(None, plan=(inp["order"], inp["seg"], T0_plan), state=samp_state)
             else:
@@ -515,7 +523,7 @@ def run_native(args):
     top = max(single, key=lambda n: ops[n]["share"])
     roofline = {"kernel": top, "bound": ops[top]["bound"], "achieved": ops[top]["achieved"], "peak": ops[top]["peak"],
                 "unit": ops[top]["unit"], "frac": ops[top]["frac"], "traffic": NCU_TRAFFIC_BYTES.get(top),
-                "traffic_source": "profiles/r01_d_ncu_full.md (dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+                "traffic_source": "profiles/r02_ncu_full.md (dram__bytes_read.sum + dram__bytes_write.sum per launch)",
                 "algorithmic_bytes": work[top].get("bytes"), "peak_source": pk["source"]}
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -533,13 +541,16 @@ def run_native(args):
                    "ops_timing": "each op captured into its own CUDA graph, replayed steps x batches_per_step times between CUDA events, after the timed region; edge_bwd_c21 = edge_rev_build + edge_bwd_gather_c21 (listed separately as well)",
                    "e2e_pipeline": "2 device buffer sets; upload / compute / download on 3 streams",
                    "overlap": "the reverse graph of each layer's backward is built on a second stream during that layer's forward"},
-        "e2e": {"value": e2e_dev["value"], "unit": UNIT, "h2d_bytes_per_step": e2e_dev["h2d_bytes_per_step"],
-                "d2h_bytes_per_step": e2e_dev["d2h_bytes_per_step"],
-                "inputs": "points, layer inputs, embeddings, sampling plan (label-sorted order + segments); triplets drawn on the GPU inside the step"},
+        "e2e": {"value": e2e_pts["value"], "unit": UNIT, "h2d_bytes_per_step": e2e_pts["h2d_bytes_per_step"],
+                "d2h_bytes_per_step": e2e_pts["d2h_bytes_per_step"],
+                "inputs": "what a training step takes from the host, every batch, from pinned memory: the un-rotated clouds [B,N,3], the "
+                          "rotation draws randn(B,4), the sampling plan (label-sorted order + segments).  Rotation + transpose run on the "
+                          "device (row f-4), the triplets are drawn on the GPU inside the step (fresh per replay); the 63-d layer inputs and "
+                          "the embeddings are activations of device-resident layers in a real step (synthetic stand-ins here) and stay in "
+                          "HBM.  Results read back every batch: loss, kept, d scale"},
+        "e2e_all_inputs_uploaded": dict({k: e2e_dev[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")},
+                                        note="conservative variant (round 1's headline): the layer inputs and embeddings are re-uploaded every batch too"),
         "e2e_host_sampled_triplets": {k: e2e_host[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")},
-        "e2e_points_only": dict({k: e2e_pts[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")},
-                                note="only what the reference's training step takes from the host goes up (point clouds + sampling plan); "
-                                     "the 63-d layer inputs and the embeddings, which device-resident layers produce there, stay in HBM"),
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
@@ -548,11 +559,15 @@ def run_native(args):
         "decode": decode_rec,
         "edgeconv": edgeconv_rec,
         "loss": loss_val,
-        "e2e_loss": e2e_host["loss"],
-        "e2e_loss_device_sampler": e2e_dev["loss"],
+        "e2e_loss": e2e_pts["loss"],
+        "e2e_loss_host_sampled": e2e_host["loss"],
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_pass(steps=1, warmup=0)        # bounded: one 32-cloud step, 10-25 s of CPU work
+        try:
+            line["torch_gpu_baseline"] = torch_gpu_reference_pass(dev, B)
+        except RuntimeError as exc:                                         # e.g. out of memory for the dense matrices: say so
+            line["torch_gpu_baseline"] = {"unavailable": str(exc)[:200]}
     print(json.dumps(line), flush=True)
 
 
@@ -841,6 +856,47 @@ def cpu_reference_pass(steps, warmup, B=None):
             "sample": f"{B} clouds x {N_PTS} pts ({B * N_PTS * T_PER_ANCHOR} mined triplets) per step, "
                       f"oracle restatement of the reference PyTorch path, torch CPU threads={cores}",
             "s_per_step": round(dt, 3)}
+
+
+def torch_gpu_reference_pass(dev, B, steps=2, warmup=1):
+    """The reference's PyTorch composition of the path (the oracle's restatement of it: topk kNN over the [B,N,N] matrix,
+    gather / cat / permute edge features, dense [n,n] similarity matrices in the miner's filter and in compute_hyp, three
+    hyp_lca chains) executed ON THE SAME GPU, same batch, fp32, autograd backward.  A reported baseline next to the CPU one:
+    it answers 'what would the reference's own code do on this B200' -- it is still the port, not the unmodified repo."""
+    from oracle import hpcs_oracle as O
+    host = synth_inputs(B, seed=0)
+    torch.manual_seed(1000)
+    trip = tuple(t.to(dev) for t in O.sample_triplets(host["labels"], T_PER_ANCHOR, 0.0))
+    xs = [host[k].to(dev) for k in ("pts", "f1", "f2")]
+    emb0 = host["emb"].to(dev)
+    gen = torch.Generator(device=dev).manual_seed(0)
+    gs = [torch.randn(B, 2 * c, 3, N_PTS, K_NN, device=dev, generator=gen) for c in (1, C_FEAT, C_FEAT)]
+    scale = torch.tensor([SCALE], device=dev, requires_grad=True)
+
+    def one():
+        for x, g in zip(xs, gs):
+            xr = x.clone().requires_grad_(True)
+            torch.autograd.grad(O.graph_feature(xr, K_NN), xr, g)
+        emb = emb0.clone().requires_grad_(True)
+        a, p, n = O.filter_triplets(emb.detach(), *trip)
+        torch.autograd.grad(O.compute_hyp(emb, a, p, n, scale, TEMPERATURE), (emb, scale))
+
+    for _ in range(warmup):
+        one()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.reset_peak_memory_stats(dev)
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    out = {"value": round(B / (ms * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms, 2), "kind": "port", "device": "cuda (same B200)",
+           "peak_mem_gb": round(torch.cuda.max_memory_allocated(dev) / 1e9, 1),
+           "sample": f"{B} clouds x {N_PTS} pts, oracle restatement of the reference's PyTorch ops run on the GPU (torch {torch.__version__}), {steps} steps"}
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_reference(args):

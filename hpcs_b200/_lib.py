@@ -61,6 +61,7 @@ SIGNATURES = {
     "hpcs_edgeconv_coef_floats": (_I, []),
     "hpcs_edgeconv_scratch_floats": (_Z, [_I, _I, _I]),
     "hpcs_vn_point_linear_f32": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
+    "hpcs_vn_point_linear_bwd_f32": (_I, [_P, _P, _P, _P, _I, _I, _I, _P, _P, _P]),
     "hpcs_edgeconv_fwd_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P, _P, _P]),
     "hpcs_edgeconv_bwd_stage2_f32": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     "hpcs_edgeconv_bwd_stage1_f32": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _P]),

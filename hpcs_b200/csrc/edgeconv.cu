@@ -233,6 +233,59 @@ __global__ void __launch_bounds__(256) vn_point_linear_kernel(const float* __res
     }
 }
 
+// ---- backward of the per-point maps ------------------------------------------------------------------------------------
+// gUU / gVV [B*N][128] (gradients wrt the U and V rows) -> gx[B,C,3,N] = sum_m W4[m]^T g_m  and  dW4[4][21][C] += sum over
+// points and components of g_m (x) x.  64 points per block; the block's weight-gradient partials leave as one atomic each.
+constexpr int kPbPts = 64;
+constexpr int kPbStride = 129;                          // odd stride: a warp's 32 points read a column without bank conflicts
+__global__ void __launch_bounds__(256) vn_point_linear_bwd_kernel(const float* __restrict__ gUU, const float* __restrict__ gVV,
+                                                                  const float* __restrict__ x, const float* __restrict__ W4, int C, int N,
+                                                                  float* __restrict__ gx, float* __restrict__ dW4) {
+    extern __shared__ float sm[];
+    float* gs = sm;                                     // [2][kPbPts][129]: rows of gUU, then of gVV
+    float* xs = gs + 2 * kPbPts * kPbStride;            // [3C][kPbPts]
+    float* ws = xs + 3 * C * kPbPts;                    // [4][21][C]
+    const int b = blockIdx.y, n0 = blockIdx.x * kPbPts;
+    const int np = min(kPbPts, N - n0);
+    const size_t row0 = ((size_t)b * N + n0) * kRowF;
+    for (int i = threadIdx.x; i < 2 * kPbPts * kRowF; i += blockDim.x) {
+        const int half = i / (kPbPts * kRowF), r = (i / kRowF) % kPbPts, col = i % kRowF;
+        gs[(half * kPbPts + r) * kPbStride + col] = r < np ? __ldg((half ? gVV : gUU) + row0 + (size_t)r * kRowF + col) : 0.f;
+    }
+    for (int i = threadIdx.x; i < 3 * C * kPbPts; i += blockDim.x) {
+        const int row = i / kPbPts, p = i % kPbPts;
+        xs[i] = p < np ? __ldg(x + ((size_t)b * 3 * C + row) * N + n0 + p) : 0.f;
+    }
+    for (int i = threadIdx.x; i < 4 * kVO * C; i += blockDim.x) ws[i] = W4[i];
+    __syncthreads();
+    // gx: thread -> (point p, input channel ci), all three components; m = 0,1 read the gUU row (feat | dir), m = 2,3 the gVV row
+    for (int t = threadIdx.x; t < kPbPts * C; t += blockDim.x) {
+        const int p = t % kPbPts, ci = t / kPbPts;
+        if (p >= np) continue;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+            const float* g = gs + ((m >> 1) * kPbPts + p) * kPbStride + (m & 1) * 64;
+            for (int o = 0; o < kVO; ++o) {
+                const float w = ws[(m * kVO + o) * C + ci];
+                a0 = fmaf(w, g[3 * o], a0); a1 = fmaf(w, g[3 * o + 1], a1); a2 = fmaf(w, g[3 * o + 2], a2);
+            }
+        }
+        float* dst = gx + ((size_t)b * 3 * C + ci * 3) * N + n0 + p;
+        dst[0] = a0; dst[N] = a1; dst[2 * (size_t)N] = a2;
+    }
+    // dW4[m][o][ci]: thread -> one entry, summed over the block's points and the three components
+    for (int t = threadIdx.x; t < 4 * kVO * C; t += blockDim.x) {
+        const int ci = t % C, mo = t / C, m = mo / kVO, o = mo % kVO;
+        const float* g = gs + (m >> 1) * kPbPts * kPbStride + (m & 1) * 64 + 3 * o;
+        const float* xr = xs + ci * 3 * kPbPts;
+        float acc = 0.f;
+        for (int p = 0; p < np; ++p)
+            acc = fmaf(g[p * kPbStride], xr[p], fmaf(g[p * kPbStride + 1], xr[kPbPts + p], fmaf(g[p * kPbStride + 2], xr[2 * kPbPts + p], acc)));
+        atomicAdd(dW4 + t, acc);
+    }
+}
+
 // ---- per-edge machinery ---------------------------------------------------------------------------------------------
 // One thread per edge; a tile is P consecutive points x their k edges (P*k <= kMaxTileThreads), two CTAs per SM.
 // Shared memory of a CTA: packed coefficients | U rows of the tile's edges (cp.async, 528-byte stride: conflict-free 128-bit
@@ -760,6 +813,20 @@ extern "C" int hpcs_vn_point_linear_f32(const float* x, const float* W4, int B, 
     }
     vn_point_linear_kernel<<<dim3((N + kPlPts - 1) / kPlPts, B), 256, smem, as_stream(stream)>>>(x, W4, C, N, UU, VV);
     return check_launch("vn_point_linear_kernel");
+}
+
+extern "C" int hpcs_vn_point_linear_bwd_f32(const float* gUU, const float* gVV, const float* x, const float* W4, int B, int C, int N,
+                                            float* gx, float* dW4, void* stream) {
+    if (!gUU || !gVV || !x || !W4 || !gx || !dW4) return fail(HPCS_ERR_ARG, "vn_point_linear_bwd: null pointer");
+    if (B <= 0 || B > 65535 || C < 1 || C > 64 || N <= 0) return fail(HPCS_ERR_ARG, "vn_point_linear_bwd: bad shape B=%d C=%d N=%d", B, C, N);
+    const size_t smem = sizeof(float) * ((size_t)2 * kPbPts * kPbStride + (size_t)3 * C * kPbPts + 4 * kVO * C);
+    static thread_local size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        cudaFuncSetAttribute(vn_point_linear_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = smem;
+    }
+    vn_point_linear_bwd_kernel<<<dim3((N + kPbPts - 1) / kPbPts, B), 256, smem, as_stream(stream)>>>(gUU, gVV, x, W4, C, N, gx, dW4);
+    return check_launch("vn_point_linear_bwd_kernel");
 }
 
 template <typename K>

@@ -98,6 +98,11 @@ knn_pack_kernel(const float* __restrict__ x, const float* __restrict__ mu, int D
             float vr = tile[d][r];
             float vc = d < D ? __fsub_rn(vr, h ? m1 : m0) : 0.f;
             if (d == kKP - 1) { vr = -0.5f * nrm[0][r]; vc = -0.5f * nrm[1][r]; }   // column 63 is free (D <= 63)
+            // the tensor cores drop the low 13 mantissa bits of an fp32 operand (truncation: 2^-10 relative per operand);
+            // rounding to nearest TF32 here makes that a no-op and halves the error bound of the safety test (2^-11)
+            unsigned vbits;
+            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(vbits) : "f"(vc));
+            vc = __uint_as_float(vbits);
             xr[row + d] = vr;
             xc[row + d] = vc;
         }
@@ -476,14 +481,14 @@ knn_rerank_kernel(const float* __restrict__ xb /* raw rows xr */, const float* _
     const float rmax2 = __uint_as_float(__ldg(cmax_bits + gridDim.y + b));   // max_j |x_j|^2
     const float ni = sqrtf(__ldg(sqc + gi)), nmax = sqrtf(cmax2);
     const float rsum = sqrtf(sq_i) + sqrtf(rmax2);
-    // |tensor-core score - exact pd/2| <= TF32 truncation of both operands (2^-9 relative per product, summed with
-    // Cauchy-Schwarz) and of the norm column (2^-10 of |c_j|^2/2), + fp32 rounding of x - mu, of both accumulations
+    // |tensor-core score - exact pd/2| <= TF32 rounding of both operands (round-to-nearest in the pack kernel: 2^-11 each, 2^-10
+    // relative per product, summed with Cauchy-Schwarz) and of the norm column (2^-11 of |c_j|^2/2), + fp32 rounding of x - mu, of both accumulations
     // and of the shift (2^-16 and 2^-20 terms are generous), all on the CENTRED data; plus the rounding error
     // of the canonical fp32 arithmetic itself, which works on the RAW data: D-step fma chains for the dot and
     // both norms and two final roundings, |pd_canonical - pd_true| / 2 <= (D + 8) 2^-25 (|x_i| + max|x_j|)^2
     // (taken twice).  A cloud far from the origin relative to its extent fails this test honestly: its
     // canonical order is decided by fp32 rounding, which only the exact kernels reproduce.
-    const float eps = 1.01f * (ni * nmax * (1.f / 512.f + 1.f / 65536.f) + cmax2 * (1.f / 2048.f) +
+    const float eps = 1.01f * (ni * nmax * (1.f / 1024.f + 1.f / 65536.f) + cmax2 * (1.f / 4096.f) +
                                (ni + nmax) * (ni + nmax) * (1.f / 1048576.f) +
                                (float)(D + 8) * rsum * rsum * (1.f / 16777216.f));
     const float quant = fabsf(tau) * exp2f((float)(idx_bits - 22));
@@ -597,7 +602,7 @@ knn_rerank32_kernel(const float* __restrict__ xr, const float* __restrict__ sq, 
     const float ni = sqrtf(__ldg(sqc + gi)), nmax = sqrtf(cmax2);
     const float rsum = sqrtf(sq_i) + sqrtf(rmax2);
     // error bound: see knn_rerank_kernel
-    const float eps = 1.01f * (ni * nmax * (1.f / 512.f + 1.f / 65536.f) + cmax2 * (1.f / 2048.f) +
+    const float eps = 1.01f * (ni * nmax * (1.f / 1024.f + 1.f / 65536.f) + cmax2 * (1.f / 4096.f) +
                                (ni + nmax) * (ni + nmax) * (1.f / 1048576.f) +
                                (float)(D + 8) * rsum * rsum * (1.f / 16777216.f));
     const float qscale = exp2f((float)(idx_bits - 22));

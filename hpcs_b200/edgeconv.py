@@ -133,13 +133,15 @@ class _EdgeConv(torch.autograd.Function):
             _lib.check(lib.hpcs_edgeconv_bwd_stage1_f32(_lib.ptr(UU), _lib.ptr(VV), idx.data_ptr(), B, N, k, coef.data_ptr(),
                                                         _lib.ptr(xd), _lib.ptr(gO1), G.data_ptr(), gUU.data_ptr(), gVV.data_ptr(),
                                                         _lib.stream_ptr(dev)), "hpcs_edgeconv_bwd_stage1_f32")
-        # per-point contractions (B*N points x 4 small maps): gradients wrt x and wrt the first Linear's weights
-        parts = torch.stack([gUU[:, :63], gUU[:, 64:127], gVV[:, :63], gVV[:, 64:127]]).view(4, B, N, VO, 3)
-        gx = torch.einsum("moi,mbnoc->bicn", W4, parts).contiguous() if ctx.needs_input_grad[0] else None
-        dW4 = torch.einsum("mbnoc,bicn->moi", parts, x)
+        # per-point contractions (B*N points x 4 small maps): gradients wrt x and wrt the first Linear's weights, one kernel
+        gx = torch.empty_like(x)
+        dW4 = torch.zeros_like(W4)
+        with torch.cuda.device(dev):
+            _lib.check(lib.hpcs_vn_point_linear_bwd_f32(gUU.data_ptr(), gVV.data_ptr(), x.data_ptr(), W4.data_ptr(), B, C, N,
+                                                        gx.data_ptr(), dW4.data_ptr(), _lib.stream_ptr(dev)), "hpcs_vn_point_linear_bwd_f32")
         dwf1 = torch.cat([dW4[0] - dW4[2], dW4[2]], dim=1)
         dwd1 = torch.cat([dW4[1] - dW4[3], dW4[3]], dim=1)
-        return (gx, None, dwf1, dwd1, grads["g1"], grads["b1"], grads.get("wf2"), grads.get("wd2"),
+        return (gx if ctx.needs_input_grad[0] else None, None, dwf1, dwd1, grads["g1"], grads["b1"], grads.get("wf2"), grads.get("wd2"),
                 grads.get("g2") if stages == 2 else None, grads.get("b2") if stages == 2 else None, None, None, None, None)
 
 

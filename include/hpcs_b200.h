@@ -221,6 +221,9 @@ int hpcs_one_hot_f32(const int64_t* y, int64_t rows, int num_classes, float* out
 int hpcs_edgeconv_coef_floats(void);
 size_t hpcs_edgeconv_scratch_floats(int B, int N, int k);   /* floats of the gO1 scratch between the two backward kernels */
 int hpcs_vn_point_linear_f32(const float* x, const float* W4, int B, int C, int N, float* UU, float* VV, void* stream);
+/* its backward: gUU, gVV [B*N][128] -> gx[B,C,3,N] (overwritten) and dW4[4][21][C] += (the caller zeroes it) */
+int hpcs_vn_point_linear_bwd_f32(const float* gUU, const float* gVV, const float* x, const float* W4, int B, int C, int N, float* gx,
+                                 float* dW4, void* stream);
 int hpcs_edgeconv_fwd_f32(const float* UU, const float* VV, const int64_t* idx, int B, int N, int k, int stages,
                           const float* coef, const float* x_direct, int mode, double* stats, float* out, float* ysum,
                           float* yrsum, void* stream);
