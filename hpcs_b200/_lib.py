@@ -58,6 +58,9 @@ SIGNATURES = {
     "hpcs_cut_scores_f64": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "hpcs_rotate_points_f32": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "hpcs_one_hot_f32": (_I, [_P, _L, _I, _P, _P]),
+    "hpcs_edgeconv_bn_fold_f32": (_I, [_P, _L, _P, _P, _P, _P, _P, _F, _F, _I, _P, _I, _P]),
+    "hpcs_edgeconv_bn_sums_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P]),
+    "hpcs_edgeconv_bn_sums_finish_f32": (_I, [_P, _L, _I, _P, _I, _P, _P, _P]),
     "hpcs_edgeconv_coef_floats": (_I, []),
     "hpcs_edgeconv_scratch_floats": (_Z, [_I, _I, _I]),
     "hpcs_vn_point_linear_f32": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),

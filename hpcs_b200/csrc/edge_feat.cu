@@ -536,6 +536,15 @@ int hpcs_edge_feat_bwd_f32(const float* gout, const float* x, const int64_t* idx
     cudaStream_t st = as_stream(stream);
     const size_t E = (size_t)N * k;
     if (!cross && edge_bwd_fast_applicable(gout, N, k)) return edge_bwd_fast_run(gout, idx, B, C, N, k, gx, ws, st);
+    if (!cross) {
+        // beyond the persistent gather (a gradient plane no longer fits shared memory: N*k > ~45000) the plain scatter with fp32
+        // reductions beats the reverse-CSR kernel below (measured, C=21: B=4 N=16384 k=20 1.00 TB/s against 0.49 / 0.19 TB/s of the
+        // CSR kernel at N=4096 / 8192) and has no size limit; the CSR kernel stays for the cross features, which need x.
+        cudaError_t ce = cudaMemsetAsync(gx, 0, sizeof(float) * (size_t)B * 3 * C * N, st);
+        if (ce != cudaSuccess) return fail(HPCS_ERR_CUDA, "edge_feat_bwd: memset: %s", cudaGetErrorString(ce));
+        edge_feat_bwd_scatter_kernel<<<dim3((N + 255) / 256, 3 * C, B), 256, 0, st>>>(gout, idx, C, N, k, gx);
+        return check_launch("edge_feat_bwd_scatter_kernel");
+    }
     int* wsi = static_cast<int*>(ws);
     {
         // warps per CTA: as many private histogram rows as fit in ~128 KB of shared memory
@@ -544,13 +553,7 @@ int hpcs_edge_feat_bwd_f32(const float* gout, const float* x, const int64_t* idx
         auto smem_for = [&](int w) { return ((size_t)w * N + (size_t)N + (N + 1) + (N + 2) + N + G + (G + 1)) * sizeof(int); };
         while (nw > 1 && ((size_t)nw * N * sizeof(int) > 128 * 1024 || smem_for(nw) > 220 * 1024)) nw >>= 1;
         const size_t smem = smem_for(nw);
-        if (smem > 220 * 1024) {                             // the reverse graph of one cloud does not fit: scatter with reductions
-            if (cross) return fail(HPCS_ERR_ARG, "edge_feat_bwd: cross features with N=%d (max ~11000)", N);
-            cudaError_t ce = cudaMemsetAsync(gx, 0, sizeof(float) * (size_t)B * 3 * C * N, st);
-            if (ce != cudaSuccess) return fail(HPCS_ERR_CUDA, "edge_feat_bwd: memset: %s", cudaGetErrorString(ce));
-            edge_feat_bwd_scatter_kernel<<<dim3((N + 255) / 256, 3 * C, B), 256, 0, st>>>(gout, idx, C, N, k, gx);
-            return check_launch("edge_feat_bwd_scatter_kernel");
-        }
+        if (smem > 220 * 1024) return fail(HPCS_ERR_ARG, "edge_feat_bwd: cross features with N=%d (max ~11000)", N);
         cudaFuncSetAttribute(edge_rev_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         edge_rev_build_kernel<<<B, nw * 32, smem, st>>>(idx, N, k, wsi);
         int rc = check_launch("edge_rev_build_kernel");

@@ -233,6 +233,74 @@ __global__ void __launch_bounds__(256) vn_point_linear_kernel(const float* __res
     }
 }
 
+// ---- BatchNorm bookkeeping on the device (one launch instead of ~15 tiny tensor ops per conv) ------------------------------
+// stats[21][2] = sum r, sum r^2 over M norms -> batch mean / biased variance; running buffers updated like nn.BatchNorm2d
+// (unbiased variance, momentum; momentum < 0: cumulative average with the already incremented num_batches_tracked); folded
+// coefficients a, b, mu, rstd written to the coefficient buffer of `stage`.  training == 0: the running buffers are the statistics.
+__global__ void edgeconv_bn_fold_kernel(const double* __restrict__ stats, double M, const float* __restrict__ gamma,
+                                        const float* __restrict__ beta, float* __restrict__ running_mean, float* __restrict__ running_var,
+                                        const long long* __restrict__ num_batches_tracked, float momentum, float eps, int training,
+                                        float* __restrict__ coef, int stage) {
+    const int o = threadIdx.x;
+    if (o >= kVO) return;
+    double mean, var;
+    if (training) {
+        mean = stats[2 * o] / M;
+        var = stats[2 * o + 1] / M - mean * mean;
+        if (var < 0.) var = 0.;
+        if (running_mean) {
+            const double mom = momentum >= 0.f ? (double)momentum : 1.0 / (double)(num_batches_tracked ? *num_batches_tracked : 1);
+            running_mean[o] = (float)((1.0 - mom) * running_mean[o] + mom * mean);
+            running_var[o] = (float)((1.0 - mom) * running_var[o] + mom * var * (M / (M > 1. ? M - 1. : 1.)));
+        }
+    } else {
+        mean = running_mean[o];
+        var = running_var[o];
+    }
+    const float meanf = (float)mean;
+    const float rstd = rsqrtf((float)var + eps);
+    const float a = gamma[o] * rstd;
+    float* c = coef + stage * kOffBn;
+    c[BN_A * kVO + o] = a;
+    c[BN_B * kVO + o] = beta[o] - meanf * a;
+    c[BN_MU * kVO + o] = meanf;
+    c[BN_RSTD * kVO + o] = rstd;
+}
+
+// S1[o] = sum G.ysum / k, S2[o] = sum G.yrsum / k over all points and components (the BatchNorm-backward sums of the last conv):
+// one warp per (cloud, channel-component) row of G, coalesced along n; fp64 accumulation across warps.
+__global__ void __launch_bounds__(256) edgeconv_bn_sums_kernel(const float* __restrict__ G, const float* __restrict__ ysum,
+                                                               const float* __restrict__ yrsum, int B, int N, float inv_k,
+                                                               double* __restrict__ sums /*[21][2], zeroed by the caller*/) {
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= B * kVD) return;
+    const int b = row / kVD, oc = row - b * kVD;
+    const float* g = G + (size_t)row * N;
+    const float* y = ysum + (size_t)b * N * kVD + oc;
+    const float* yr = yrsum + (size_t)b * N * kVD + oc;
+    float s1 = 0.f, s2 = 0.f;
+    for (int n = lane; n < N; n += 32) {
+        const float gv = __ldg(g + n) * inv_k;
+        s1 = fmaf(gv, __ldg(y + (size_t)n * kVD), s1);
+        s2 = fmaf(gv, __ldg(yr + (size_t)n * kVD), s2);
+    }
+    const double d1 = warp_sum((double)s1), d2 = warp_sum((double)s2);
+    if (lane == 0) { atomicAdd(sums + 2 * (oc / 3), d1); atomicAdd(sums + 2 * (oc / 3) + 1, d2); }
+}
+
+// s1m = S1 / M, s2m = S2 / M into the coefficient buffer (training), gradients of the BatchNorm affine out
+__global__ void edgeconv_bn_sums_finish_kernel(const double* __restrict__ sums, double M, int training, float* __restrict__ coef, int stage,
+                                               float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int o = threadIdx.x;
+    if (o >= kVO) return;
+    const double s1 = sums[2 * o], s2 = sums[2 * o + 1];
+    float* c = coef + stage * kOffBn;
+    c[BN_S1M * kVO + o] = training ? (float)(s1 / M) : 0.f;
+    c[BN_S2M * kVO + o] = training ? (float)(s2 / M) : 0.f;
+    dgamma[o] = (float)s2;
+    dbeta[o] = (float)s1;
+}
+
 // ---- backward of the per-point maps ------------------------------------------------------------------------------------
 // gUU / gVV [B*N][128] (gradients wrt the U and V rows) -> gx[B,C,3,N] = sum_m W4[m]^T g_m  and  dW4[4][21][C] += sum over
 // points and components of g_m (x) x.  64 points per block; the block's weight-gradient partials leave as one atomic each.
@@ -827,6 +895,37 @@ extern "C" int hpcs_vn_point_linear_bwd_f32(const float* gUU, const float* gVV, 
     }
     vn_point_linear_bwd_kernel<<<dim3((N + kPbPts - 1) / kPbPts, B), 256, smem, as_stream(stream)>>>(gUU, gVV, x, W4, C, N, gx, dW4);
     return check_launch("vn_point_linear_bwd_kernel");
+}
+
+extern "C" int hpcs_edgeconv_bn_fold_f32(const double* stats, int64_t M, const float* gamma, const float* beta, float* running_mean,
+                                         float* running_var, const int64_t* num_batches_tracked, float momentum, float eps, int training,
+                                         float* coef, int stage, void* stream) {
+    if (!gamma || !beta || !coef || (training && !stats) || (!training && (!running_mean || !running_var)) || stage < 0 || stage > 1 || M <= 0)
+        return fail(HPCS_ERR_ARG, "edgeconv_bn_fold: bad arguments");
+    edgeconv_bn_fold_kernel<<<1, 32, 0, as_stream(stream)>>>(stats, (double)M, gamma, beta, running_mean, running_var,
+                                                             reinterpret_cast<const long long*>(num_batches_tracked), momentum, eps, training, coef, stage);
+    return check_launch("edgeconv_bn_fold_kernel");
+}
+
+extern "C" int hpcs_edgeconv_bn_sums_f32(const float* G, const float* ysum, const float* yrsum, int B, int N, int k, int training, double* sums,
+                                         float* coef, int stage, float* dgamma, float* dbeta, void* stream) {
+    if (!G || !ysum || !yrsum || !sums || !coef || !dgamma || !dbeta || B <= 0 || N <= 0 || k <= 0 || stage < 0 || stage > 1)
+        return fail(HPCS_ERR_ARG, "edgeconv_bn_sums: bad arguments");
+    cudaStream_t st = as_stream(stream);
+    cudaError_t ce = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * kVO, st);
+    if (ce != cudaSuccess) return fail(HPCS_ERR_CUDA, "edgeconv_bn_sums: memset: %s", cudaGetErrorString(ce));
+    edgeconv_bn_sums_kernel<<<(B * kVD + 7) / 8, 256, 0, st>>>(G, ysum, yrsum, B, N, 1.0f / k, sums);
+    if (int rc = check_launch("edgeconv_bn_sums_kernel")) return rc;
+    edgeconv_bn_sums_finish_kernel<<<1, 32, 0, st>>>(sums, (double)B * N * k, training, coef, stage, dgamma, dbeta);
+    return check_launch("edgeconv_bn_sums_finish_kernel");
+}
+
+/* same finish step for sums that a kernel already accumulated (the first conv's, from hpcs_edgeconv_bwd_stage2_f32) */
+extern "C" int hpcs_edgeconv_bn_sums_finish_f32(const double* sums, int64_t M, int training, float* coef, int stage, float* dgamma, float* dbeta,
+                                                void* stream) {
+    if (!sums || !coef || !dgamma || !dbeta || stage < 0 || stage > 1 || M <= 0) return fail(HPCS_ERR_ARG, "edgeconv_bn_sums_finish: bad arguments");
+    edgeconv_bn_sums_finish_kernel<<<1, 32, 0, as_stream(stream)>>>(sums, (double)M, training, coef, stage, dgamma, dbeta);
+    return check_launch("edgeconv_bn_sums_finish_kernel");
 }
 
 template <typename K>

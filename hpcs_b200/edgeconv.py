@@ -29,13 +29,6 @@ def _coef_buffer(dev) -> torch.Tensor:
     return torch.zeros(_lib.load().hpcs_edgeconv_coef_floats(), dtype=torch.float32, device=dev)
 
 
-def _set_bn(coef, stage, mean, var, gamma, beta, eps):
-    rstd = torch.rsqrt(var + eps)
-    a = gamma * rstd
-    base = stage * _BN
-    coef[base:base + 4 * VO] = torch.cat([a, beta - mean * a, mean, rstd]).to(torch.float32)
-
-
 def _launch_fwd(lib, UU, VV, xd, idx, B, N, k, stages, coef, mode, stats=None, out=None, ysum=None, yrsum=None):
     dev = idx.device
     with torch.cuda.device(dev):
@@ -72,21 +65,17 @@ class _EdgeConv(torch.autograd.Function):
                 coef[_WD:_WD + VO * _WPAD].view(VO, _WPAD)[:, :VO] = wd2
             for s, (gamma, beta) in enumerate(((g1, b1), (g2, b2))[:stages]):
                 rm, rv, nbt = bufs[3 * s:3 * s + 3]
+                stats = None
                 if training:                                         # batch statistics of the norms: one light pass per stage
                     stats = torch.zeros((VO, 2), dtype=torch.float64, device=dev)
                     _launch_fwd(lib, UU, VV, xd, idx, B, N, k, stages, coef, s, stats=stats)
-                    mean = stats[:, 0] / M
-                    var = (stats[:, 1] / M - mean * mean).clamp_min(0)
-                    if rm is not None:                               # nn.BatchNorm2d bookkeeping (momentum None: cumulative average)
-                        if nbt is not None:
-                            nbt.add_(1)
-                        mom = momentum[s] if momentum[s] is not None else 1.0 / nbt.to(torch.float64)
-                        rm.mul_(1 - mom).add_((mom * mean).to(rm.dtype))
-                        rv.mul_(1 - mom).add_((mom * var * (M / max(M - 1, 1))).to(rv.dtype))
-                    mean, var = mean.float(), var.float()
-                else:
-                    mean, var = rm.float(), rv.float()
-                _set_bn(coef, s, mean, var, gamma.float(), beta.float(), eps[s])
+                    if nbt is not None:
+                        nbt.add_(1)
+                # statistics -> folded coefficients (and the nn.BatchNorm2d running-buffer update) in one small launch
+                with torch.cuda.device(dev):
+                    _lib.check(lib.hpcs_edgeconv_bn_fold_f32(_lib.ptr(stats), M, gamma.data_ptr(), beta.data_ptr(), _lib.ptr(rm), _lib.ptr(rv),
+                                                             _lib.ptr(nbt), -1.0 if momentum[s] is None else float(momentum[s]), float(eps[s]),
+                                                             int(training), coef.data_ptr(), s, _lib.stream_ptr(dev)), "hpcs_edgeconv_bn_fold_f32")
             out = torch.empty((B, VO, 3, N), dtype=torch.float32, device=dev)
             need = any(ctx.needs_input_grad)
             ysum = torch.empty((B * N, 3 * VO), dtype=torch.float32, device=dev) if need else None
@@ -107,16 +96,14 @@ class _EdgeConv(torch.autograd.Function):
         coef = coef.clone()
         last = stages - 1
         # BatchNorm backward sums of the last stage: gy is linear in G[n]/k, the per-point coefficient sums were saved
-        Gp = G.permute(0, 3, 1, 2).reshape(B * N, 3 * VO) * (1.0 / k)
-        S1 = (Gp * ysum).view(-1, VO, 3).sum(dim=(0, 2), dtype=torch.float64)
-        S2 = (Gp * yrsum).view(-1, VO, 3).sum(dim=(0, 2), dtype=torch.float64)
-
-        def set_sums(stage, s1, s2):
-            if training:                                             # eval mode: statistics are constants, the mean terms vanish
-                base = stage * _BN + 4 * VO
-                coef[base:base + 2 * VO] = torch.cat([s1 / M, s2 / M]).float()
-        set_sums(last, S1, S2)
-        grads = {"g%d" % (last + 1): S2.float(), "b%d" % (last + 1): S1.float()}
+        sums = torch.empty((VO, 2), dtype=torch.float64, device=dev)
+        dg_last = torch.empty(VO, dtype=torch.float32, device=dev)
+        db_last = torch.empty(VO, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.hpcs_edgeconv_bn_sums_f32(G.data_ptr(), ysum.data_ptr(), yrsum.data_ptr(), B, N, k, int(training), sums.data_ptr(),
+                                                     coef.data_ptr(), last, dg_last.data_ptr(), db_last.data_ptr(), _lib.stream_ptr(dev)),
+                       "hpcs_edgeconv_bn_sums_f32")
+        grads = {"g%d" % (last + 1): dg_last, "b%d" % (last + 1): db_last}
         gO1 = None
         with torch.cuda.device(dev):
             if stages == 2:
@@ -126,10 +113,13 @@ class _EdgeConv(torch.autograd.Function):
                 _lib.check(lib.hpcs_edgeconv_bwd_stage2_f32(_lib.ptr(UU), _lib.ptr(VV), idx.data_ptr(), B, N, k, coef.data_ptr(),
                                                             _lib.ptr(xd), G.data_ptr(), gO1.data_ptr(), dW2.data_ptr(), stats1.data_ptr(),
                                                             _lib.stream_ptr(dev)), "hpcs_edgeconv_bwd_stage2_f32")
-                set_sums(0, stats1[:, 0], stats1[:, 1])
-                grads.update(g1=stats1[:, 1].float(), b1=stats1[:, 0].float(), wf2=dW2[:, 0, :], wd2=dW2[:, 1, :])
+                dg1 = torch.empty(VO, dtype=torch.float32, device=dev)
+                db1 = torch.empty(VO, dtype=torch.float32, device=dev)
+                _lib.check(lib.hpcs_edgeconv_bn_sums_finish_f32(stats1.data_ptr(), M, int(training), coef.data_ptr(), 0, dg1.data_ptr(),
+                                                                db1.data_ptr(), _lib.stream_ptr(dev)), "hpcs_edgeconv_bn_sums_finish_f32")
+                grads.update(g1=dg1, b1=db1, wf2=dW2[:, 0, :], wd2=dW2[:, 1, :])
             gUU = torch.zeros((B * N, ROW), dtype=torch.float32, device=dev)
-            gVV = torch.zeros((B * N, ROW), dtype=torch.float32, device=dev)
+            gVV = torch.empty((B * N, ROW), dtype=torch.float32, device=dev)     # floats 63 / 127 of a row are never read
             _lib.check(lib.hpcs_edgeconv_bwd_stage1_f32(_lib.ptr(UU), _lib.ptr(VV), idx.data_ptr(), B, N, k, coef.data_ptr(),
                                                         _lib.ptr(xd), _lib.ptr(gO1), G.data_ptr(), gUU.data_ptr(), gVV.data_ptr(),
                                                         _lib.stream_ptr(dev)), "hpcs_edgeconv_bwd_stage1_f32")

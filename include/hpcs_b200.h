@@ -76,7 +76,8 @@ int hpcs_edge_feat_fwd_f32(const float* x, const int64_t* idx, int B, int C, int
 size_t hpcs_edge_feat_bwd_workspace_bytes(int B, int N, int k);
 /* 1 when hpcs_edge_feat_bwd_f32 will take the persistent TMA gather for this shape (no cross term, N <= 2048,
  * N*k <= 65535, N*k % 4 == 0, 16-byte aligned gout, at least one N*k plane fits shared memory: N*k <= ~45000); that path sums in a fixed
- * order (bitwise repeatable).  The general path is repeatable up to the placement of equal-degree targets. */
+ * order (bitwise repeatable).  Other shapes (any N) scatter with fp32 reductions: results agree to rounding, not bit for bit
+ * run to run; the cross variant keeps the reverse-CSR gather (N up to ~11000). */
 int hpcs_edge_feat_bwd_is_fast(const float* gout, int N, int k, int cross);
 int hpcs_edge_feat_bwd_f32(const float* gout, const float* x, const int64_t* idx, int B, int C, int N,
                            int k, int cross, float* gx, void* ws, size_t ws_bytes, void* stream);
@@ -218,6 +219,20 @@ int hpcs_one_hot_f32(const int64_t* y, int64_t rows, int num_classes, float* out
  *   floats, private tile-major layout: the gradient wrt convA's output per edge), dW2[21][2][21] += (out, {feat, dir}, in), stats1[21][2] (fp64) += sum gy, sum gy rhat of convA.
  * hpcs_edgeconv_bwd_stage1_f32: gO1 (or NULL for a one-stage layer: then gO1 = G[n]/k) -> gUU[B*N][128] += (caller zeroes),
  *   gVV[B*N][128] = (floats 63 and 127 of a gVV row are not written); the caller contracts them with x and W4. */
+/* BatchNorm bookkeeping of a conv on the device (no host round trip of batch statistics):
+ *   hpcs_edgeconv_bn_fold_f32: stats[21][2] (fp64: sum r, sum r^2 over M norms; training) or the running buffers (eval) -> folded
+ *     a, b, mu, rstd in coef for `stage`; in training the running buffers are updated like nn.BatchNorm2d (momentum < 0: cumulative
+ *     average over *num_batches_tracked, which the caller has already incremented).
+ *   hpcs_edgeconv_bn_sums_f32: BatchNorm-backward sums of the LAST conv from G and the forward's ysum / yrsum -> s1m, s2m in coef
+ *     (training), d gamma, d beta; `sums` is fp64 scratch [21][2].  hpcs_edgeconv_bn_sums_finish_f32: the same last step for sums
+ *     accumulated by hpcs_edgeconv_bwd_stage2_f32 (the first conv of a two-conv layer). */
+int hpcs_edgeconv_bn_fold_f32(const double* stats, int64_t M, const float* gamma, const float* beta, float* running_mean,
+                              float* running_var, const int64_t* num_batches_tracked, float momentum, float eps, int training,
+                              float* coef, int stage, void* stream);
+int hpcs_edgeconv_bn_sums_f32(const float* G, const float* ysum, const float* yrsum, int B, int N, int k, int training, double* sums,
+                              float* coef, int stage, float* dgamma, float* dbeta, void* stream);
+int hpcs_edgeconv_bn_sums_finish_f32(const double* sums, int64_t M, int training, float* coef, int stage, float* dgamma, float* dbeta,
+                                     void* stream);
 int hpcs_edgeconv_coef_floats(void);
 size_t hpcs_edgeconv_scratch_floats(int B, int N, int k);   /* floats of the gO1 scratch between the two backward kernels */
 int hpcs_vn_point_linear_f32(const float* x, const float* W4, int B, int C, int N, float* UU, float* VV, void* stream);

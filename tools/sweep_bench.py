@@ -53,8 +53,19 @@ def main():
             (8, 8192, 10), (4, 16384, 20)]
     if args.quick:
         grid = grid[:3]
-    print("| B | N | k | kNN D=3 µs | kNN D=63 µs | path | edge fwd C=21 µs (TB/s) | edge bwd C=21 µs (TB/s) | loss fwd+bwd µs (50 triplets/pt) | checks |")
-    print("|---|---|---|---|---|---|---|---|---|---|")
+    print("| B | N | k | kNN D=3 µs | kNN D=63 µs | path | edge fwd C=21 µs (TB/s) | edge bwd C=21 µs (TB/s) | fused EdgeConv layer (C=21, two convs) fwd eval / fwd+bwd train, µs | loss fwd+bwd µs (50 triplets/pt) | checks |")
+    print("|---|---|---|---|---|---|---|---|---|---|---|")
+    from hpcs_b200.edgeconv import edgeconv
+
+    class Conv(torch.nn.Module):
+        def __init__(self, cin):
+            super().__init__()
+            self.negative_slope = 0.2
+            self.map_to_feat = torch.nn.Linear(cin, 21, bias=False)
+            self.map_to_dir = torch.nn.Linear(cin, 21, bias=False)
+            self.batchnorm = torch.nn.Module()
+            self.batchnorm.bn = torch.nn.BatchNorm2d(21)
+    convs = [Conv(42).to(dev), Conv(21).to(dev)]
     for B, N, k in grid:
         x3 = torch.randn(B, 3, N, device=dev, generator=gen)
         x63 = torch.randn(B, 63, N, device=dev, generator=gen)
@@ -68,9 +79,7 @@ def main():
         # edge features (C = 21): skip shapes whose output would not fit comfortably
         C = 21
         out_bytes = B * 2 * C * 3 * N * k * 4
-        if N > 11000:
-            edge = "— | — (N beyond the general backward's shared-memory limit, ~11000)"
-        elif out_bytes <= 24e9:
+        if out_bytes <= 24e9:
             x = x63.view(B, C, 3, N)
             g = torch.randn(B, 2 * C, 3, N, k, device=dev, generator=gen)
             tf = timed(lambda: hgraph.edge_features_forward(x, i63), reps=5)
@@ -85,10 +94,35 @@ def main():
             ref.index_add_(1, idx0.reshape(-1), g0[:C].reshape(C * 3, N * k))
             err = (gx.reshape(C * 3, N) - ref).abs().max().item() / ref.abs().max().item()
             ok.append("edge" if err < 1e-5 else f"EDGE-ERR {err:.1e}")
-            edge = f"{tf:.0f} ({byt / tf / 1e6:.2f}) | {tb:.0f} ({byt / tb / 1e6:.2f}{'' if fast else ', general path'})"
+            how = "" if fast else ", scatter path"
+            edge = f"{tf:.0f} ({byt / tf / 1e6:.2f}) | {tb:.0f} ({byt / tb / 1e6:.2f}{how})"
             del g, gx
         else:
             edge = "— | —"
+        # the fused layer covers every shape (row gathers from L2, no per-cloud shared-memory structure); eager launches
+        def eager(fn, reps=3):
+            fn(); torch.cuda.synchronize()
+            s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s_.record()
+            for _ in range(reps):
+                fn()
+            e_.record(); torch.cuda.synchronize()
+            return s_.elapsed_time(e_) / reps * 1e3
+        xl = x63.view(B, 21, 3, N)
+        gl = torch.randn(B, 21, 3, N, device=dev, generator=gen)
+        for c_ in convs:
+            c_.eval()
+        with torch.no_grad():
+            tfe = eager(lambda: edgeconv(xl, k, convs[0], convs[1], idx=i63))
+        for c_ in convs:
+            c_.train()
+
+        def layer_step():
+            xr = xl.detach().requires_grad_(True)
+            y = edgeconv(xr, k, convs[0], convs[1], idx=i63)
+            torch.autograd.grad((y * gl).sum(), [xr] + [p_ for c_ in convs for p_ in c_.parameters()])
+        tft = eager(layer_step)
+        fusedcol = f"{tfe:.0f} / {tft:.0f}"
         # loss on n = B*N points (capped), 50 triplets per anchor, device sampler
         n = min(B * N, 65536)
         emb = torch.randn(n, 32, device=dev, generator=gen)
@@ -106,7 +140,7 @@ def main():
             return l
         tl = timed(loss_step, reps=5)
         ok.append("loss" if torch.isfinite(loss_step()) else "LOSS-NAN")
-        print(f"| {B} | {N} | {k} | {t3:.0f} | {t63:.0f} | {path} | {edge} | {tl:.0f} ({T0 / tl:.0f} M triplets/s, n={n}) | {' '.join(ok)} |", flush=True)
+        print(f"| {B} | {N} | {k} | {t3:.0f} | {t63:.0f} | {path} | {edge} | {fusedcol} | {tl:.0f} ({T0 / tl:.0f} M triplets/s, n={n}) | {' '.join(ok)} |", flush=True)
         del x3, x63, emb
         torch.cuda.empty_cache()
 
