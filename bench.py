@@ -342,7 +342,7 @@ def run_native(args):
         for tag, xin in (("gaussian", x63), ("clustered", xclu)):
             st_ = {}
             hb.knn(xin, K_NN, stats=st_)
-            knn_stats[tag] = st_.get("fallback_rows")
+            knn_stats[tag] = {"exact_redo_rows": st_.get("fallback_rows"), "second_chance_rows": st_.get("second_chance_rows")}
         time_op("knn_d63_clustered", lambda: hb.knn(xclu, K_NN), 0)
         time_op("edge_fwd_c1", lambda: hgraph.edge_features_forward(d["pts"], idx3), 1)
         time_op("edge_fwd_c21", lambda: hgraph.edge_features_forward(d["f1"], idx63), 2)

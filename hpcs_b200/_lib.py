@@ -32,6 +32,7 @@ SIGNATURES = {
     "hpcs_knn_f32": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "hpcs_knn_ffma_f32": (_I, [_P, _I, _I, _I, _I, _P, _P, _P, _Z, _P]),
     "hpcs_knn_fallback_rows": (_I, [_P, _Z, _I, _I, _I, _I, _P, _c.POINTER(_c.c_int)]),
+    "hpcs_knn_path_stats": (_I, [_P, _Z, _I, _I, _I, _I, _P, _c.POINTER(_c.c_int)]),
     "hpcs_edge_feat_fwd_f32": (_I, [_P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "hpcs_edge_feat_bwd_workspace_bytes": (_Z, [_I, _I, _I]),
     "hpcs_edge_feat_bwd_is_fast": (_I, [_P, _I, _I, _I]),

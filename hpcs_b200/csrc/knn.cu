@@ -427,7 +427,19 @@ int hpcs_knn_fallback_rows(const void* ws, size_t ws_bytes, int B, int D, int N,
     *rows_host = 0;
     if (!knn_tc_applicable(D, N, k)) return HPCS_OK;
     if (ws_bytes < hpcs_knn_workspace_bytes(B, D, N, k)) return fail(HPCS_ERR_WORKSPACE, "knn_fallback_rows: workspace too small");
-    return knn_tc_fallback_rows(ws, B, D, N, k, as_stream(stream), rows_host);
+    int both[2] = {0, 0};
+    const int rc = knn_tc_fallback_rows(ws, B, D, N, k, as_stream(stream), both);
+    *rows_host = both[0];
+    return rc;
+}
+
+int hpcs_knn_path_stats(const void* ws, size_t ws_bytes, int B, int D, int N, int k, void* stream, int* stats_host) {
+    using namespace hpcs;
+    if (!ws || !stats_host) return fail(HPCS_ERR_ARG, "knn_path_stats: null pointer");
+    stats_host[0] = stats_host[1] = 0;
+    if (!knn_tc_applicable(D, N, k)) return HPCS_OK;
+    if (ws_bytes < hpcs_knn_workspace_bytes(B, D, N, k)) return fail(HPCS_ERR_WORKSPACE, "knn_path_stats: workspace too small");
+    return knn_tc_fallback_rows(ws, B, D, N, k, as_stream(stream), stats_host);
 }
 
 int hpcs_knn_ffma_f32(const float* x, int B, int D, int N, int k, int64_t* idx, float* val, void* ws,

@@ -165,10 +165,21 @@ __device__ __forceinline__ void sort_desc(float (&c)[NV]) {           // bitonic
     }
 }
 
-template <int KL, bool TWO_PASS>
+// MODE 0: one selection pass; 1: two passes (threshold from chunk maxima, then selection); 2: SECOND CHANCE for the rows whose
+// 32-entry list could not be proven (knn_rerank32_kernel leaves thr2[row] = k-th exact value / 2 - error bound there, +inf
+// elsewhere): one pass that appends EVERY candidate whose score reaches the row's threshold to sup[row][..] -- a rigorous
+// superset of the row's true k nearest (a score below the threshold is below the k-th exact value even after the TF32 error) --
+// for knn_rerank_super_kernel to evaluate exactly.  Gated on the device-side counter of unproven rows.
+constexpr int kSupCap = 256;
+
+template <int KL, int MODE>
 __global__ void __launch_bounds__(kTcThreads, 2)
 knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const float* __restrict__ sqc,
-              int N, unsigned keep_mask, float* __restrict__ cand /*[B*N][KL] keys*/, float* __restrict__ tau_out /*[B*N]*/) {
+              int N, unsigned keep_mask, float* __restrict__ cand /*[B*N][KL] keys*/, float* __restrict__ tau_out /*[B*N]*/,
+              const float* __restrict__ thr2, unsigned short* __restrict__ sup, int* __restrict__ supcnt, const int* __restrict__ gate) {
+    constexpr bool TWO_PASS = MODE == 1;
+    constexpr bool SUPER = MODE == 2;
+    if (SUPER && *gate == 0) return;                                   // every row was proven: nothing to collect
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // the 128B-swizzle atoms must start on 1024-byte boundaries of the shared window
     unsigned char* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -305,6 +316,34 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             __syncwarp();                                              // the FIFO reuses the chunk-maxima rows
             v0 = TV;
         }
+        if (SUPER) {
+            // ---- second chance: every candidate whose score reaches the row's threshold goes to the row's list ----
+            const float Ti = i < N ? __ldg(thr2 + (size_t)b * N + i) : INFINITY;
+            unsigned short* mylist = sup + ((size_t)b * N + min(i, N - 1)) * kSupCap;
+            int cnt = 0;
+            for (int v = 0; v < TV; ++v) {
+                ptx::mbar_wait(acc_full + (v & 1), (v >> 1) & 1);
+                ptx::tc_fence_after_sync();
+#pragma unroll 1
+                for (int c0 = 0; c0 < kTN; c0 += 32) {
+                    const int jbase = v * kTN + c0;
+                    if (jbase >= N) break;                             // warp-uniform
+                    float x[32];
+                    ptx::tmem_ld_32x32(trow + (v & 1) * kTN + c0, x);
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) {
+                        if (x[c] - h >= Ti && jbase + c < N) {
+                            if (cnt < kSupCap) mylist[cnt] = (unsigned short)(jbase + c);
+                            ++cnt;
+                        }
+                    }
+                }
+                ptx::tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(epi_done + (v & 1));
+            }
+            if (i < N) supcnt[(size_t)b * N + i] = cnt;
+        } else {
         // ---- selection pass: sorted insert of the scores that pass the threshold(s) ----
         KeyTopK<KL> top;
         top.init();
@@ -372,6 +411,7 @@ knn_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                 bound = fmaxf(bound, tb);
             }
             tau_out[(size_t)b * N + i] = bound;
+        }
         }
     }
     ptx::tc_fence_before_sync();
@@ -519,7 +559,7 @@ __global__ void __launch_bounds__(256)
 knn_rerank32_kernel(const float* __restrict__ xr, const float* __restrict__ sq, const float* __restrict__ sqc,
                     const float* __restrict__ cand, const float* __restrict__ tau_in, const unsigned* __restrict__ cmax_bits, int D, int N,
                     int k, unsigned keep_mask, int idx_bits, int64_t* __restrict__ idx, float* __restrict__ val,
-                    int* __restrict__ fb_list, int* __restrict__ fb_count) {
+                    int* __restrict__ fb_list, int* __restrict__ fb_count, float* __restrict__ thr2) {
     constexpr int RS = kKP + 4;                                        // padded smem row stride
     extern __shared__ __align__(16) float sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -627,12 +667,117 @@ knn_rerank32_kernel(const float* __restrict__ xr, const float* __restrict__ sq, 
         ok = safe_against(tau);
     }
     if (!ok) {
-        if (lane == 0) fb_list[atomicAdd(fb_count, 1)] = (int)gi;
+        // second chance: anything whose tensor-core score is below (k-th exact value so far) / 2 - eps cannot be among the k nearest
+        const float kth = __shfl_sync(kFull, sorted_value(), k - 1);
+        if (lane == 0) {
+            fb_list[atomicAdd(fb_count, 1)] = (int)gi;
+            thr2[gi] = 0.5f * kth - eps;                              // -inf when fewer than k candidates were valid: collect everything
+        }
         return;
     }
+    if (lane == 0) thr2[gi] = INFINITY;
     if (lane < k) {
         idx[gi * k + lane] = (int64_t)(~(unsigned)skey);
         if (val) val[gi * k + lane] = sorted_value();
+    }
+}
+
+// ---- 3b. second chance: exact evaluation of the superset lists ----------------------------------------------------------
+// One warp per unproven row (grid-stride over fb_list).  The row's list (knn_tc_kernel MODE 2) holds every candidate that can
+// still be among its k nearest; they are evaluated 32 at a time with the canonical fp32 chain (rows gathered from L2 like in
+// knn_rerank32_kernel), each batch is sorted and merged into the running best 32 (larger value first, ties -> lower index), and
+// the first k are the answer -- exact, because the list is a superset of the true k nearest.  A list that overflowed its
+// capacity (or holds fewer than k candidates) sends the row on to the exact redo kernels.
+__global__ void __launch_bounds__(256)
+knn_rerank_super_kernel(const float* __restrict__ xr, const float* __restrict__ sq, const unsigned short* __restrict__ sup,
+                        const int* __restrict__ supcnt, int D, int N, int k, const int* __restrict__ fb_list,
+                        const int* __restrict__ fb_count, int64_t* __restrict__ idx, float* __restrict__ val, int* __restrict__ fb2_list,
+                        int* __restrict__ fb2_count) {
+    constexpr int RS = kKP + 4;
+    extern __shared__ __align__(16) float sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* rows = sm + (size_t)warp * (32 * RS + kKP);                 // [32][RS] candidate rows
+    float* qrow = rows + 32 * RS;                                      // [64] query row
+    const int count = *fb_count;
+    const int half = lane >> 4, q4 = lane & 15;
+    float* my_dst = rows + 4 * q4;
+    for (int f = blockIdx.x * 8 + warp; f < count; f += gridDim.x * 8) {
+        const size_t gi = (size_t)fb_list[f];
+        const int b = (int)(gi / N);
+        const int c = supcnt[gi];
+        if (c > kSupCap || c < k) {                                    // warp-uniform
+            if (lane == 0) fb2_list[atomicAdd(fb2_count, 1)] = (int)gi;
+            continue;
+        }
+        const float sq_i = __ldg(sq + gi);
+        __syncwarp();
+        *reinterpret_cast<float2*>(qrow + 2 * lane) = __ldg(reinterpret_cast<const float2*>(xr + gi * kKP) + lane);
+        const float4* xr4 = reinterpret_cast<const float4*>(xr) + (size_t)b * N * (kKP / 4) + q4;
+        unsigned long long best = 0ull;                                // running best 32, sorted descending across the lanes
+        for (int r0 = 0; r0 < c; r0 += 32) {
+            const int cj0 = r0 + lane < c ? (int)sup[gi * kSupCap + r0 + lane] : -1;
+            const int hi = min(32, c - r0);
+            for (int rr0 = 0; rr0 < hi; rr0 += 16) {                   // gather: two rows per warp instruction, eight loads in flight
+                float4 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int rr = rr0 + 2 * u + half;
+                    const int src = __shfl_sync(kFull, cj0, rr & 31);
+                    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rr < hi && src >= 0) v[u] = __ldg(xr4 + src * (kKP / 4));
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int rr = rr0 + 2 * u + half;
+                    if (rr < hi) *reinterpret_cast<float4*>(my_dst + rr * RS) = v[u];
+                }
+            }
+            __syncwarp();
+            float pd0 = -INFINITY;
+            if (cj0 >= 0) {
+                const float* cr = rows + lane * RS;
+                float acc = 0.f;
+                int d = 0;
+                for (; d + 4 <= D; d += 4) {                           // fma chain over d ascending (canonical)
+                    const float4 c4 = *reinterpret_cast<const float4*>(cr + d);
+                    const float4 a4 = *reinterpret_cast<const float4*>(qrow + d);
+                    acc = __fmaf_rn(a4.x, c4.x, acc);
+                    acc = __fmaf_rn(a4.y, c4.y, acc);
+                    acc = __fmaf_rn(a4.z, c4.z, acc);
+                    acc = __fmaf_rn(a4.w, c4.w, acc);
+                }
+                for (; d < D; ++d) acc = __fmaf_rn(qrow[d], cr[d], acc);
+                const float sq_j = -2.f * cr[kKP - 1];
+                pd0 = __fsub_rn(__fmaf_rn(2.f, acc, -sq_i), sq_j);
+            }
+            __syncwarp();
+            const unsigned fb = __float_as_uint(pd0);
+            const unsigned ord = (fb & 0x80000000u) ? ~fb : (fb | 0x80000000u);
+            unsigned long long skey = cj0 >= 0 ? (((unsigned long long)ord << 32) | ~(unsigned)cj0) : 0ull;
+#pragma unroll
+            for (int size = 2; size <= 32; size <<= 1) {               // sort the batch, descending
+#pragma unroll
+                for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                    const unsigned long long other = __shfl_xor_sync(kFull, skey, stride);
+                    const bool want_max = ((lane & stride) == 0) == ((lane & size) == 0);
+                    skey = want_max ? (skey > other ? skey : other) : (skey < other ? skey : other);
+                }
+            }
+            // best 32 of (running, batch): max(best[l], batch[31 - l]) is bitonic and holds them; one bitonic merge sorts it
+            const unsigned long long rev = __shfl_sync(kFull, skey, 31 - lane);
+            best = best > rev ? best : rev;
+#pragma unroll
+            for (int stride = 16; stride > 0; stride >>= 1) {
+                const unsigned long long other = __shfl_xor_sync(kFull, best, stride);
+                const bool want_max = (lane & stride) == 0;
+                best = want_max ? (best > other ? best : other) : (best < other ? best : other);
+            }
+        }
+        if (lane < k) {
+            const unsigned ordv = (unsigned)(best >> 32);
+            idx[gi * k + lane] = (int64_t)(~(unsigned)best);
+            if (val) val[gi * k + lane] = __uint_as_float((ordv & 0x80000000u) ? (ordv & 0x7fffffffu) : ~ordv);
+        }
     }
 }
 
@@ -748,6 +893,9 @@ struct TcLayout {
     float *xc, *xr, *sq, *sqc, *cand, *tau, *mu;
     unsigned* cmax;
     int *fb_count, *fb_list;
+    float* thr2;                   // second chance: per-row score threshold (+inf: row proven)
+    unsigned short* sup;           // [rows][kSupCap] superset lists
+    int *supcnt, *fb2_list, *fb2_count;
     int n_zero;
     size_t bytes;
 };
@@ -764,10 +912,19 @@ static TcLayout tc_layout(void* ws, int B, int D, int N, int KL) {
     L.cand = reinterpret_cast<float*>(p + off); off += align_up(rows * KL * sizeof(float), 256);
     L.tau = reinterpret_cast<float*>(p + off);  off += align_up(rows * sizeof(float), 256);
     L.mu = reinterpret_cast<float*>(p + off);   off += align_up((size_t)B * D * sizeof(float), 256);
-    L.cmax = reinterpret_cast<unsigned*>(p + off);  off += align_up((size_t)(2 * B + 1) * sizeof(unsigned), 256);
-    L.fb_count = reinterpret_cast<int*>(L.cmax + 2 * B);              // [B] centred max, [B] raw max, counter
-    L.n_zero = 2 * B + 1;
+    L.cmax = reinterpret_cast<unsigned*>(p + off);  off += align_up((size_t)(2 * B + 2) * sizeof(unsigned), 256);
+    L.fb_count = reinterpret_cast<int*>(L.cmax + 2 * B);              // [B] centred max, [B] raw max, two counters
+    L.fb2_count = L.fb_count + 1;
+    L.n_zero = 2 * B + 2;
     L.fb_list = reinterpret_cast<int*>(p + off); off += align_up(rows * sizeof(int), 256);
+    L.fb2_list = L.fb_list;
+    L.thr2 = nullptr; L.sup = nullptr; L.supcnt = nullptr;
+    if (KL == 32) {                                                    // second-chance buffers (lists of 32 only)
+        L.fb2_list = reinterpret_cast<int*>(p + off);            off += align_up(rows * sizeof(int), 256);
+        L.thr2 = reinterpret_cast<float*>(p + off);              off += align_up(rows * sizeof(float), 256);
+        L.supcnt = reinterpret_cast<int*>(p + off);              off += align_up(rows * sizeof(int), 256);
+        L.sup = reinterpret_cast<unsigned short*>(p + off);      off += align_up(rows * kSupCap * sizeof(unsigned short), 256);
+    }
     L.bytes = off;
     return L;
 }
@@ -800,13 +957,13 @@ static int run_tc(const float* x, int B, int D, int N, int k, int64_t* idx, floa
                             (6 + 2 * kStages) * sizeof(uint64_t) + 16 + 1024;
         const dim3 grid((N + kTM - 1) / kTM, B);
         if (KL == 32 && N >= 32 * kThrRank) {
-            auto kern = knn_tc_kernel<KL, true>;
+            auto kern = knn_tc_kernel<KL, 1>;
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            kern<<<grid, kTcThreads, smem, st>>>(map_a, map_b, L.sqc, N, keep_mask, L.cand, L.tau);
+            kern<<<grid, kTcThreads, smem, st>>>(map_a, map_b, L.sqc, N, keep_mask, L.cand, L.tau, nullptr, nullptr, nullptr, nullptr);
         } else {
-            auto kern = knn_tc_kernel<KL, false>;
+            auto kern = knn_tc_kernel<KL, 0>;
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            kern<<<grid, kTcThreads, smem, st>>>(map_a, map_b, L.sqc, N, keep_mask, L.cand, L.tau);
+            kern<<<grid, kTcThreads, smem, st>>>(map_a, map_b, L.sqc, N, keep_mask, L.cand, L.tau, nullptr, nullptr, nullptr, nullptr);
         }
         rc = check_launch("knn_tc_kernel");
         if (rc) return rc;
@@ -816,7 +973,7 @@ static int run_tc(const float* x, int B, int D, int N, int k, int64_t* idx, floa
         if (KL == 32) {
             cudaFuncSetAttribute(knn_rerank32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             knn_rerank32_kernel<<<dim3((N + 7) / 8, B), 256, smem, st>>>(L.xr, L.sq, L.sqc, L.cand, L.tau, L.cmax, D, N, k, keep_mask, idx_bits,
-                                                                         idx, val, L.fb_list, L.fb_count);
+                                                                         idx, val, L.fb_list, L.fb_count, L.thr2);
         } else {
             auto kern = knn_rerank_kernel<KL>;
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -826,22 +983,52 @@ static int run_tc(const float* x, int B, int D, int N, int k, int64_t* idx, floa
         rc = check_launch("knn_rerank_kernel");
         if (rc) return rc;
     }
-    // rows that failed the safety test: a short list is redone row by row; a long one (> 1/16 of all rows) means the
-    // canonical order of whole clouds is decided by fp32 rounding, and the all-FFMA path redoes everything instead
+    // rows whose list of 32 could not be proven get a second chance (lists of 32 only): one more Gram pass that collects, per
+    // row, every candidate that can still be among its k nearest, and an exact evaluation of those lists; both launches return
+    // at once when every row was proven.  Tight clusters (many neighbours inside the TF32 error bound) end here, not below.
+    const int* redo_list = L.fb_list;
+    const int* redo_count = L.fb_count;
+    if (KL == 32) {
+        const size_t smem = 2 * (size_t)kAtomBytes + (size_t)kStages * 2 * kAtomB + (size_t)kTcQueue * kTM * sizeof(float) +
+                            (6 + 2 * kStages) * sizeof(uint64_t) + 16 + 1024;
+        auto kern = knn_tc_kernel<KL, 2>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kern<<<dim3((N + kTM - 1) / kTM, B), kTcThreads, smem, st>>>(map_a, map_b, L.sqc, N, keep_mask, nullptr, nullptr, L.thr2, L.sup, L.supcnt,
+                                                                      L.fb_count);
+        if ((rc = check_launch("knn_tc_kernel(second chance)"))) return rc;
+        const size_t smem_r = 8 * ((size_t)32 * (kKP + 4) + kKP) * sizeof(float);
+        cudaFuncSetAttribute(knn_rerank_super_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r);
+        knn_rerank_super_kernel<<<2 * sm_count(), 256, smem_r, st>>>(L.xr, L.sq, L.sup, L.supcnt, D, N, k, L.fb_list, L.fb_count, idx, val,
+                                                                     L.fb2_list, L.fb2_count);
+        if ((rc = check_launch("knn_rerank_super_kernel"))) return rc;
+        redo_list = L.fb2_list;
+        redo_count = L.fb2_count;
+    }
+    // rows still open: a short list is redone row by row; a long one (> 1/16 of all rows) means the canonical order of whole
+    // clouds is decided by fp32 rounding, and the all-FFMA path redoes everything instead
     const int gate = (int)(rows / 16);
     {
         const size_t smem = (64 + (size_t)N) * sizeof(float);
         cudaFuncSetAttribute(knn_fallback_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        knn_fallback_kernel<<<4 * sm_count(), kFbThreads, smem, st>>>(x, L.sq, D, N, k, L.fb_list, L.fb_count, gate, idx, val);
+        knn_fallback_kernel<<<4 * sm_count(), kFbThreads, smem, st>>>(x, L.sq, D, N, k, redo_list, redo_count, gate, idx, val);
         rc = check_launch("knn_fallback_kernel");
         if (rc) return rc;
     }
-    return knn_ffma_gated(x, L.sq, B, D, N, k, idx, val, L.fb_count, gate, st);
+    return knn_ffma_gated(x, L.sq, B, D, N, k, idx, val, redo_count, gate, st);
 }
 
 int knn_tc_fallback_rows(const void* ws, int B, int D, int N, int k, cudaStream_t st, int* out_host) {
     const TcLayout L = tc_layout(const_cast<void*>(ws), B, D, N, tc_list_len(k));
-    cudaError_t e = cudaMemcpyAsync(out_host, L.fb_count, sizeof(int), cudaMemcpyDeviceToHost, st);
+    // out_host[0]: rows that went to the exact redo kernels; out_host[1] (lists of 32): rows that took the second chance
+    int both[2] = {0, 0};
+    cudaError_t e = cudaMemcpyAsync(both, L.fb_count, 2 * sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e == cudaSuccess) {
+        const bool second = tc_list_len(k) == 32;
+        out_host[0] = second ? both[1] : both[0];
+        out_host[1] = second ? both[0] : 0;
+        return HPCS_OK;
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) return fail(HPCS_ERR_CUDA, "knn_tc_fallback_rows: %s", cudaGetErrorString(e));
     return HPCS_OK;

@@ -21,7 +21,8 @@ def knn(x: torch.Tensor, k: int, return_values: bool = False, method: str = "aut
     descending ``-|xi-xj|^2``; exact ties resolve to the lower index (see oracle/knn_canonical.c).
     ``method``: "auto" (tensor-core Gram + exact re-rank where it applies) or "ffma" (all-FFMA exact
     kernel); both give the same bits.  ``stats`` (a dict) receives ``fallback_rows``: rows the
-    tensor-core path had to redo exactly (this synchronises the stream; leave it None on hot paths)."""
+    tensor-core path had to redo with the exact kernels, and ``second_chance_rows``: rows whose 32 candidates could not be
+    proven and were resolved from a superset list instead (this synchronises the stream; leave it None on hot paths)."""
     if x.dim() != 3:
         raise ValueError(f"knn expects x[B,D,N], got {tuple(x.shape)}")
     dev = _lib.require_cuda(x)
@@ -43,11 +44,11 @@ def knn(x: torch.Tensor, k: int, return_values: bool = False, method: str = "aut
                          ws.numel(), _lib.stream_ptr(dev)), "hpcs_knn_f32")
         if stats is not None:
             import ctypes
-            rows = ctypes.c_int(0)
+            both = (ctypes.c_int * 2)(0, 0)
             if method == "auto":
-                _lib.check(lib.hpcs_knn_fallback_rows(ws.data_ptr(), ws.numel(), B, D, N, k, _lib.stream_ptr(dev),
-                                                      ctypes.byref(rows)), "hpcs_knn_fallback_rows")
-            stats["fallback_rows"] = rows.value
+                _lib.check(lib.hpcs_knn_path_stats(ws.data_ptr(), ws.numel(), B, D, N, k, _lib.stream_ptr(dev), both),
+                           "hpcs_knn_path_stats")
+            stats["fallback_rows"], stats["second_chance_rows"] = both[0], both[1]
     idx._hpcs_knn_of = N               # produced here: every entry is in [0, N) (lets get_graph_feature skip its range check)
     return (idx, val) if return_values else idx
 

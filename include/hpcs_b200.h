@@ -64,6 +64,11 @@ int hpcs_knn_ffma_f32(const float* x, int B, int D, int N, int k, int64_t* idx, 
  * HOST pointer. */
 int hpcs_knn_fallback_rows(const void* ws, size_t ws_bytes, int B, int D, int N, int k, void* stream,
                            int* rows_host);
+/* stats_host[2] (HOST): {rows redone by the exact kernels, rows that took the second chance}.  A row whose 32-entry candidate
+ * list cannot be proven (more neighbours inside the TF32 error bound than the list has slack: tight clusters) first gets a
+ * second tensor-core pass that collects every candidate above (k-th exact value)/2 - bound -- a rigorous superset of its true
+ * k nearest -- evaluated exactly; only lists that overflow go on to the exact redo.  Synchronises `stream`. */
+int hpcs_knn_path_stats(const void* ws, size_t ws_bytes, int B, int D, int N, int k, void* stream, int* stats_host);
 
 /* get_graph_feature(x, k, idx)    hpcs/nn/dgcnn/utils/vn_dgcnn_util.py:13-41
  * get_graph_feature_cross         hpcs/nn/dgcnn/utils/vn_dgcnn_util.py:44-69   (cross != 0)

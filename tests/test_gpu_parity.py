@@ -528,6 +528,29 @@ def test_loss_full_size_properties(hb):
     assert abs(got.item() - want.item()) <= REL * abs(want.item())
 
 
+def test_knn_second_chance_on_clustered_features(hb):
+    """Backbone-like features (tight clusters, off-centre, correlated channels): the TF32 error bound exceeds the neighbour
+    spacing inside a cluster, so the 32-entry candidate lists cannot be proven.  Those rows must be resolved by the second
+    tensor-core pass (superset lists + exact evaluation), not by the all-FFMA redo, and stay bit-equal to the canonical
+    oracle.  A cloud that is ONE very tight cluster overflows the lists (capacity 256) and must come out of the exact
+    redo kernels, equal as well."""
+    import bench
+    x = bench.clustered_features(3, seed=5)                                  # [3, 63, 1024]
+    st = {}
+    idx, val = hb.knn(dev(x), 20, return_values=True, stats=st)
+    assert st["second_chance_rows"] > 300 and st["fallback_rows"] == 0, st
+    widx, wval = O.knn_canonical(x, 20, return_values=True)
+    assert torch.equal(idx.cpu(), widx) and torch.equal(val.cpu(), wval)
+    gen = torch.Generator().manual_seed(9)
+    tight = torch.randn(1, 63, 1).expand(1, 63, 700) + 1e-3 * torch.randn(1, 63, 700, generator=gen)
+    tight = torch.cat([tight, torch.randn(1, 63, 324, generator=gen)], dim=2).contiguous()
+    st = {}
+    idx, val = hb.knn(dev(tight), 20, return_values=True, stats=st)
+    assert st["fallback_rows"] > 0, st
+    widx, wval = O.knn_canonical(tight, 20, return_values=True)
+    assert torch.equal(idx.cpu(), widx) and torch.equal(val.cpu(), wval)
+
+
 # ------------------------------------------------------------------------------------------------
 # decode
 # ------------------------------------------------------------------------------------------------
