@@ -23,6 +23,10 @@ def init_from_env(backend: str = None) -> Tuple[int, int, int]:
     if world > 1 and not dist.is_initialized():
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
+        # The one collective of this path is a 5 MB gradient bucket overlapped with persistent one-CTA-per-SM kernels: NCCL's
+        # default channel count takes SMs those kernels are waiting for.  Two channels are enough for a latency-bound message
+        # (measured on 2 x B200: 0.825 ms per batch with the default, 0.806 with 2, 0.841 with 8); an explicit setting wins.
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
         if backend == "nccl":
