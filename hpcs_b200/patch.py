@@ -12,7 +12,8 @@ subclassing can leave a call site on the reference's PyTorch path:
 * **methods** of the reference's own classes (``VN_DGCNN_partseg.forward``: the three graph layers fused, row f-1;
   ``MetricHyperbolicLoss.compute_hyp``,
   ``RandomTripletMarginMiner.mine``, ``ExpMap.forward``, ``MLPExpMap.forward``,
-  ``BaseSimilarityHypHC._decode_linkage``, ``ShapeNetHypHC._forward``, ``PartNetHypHC._forward``): the class object
+  ``BaseSimilarityHypHC._decode_linkage`` and ``.forward`` (batched decode instead of the per-cloud loop),
+  ``ShapeNetHypHC._forward``, ``PartNetHypHC._forward``): the class object
   stays the reference's, so subclasses (``HierarchicalMetricHyperbolicLoss``, the PartNet default), ``isinstance``
   checks, checkpoints and hyper-parameter pickles keep working, and instances created BEFORE ``install()`` switch too.
 
@@ -46,6 +47,24 @@ FUNCTIONS: Dict[Tuple[str, str], object] = {
 def _decode_linkage(self, leaves_embeddings):
     """Bound onto ``BaseSimilarityHypHC`` (hpcs/models/base_hyp_hc.py:81-86)."""
     return decode.decode_linkage(leaves_embeddings, self.metric_hyp_loss.scale, method="complete")
+
+
+def _model_forward(self, batch, testing: bool = False):
+    """Bound onto ``BaseSimilarityHypHC.forward`` (hpcs/models/base_hyp_hc.py:120-140): same calls, same return tuples; the
+    per-cloud Python loop of ``_decode_linkage`` + device-to-host copy (:133-137) is one batched decode, with Z copied to
+    the host once (the list of per-cloud numpy matrices the caller expects)."""
+    points, x_euclidean, x_poincare, pts_labels = self._forward(batch, testing)
+    xe = x_euclidean.contiguous().view(-1, x_euclidean.shape[-1])
+    xp = x_poincare.contiguous().view(-1, x_poincare.shape[-1])
+    losses = self.compute_losses(xe, xp, pts_labels)
+    metrics = {}
+    if hasattr(self.metric_hyp_loss, "loss_cosface"):
+        y_true = pts_labels.contiguous().reshape(-1).long()
+        metrics = {"acc": self.compute_accuracy(xp, y_true), "iou": self.compute_iou(xp, y_true)}
+    if not testing:
+        return losses, metrics
+    Z = decode.decode_linkage_batch(x_poincare, self.metric_hyp_loss.scale, method="complete")
+    return losses, metrics, x_euclidean, x_poincare, list(Z.cpu().numpy()), points, pts_labels
 
 
 def _expmap_forward(self, x):
@@ -88,6 +107,7 @@ METHODS: Dict[Tuple[str, str, str], object] = {
     ("hpcs.nn.hyperbolic.hyp_embed", "MLPExpMap", "forward"): _mlp_expmap_forward,
     ("hpcs.nn.dgcnn.vn_dgcnn_partseg", "VN_DGCNN_partseg", "forward"): edgeconv.vn_dgcnn_partseg_forward,
     ("hpcs.models.base_hyp_hc", "BaseSimilarityHypHC", "_decode_linkage"): _decode_linkage,
+    ("hpcs.models.base_hyp_hc", "BaseSimilarityHypHC", "forward"): _model_forward,
     ("hpcs.models.shapenet_hyp_hc", "ShapeNetHypHC", "_forward"): pipeline.shapenet_forward,
     ("hpcs.models.partnet_hyp_hc", "PartNetHypHC", "_forward"): pipeline.partnet_forward,
 }

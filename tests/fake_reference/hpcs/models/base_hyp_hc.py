@@ -32,12 +32,22 @@ class BaseSimilarityHypHC(torch.nn.Module):
     def _forward(self, batch, testing):
         raise NotImplementedError
 
+    def compute_losses(self, x_euclidean, x_poincare, labels):
+        loss = self.metric_hyp_loss.compute_loss(x_euclidean, x_poincare, labels.view(-1, 1)[:, 0].long())
+        return {"loss_metric": loss["loss_metric"]["losses"], "loss_hyp": loss["loss_hyp"]["losses"] * self.trade_off}
+
+    def compute_accuracy(self, embeddings, labels):
+        return (self.metric_hyp_loss.get_logits(embeddings, labels).argmax(1) == labels).float().mean()
+
+    def compute_iou(self, embeddings, labels):
+        return self.compute_accuracy(embeddings, labels)
+
     def forward(self, batch, testing=False):
+        """The reference's calling structure, per-cloud decode loop included (replaced by the binding)."""
         points, x_euclidean, x_poincare, pts_labels = self._forward(batch, testing)
         xe = x_euclidean.contiguous().view(-1, x_euclidean.shape[-1])
         xp = x_poincare.contiguous().view(-1, x_poincare.shape[-1])
-        loss = self.metric_hyp_loss.compute_loss(xe, xp, pts_labels.view(-1, 1)[:, 0].long())
-        losses = {"loss_metric": loss["loss_metric"]["losses"], "loss_hyp": loss["loss_hyp"]["losses"] * self.trade_off}
+        losses = self.compute_losses(xe, xp, pts_labels)
         if not testing:
             return losses, {}
         Z = [self._decode_linkage(x_poincare[i]) for i in range(points.size(0))]

@@ -168,8 +168,9 @@ def test_shapenet_training_step_through_patched_names(tree, B, full):
 
 
 def test_test_step_decode_and_model_selection_through_patched_names(tree):
-    """forward(testing=True): per-cloud ``self._decode_linkage`` (base_hyp_hc.py:133-137) and ``get_optimal_k``
-    (:197-199) through the names ``base_hyp_hc`` imported -- Z bit-equal to scipy, same best k / score."""
+    """forward(testing=True) (base_hyp_hc.py:120-140; the binding replaces its per-cloud ``_decode_linkage`` loop,
+    :133-137, by one batched decode) and ``get_optimal_k`` (:197-199) through the names ``base_hyp_hc`` imported --
+    same return tuple, Z bit-equal to scipy per cloud, same best k / score; ``_decode_linkage`` called directly agrees."""
     hpcs = tree
     from scipy.cluster.hierarchy import linkage
     from hpcs.models import ShapeNetHypHC
@@ -190,6 +191,8 @@ def test_test_step_decode_and_model_selection_through_patched_names(tree):
         assert isinstance(Zs[i], np.ndarray) and Zs[i].dtype == np.float64 and Zs[i].shape == (N - 1, 4)
         leaves = normalize_project(x_p[i], model.scale).cpu().numpy()
         assert np.array_equal(Zs[i], linkage(leaves, method="complete", metric="cosine"))
+        assert np.array_equal(model._decode_linkage(x_p[i]), Zs[i])
+    assert set(losses) == {"loss_metric", "loss_hyp"}
     scores = model.test_scores(labels, Zs)
     for i, (pred, kbest, score) in enumerate(scores):
         wpred, wk, wscore = O.get_optimal_k_restated(labels[i].cpu().numpy(), Zs[i])
