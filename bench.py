@@ -532,7 +532,7 @@ def run_native(args):
         "config": {"workload": "shapenet_train_step_b32_n1024_k20_d32_t50 (BASELINE.json configs[1])",
                    "batches_per_step": R, "ms_per_batch": round(ms_per_batch, 4),
                    "step_definition": f"one timed step = {R} batches of {B} clouds per GPU back to back (a {round(ms_per_step * args.steps)} ms timed region); every per-batch figure below is per ONE batch",
-                   "collective": (f"all-reduce of the {GRAD_BUCKET_FLOATS * 4} B fp32 gradient bucket (SURVEY 8e), async, overlapped with the edge backwards; NCCL_MAX_NCHANNELS={os.environ.get('NCCL_MAX_NCHANNELS')}" if world > 1 else "none at 1 GPU"),
+                   "collective": (f"all-reduce of the {GRAD_BUCKET_FLOATS * 4} B fp32 gradient bucket (SURVEY 8e), async, overlapped with the edge backwards; NCCL_MAX_NCHANNELS={os.environ.get('NCCL_MAX_NCHANNELS')} NCCL_NVLS_NCHANNELS={os.environ.get('NCCL_NVLS_NCHANNELS')}" if world > 1 else "none at 1 GPU"),
                    "clouds_per_gpu": B, "points": N_PTS, "k": K_NN, "feat_channels": [1, C_FEAT, C_FEAT],
                    "emb_dim": D_EMB, "triplets_mined": T0, "triplets_kept": kept_val, "filter": "easy",
                    "scale": SCALE, "temperature": TEMPERATURE, "parallelism": f"dp{world}",

@@ -23,10 +23,15 @@ def init_from_env(backend: str = None) -> Tuple[int, int, int]:
     if world > 1 and not dist.is_initialized():
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
-        # The one collective of this path is a 5 MB gradient bucket overlapped with persistent one-CTA-per-SM kernels: NCCL's
-        # default channel count takes SMs those kernels are waiting for.  Two channels are enough for a latency-bound message
-        # (measured on 2 x B200: 0.825 ms per batch with the default, 0.806 with 2, 0.841 with 8); an explicit setting wins.
+        # The one collective of this path is a 5 MB gradient bucket overlapped with persistent one-CTA-per-SM kernels: every
+        # channel NCCL opens is a CTA on an SM those kernels are waiting for (144 gather CTAs on 148 SMs: more than four
+        # channels and a whole extra round of the gather is serialised behind them).  Two channels are enough for a
+        # latency-bound message.  Measured per batch, in-graph, B200: 2 GPUs (ring) 0.825 ms with NCCL's default, 0.806 with
+        # NCCL_MAX_NCHANNELS=2, 0.841 with 8; 8 GPUs (NVLS, which has its own channel count) 0.858 ms with the default 24 NVLS
+        # channels, 0.839 with NCCL_NVLS_NCHANNELS=2 (ring without NVLS: 1.08-1.38 ms).  The all-reduce alone takes 56 us at
+        # 8 GPUs whatever the setting (tools/allreduce_probe.py).  An explicit setting in the environment wins.
         os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")
+        os.environ.setdefault("NCCL_NVLS_NCHANNELS", "2")
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
         if backend == "nccl":
