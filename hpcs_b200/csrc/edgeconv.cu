@@ -62,50 +62,59 @@ __device__ __forceinline__ void stage_weights(float* ws, const float* __restrict
     __syncthreads();
 }
 
-// (p, d) of output channel o = rows o of the two stage-2 weight matrices times the 21 input vectors X[3i + c]
+// ---- the 21x21 channel mixes of the second conv, on packed fp32 pairs (fma.rn.f32x2 = FFMA2: one issue slot for two FMAs).  The 21
+// vectors of the first conv's output live as X2[c][m] = (X[2m][c], X[2m+1][c]), channel 21 = 0; the weight rows are read from shared
+// memory as they lie (consecutive input channels), so neither operand needs duplicating.  Measured against scalar FMAs: stage-2
+// statistics pass 116 -> 107 us, edgeconv_bwd2 835 -> 770 us (C=1 layer) and 910 -> 865 us (C=21); the full forward is unchanged
+// (it waits on the barriers of its k-reduction rounds).
+typedef unsigned long long f32x2;
+constexpr int kXP = 11;                                   // channel pairs
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ float hsum2(f32x2 v) { float lo, hi; unpack2(v, lo, hi); return lo + hi; }
+
+// (p, d) of output channel o: two partial sums per component (even / odd input channels), 11 packed FMAs each
 template <bool WITH_D>
-__device__ __forceinline__ void mix_channel(const float* ws, int o, const float (&X)[64], float& p0, float& p1, float& p2, float& d0,
-                                            float& d1, float& d2) {
-    const float4* wf = reinterpret_cast<const float4*>(ws + kOffWf + o * kWPad);
-    const float4* wd = reinterpret_cast<const float4*>(ws + kOffWd + o * kWPad);
-    p0 = p1 = p2 = d0 = d1 = d2 = 0.f;
+__device__ __forceinline__ void mix_channel(const float* ws, int o, const f32x2 (&X2)[3][kXP], float& p0, float& p1, float& p2, float& d0,
+                                             float& d1, float& d2) {
+    const ulonglong2* wf = reinterpret_cast<const ulonglong2*>(ws + kOffWf + o * kWPad);   // (w[4q], w[4q+1]), (w[4q+2], w[4q+3])
+    const ulonglong2* wd = reinterpret_cast<const ulonglong2*>(ws + kOffWd + o * kWPad);
+    f32x2 ap[3] = {0ull, 0ull, 0ull}, ad[3] = {0ull, 0ull, 0ull};
 #pragma unroll
-    for (int i4 = 0; i4 < kWPad / 4; ++i4) {
-        const float4 a = wf[i4];
-        const float af[4] = {a.x, a.y, a.z, a.w};
-        float bf[4] = {0.f, 0.f, 0.f, 0.f};
-        if (WITH_D) {
-            const float4 b = wd[i4];
-            bf[0] = b.x; bf[1] = b.y; bf[2] = b.z; bf[3] = b.w;
-        }
+    for (int q = 0; q < 6; ++q) {
+        const ulonglong2 a = wf[q];
+        ulonglong2 b = make_ulonglong2(0ull, 0ull);
+        if (WITH_D) b = wd[q];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = 4 * i4 + u;
-            if (i < kVO) {
-                p0 = fmaf(af[u], X[3 * i], p0); p1 = fmaf(af[u], X[3 * i + 1], p1); p2 = fmaf(af[u], X[3 * i + 2], p2);
-                if (WITH_D) { d0 = fmaf(bf[u], X[3 * i], d0); d1 = fmaf(bf[u], X[3 * i + 1], d1); d2 = fmaf(bf[u], X[3 * i + 2], d2); }
+        for (int c = 0; c < 3; ++c) {
+            ap[c] = ffma2(a.x, X2[c][2 * q], ap[c]);
+            if (WITH_D) ad[c] = ffma2(b.x, X2[c][2 * q], ad[c]);
+            if (2 * q + 1 < kXP) {
+                ap[c] = ffma2(a.y, X2[c][2 * q + 1], ap[c]);
+                if (WITH_D) ad[c] = ffma2(b.y, X2[c][2 * q + 1], ad[c]);
             }
         }
     }
+    p0 = hsum2(ap[0]); p1 = hsum2(ap[1]); p2 = hsum2(ap[2]);
+    d0 = d1 = d2 = 0.f;
+    if (WITH_D) { d0 = hsum2(ad[0]); d1 = hsum2(ad[1]); d2 = hsum2(ad[2]); }
 }
 
-// acc[3i + c] += wf[o][i] gp[c] + wd[o][i] gd[c]   (transpose of mix_channel)
+// acc2[c][m] += (wf[o][2m], wf[o][2m+1]) gp[c] + (wd[o][2m], wd[o][2m+1]) gd[c]   (transpose of mix_channel)
 __device__ __forceinline__ void mix_channel_transposed(const float* ws, int o, float gp0, float gp1, float gp2, float gd0, float gd1,
-                                                       float gd2, float (&acc)[64]) {
-    const float4* wf = reinterpret_cast<const float4*>(ws + kOffWf + o * kWPad);
-    const float4* wd = reinterpret_cast<const float4*>(ws + kOffWd + o * kWPad);
+                                                        float gd2, f32x2 (&acc2)[3][kXP]) {
+    const ulonglong2* wf = reinterpret_cast<const ulonglong2*>(ws + kOffWf + o * kWPad);
+    const ulonglong2* wd = reinterpret_cast<const ulonglong2*>(ws + kOffWd + o * kWPad);
+    const f32x2 gp[3] = {pack2(gp0, gp0), pack2(gp1, gp1), pack2(gp2, gp2)};
+    const f32x2 gd[3] = {pack2(gd0, gd0), pack2(gd1, gd1), pack2(gd2, gd2)};
 #pragma unroll
-    for (int i4 = 0; i4 < kWPad / 4; ++i4) {
-        const float4 a = wf[i4], b = wd[i4];
-        const float af[4] = {a.x, a.y, a.z, a.w}, bf[4] = {b.x, b.y, b.z, b.w};
+    for (int q = 0; q < 6; ++q) {
+        const ulonglong2 a = wf[q], b = wd[q];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int i = 4 * i4 + u;
-            if (i < kVO) {
-                acc[3 * i] = fmaf(af[u], gp0, fmaf(bf[u], gd0, acc[3 * i]));
-                acc[3 * i + 1] = fmaf(af[u], gp1, fmaf(bf[u], gd1, acc[3 * i + 1]));
-                acc[3 * i + 2] = fmaf(af[u], gp2, fmaf(bf[u], gd2, acc[3 * i + 2]));
-            }
+        for (int c = 0; c < 3; ++c) {
+            acc2[c][2 * q] = ffma2(a.x, gp[c], ffma2(b.x, gd[c], acc2[c][2 * q]));
+            if (2 * q + 1 < kXP) acc2[c][2 * q + 1] = ffma2(a.y, gp[c], ffma2(b.y, gd[c], acc2[c][2 * q + 1]));
         }
     }
 }
@@ -588,17 +597,21 @@ __global__ void __launch_bounds__(kMaxTileThreads, 2) edgeconv_fwd_kernel(const 
             continue;
         }
         // ---- two convs: stage 1 -> O1 in registers -----------------------------------------------------------------------
-        float X[64];
-        stage1_inputs<DIRECT>(S, A.x, A.N, e, [&](int o, float p0, float p1, float p2, float d0, float d1, float d2) {
-            const ChanFwd f = chan_fwd(p0, p1, p2, d0, d1, d2, bn_coef(ws, 0, BN_A, o), bn_coef(ws, 0, BN_B, o));
-            X[3 * o] = f.o0; X[3 * o + 1] = f.o1; X[3 * o + 2] = f.o2;
-        });
-        X[63] = 0.f;
+        f32x2 X2[3][kXP];
+        {
+            float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+            stage1_inputs<DIRECT>(S, A.x, A.N, e, [&](int o, float p0, float p1, float p2, float d0, float d1, float d2) {
+                const ChanFwd f = chan_fwd(p0, p1, p2, d0, d1, d2, bn_coef(ws, 0, BN_A, o), bn_coef(ws, 0, BN_B, o));
+                if (o & 1) { X2[0][o >> 1] = pack2(h0, f.o0); X2[1][o >> 1] = pack2(h1, f.o1); X2[2][o >> 1] = pack2(h2, f.o2); }
+                else if (o == kVO - 1) { X2[0][o >> 1] = pack2(f.o0, 0.f); X2[1][o >> 1] = pack2(f.o1, 0.f); X2[2][o >> 1] = pack2(f.o2, 0.f); }
+                else { h0 = f.o0; h1 = f.o1; h2 = f.o2; }
+            });
+        }
         if (MODE == 1) {
 #pragma unroll
             for (int o = 0; o < kVO; ++o) {
                 float p0, p1, p2, d0, d1, d2;
-                mix_channel<false>(ws, o, X, p0, p1, p2, d0, d1, d2);
+                mix_channel<false>(ws, o, X2, p0, p1, p2, d0, d1, d2);
                 const float r = vnorm(p0, p1, p2) + kVnEps;
                 if (e.valid) { sr[o] += r; sr2[o] = fmaf(r, r, sr2[o]); }
             }
@@ -614,7 +627,7 @@ __global__ void __launch_bounds__(kMaxTileThreads, 2) edgeconv_fwd_kernel(const 
             for (int jj = 0; jj < kGrp; ++jj) {
                 const int o = g7 * kGrp + jj;
                 float p0, p1, p2, d0, d1, d2;
-                mix_channel<true>(ws, o, X, p0, p1, p2, d0, d1, d2);
+                mix_channel<true>(ws, o, X2, p0, p1, p2, d0, d1, d2);
                 const ChanFwd f = chan_fwd(p0, p1, p2, d0, d1, d2, bn_coef(ws, 1, BN_A, o), bn_coef(ws, 1, BN_B, o));
                 myred[3 * jj] = e.valid ? f.o0 : 0.f; myred[3 * jj + 1] = e.valid ? f.o1 : 0.f; myred[3 * jj + 2] = e.valid ? f.o2 : 0.f;
                 if (want_y) {
@@ -677,7 +690,7 @@ struct Bwd2Args {
     double* stats1;         // [21][2] += sum gy1, sum gy1 rhat1
 };
 constexpr int kDwEntries = 2 * kVO * kVO;                 // 882
-constexpr int kDwRow = 48;                                // per output channel: 42 entries (half, in) padded to 3 groups of 16
+constexpr int kDwRow = 48;                                // per output channel: [half][22 in (21 + one zero)] + 4 padding = 3 groups of 16
 constexpr int kDwPad = kVO * kDwRow;                      // 1008
 
 template <bool DIRECT>
@@ -702,41 +715,68 @@ __global__ void __launch_bounds__(kMaxTileThreads, 2) edgeconv_bwd2_kernel(const
             S.gs[pl * 64 + oc] = g < A.BN ? A.G[((g / A.N) * kVD + oc) * A.N + g % A.N] * inv_k : 0.f;
         }
         __syncthreads();
-        float X[64];                                                           // O1: output of the first conv
-        stage1_inputs<DIRECT>(S, A.x, A.N, e, [&](int o, float p0, float p1, float p2, float d0, float d1, float d2) {
-            const ChanFwd f = chan_fwd(p0, p1, p2, d0, d1, d2, bn_coef(ws, 0, BN_A, o), bn_coef(ws, 0, BN_B, o));
-            X[3 * o] = f.o0; X[3 * o + 1] = f.o1; X[3 * o + 2] = f.o2;
-        });
-        X[63] = 0.f;
-        float GO[64];                                                          // gO1 = W2^T g, accumulated over output channels
+        f32x2 X2[3][kXP];                                                      // O1: output of the first conv, channel pairs
+        {
+            float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+            stage1_inputs<DIRECT>(S, A.x, A.N, e, [&](int o, float p0, float p1, float p2, float d0, float d1, float d2) {
+                const ChanFwd f = chan_fwd(p0, p1, p2, d0, d1, d2, bn_coef(ws, 0, BN_A, o), bn_coef(ws, 0, BN_B, o));
+                if (o & 1) { X2[0][o >> 1] = pack2(h0, f.o0); X2[1][o >> 1] = pack2(h1, f.o1); X2[2][o >> 1] = pack2(h2, f.o2); }
+                else if (o == kVO - 1) { X2[0][o >> 1] = pack2(f.o0, 0.f); X2[1][o >> 1] = pack2(f.o1, 0.f); X2[2][o >> 1] = pack2(f.o2, 0.f); }
+                else { h0 = f.o0; h1 = f.o1; h2 = f.o2; }
+            });
+        }
+        f32x2 GO2[3][kXP];                                                     // gO1 = W2^T g, accumulated over output channels
 #pragma unroll
-        for (int i = 0; i < 64; ++i) GO[i] = 0.f;
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int m = 0; m < kXP; ++m) GO2[c][m] = 0ull;
         const float* grow = S.gs + e.pl * 64;
         float stag[16];
 #pragma unroll 1                                                               // a real loop: the body is ~700 instructions; unrolled 21 times
         for (int o = 0; o < kVO; ++o) {                                        // it thrashes the instruction cache (1.56 ms; by 3: 1.16; 1: 0.91)
             float p0, p1, p2, d0, d1, d2;
-            mix_channel<true>(ws, o, X, p0, p1, p2, d0, d1, d2);
+            mix_channel<true>(ws, o, X2, p0, p1, p2, d0, d1, d2);
             const ChanFwd f = chan_fwd(p0, p1, p2, d0, d1, d2, bn_coef(ws, 1, BN_A, o), bn_coef(ws, 1, BN_B, o));
             float gp0, gp1, gp2, gd0, gd1, gd2, gy, rhat;
             chan_bwd(f, p0, p1, p2, d0, d1, d2, grow[3 * o], grow[3 * o + 1], grow[3 * o + 2], bn_coef(ws, 1, BN_A, o), bn_coef(ws, 1, BN_MU, o),
                      bn_coef(ws, 1, BN_RSTD, o), bn_coef(ws, 1, BN_S1M, o), bn_coef(ws, 1, BN_S2M, o), gp0, gp1, gp2, gd0, gd1, gd2, gy, rhat);
             if (!e.valid) { gp0 = gp1 = gp2 = gd0 = gd1 = gd2 = 0.f; }
-            mix_channel_transposed(ws, o, gp0, gp1, gp2, gd0, gd1, gd2, GO);
-            // weight gradient: entry (out o, half h, in i) <- sum over edges of g_h[o] . O1[i]; the 42 entries of this output
-            // channel go through the warp transpose 16 at a time, after which lane l (< 16) owns entry 16*group + l of the row
+            mix_channel_transposed(ws, o, gp0, gp1, gp2, gd0, gd1, gd2, GO2);
+            // weight gradient: entry (out o, half h, in i) <- sum over edges of g_h[o] . O1[i]; the row of this output channel is
+            // [h][22] (+4 padding) and goes through the warp transpose 16 entries at a time, after which lane l (< 16) owns entry
+            // 16*group + l of the row.  (Scalar FMAs on the halves of the channel pairs: packed ones here, with the duplicated
+            // gradient operands and the unpacking they need, measured slower -- 954 vs 865 us for the C=21 layer.)
 #pragma unroll
-            for (int q = 0; q < kDwRow; ++q) {
-                const int h = q / kVO, i = q - h * kVO;
-                stag[q & 15] = q >= 2 * kVO ? 0.f
-                               : h == 0     ? fmaf(gp2, X[3 * i + 2], fmaf(gp1, X[3 * i + 1], gp0 * X[3 * i]))
-                                            : fmaf(gd2, X[3 * i + 2], fmaf(gd1, X[3 * i + 1], gd0 * X[3 * i]));
-                if ((q & 15) == 15) {
+            for (int q2 = 0; q2 < kDwRow / 2; ++q2) {
+                const int h = q2 / kXP, m = q2 - h * kXP;
+                float lo = 0.f, hi = 0.f;
+                if (h < 2) {
+                    float x0l, x0h, x1l, x1h, x2l, x2h;
+                    unpack2(X2[0][m], x0l, x0h); unpack2(X2[1][m], x1l, x1h); unpack2(X2[2][m], x2l, x2h);
+                    const float a0 = h == 0 ? gp0 : gd0, a1 = h == 0 ? gp1 : gd1, a2 = h == 0 ? gp2 : gd2;
+                    lo = fmaf(a2, x2l, fmaf(a1, x1l, a0 * x0l));
+                    hi = fmaf(a2, x2h, fmaf(a1, x1h, a0 * x0h));
+                }
+                stag[(2 * q2) & 15] = lo;
+                stag[(2 * q2 + 1) & 15] = hi;
+                if (((2 * q2 + 1) & 15) == 15) {
                     const float tot = warp_transpose_sum16(stag, lane);
-                    if (lane < 16) atomicAdd(dw_s + o * kDwRow + (q & ~15) + lane, tot);
+                    if (lane < 16) atomicAdd(dw_s + o * kDwRow + ((2 * q2) & ~15) + lane, tot);
                 }
             }
         }
+        // unpack gO1 into the flat [3 i + c] order of the scratch (register renaming, no instructions)
+        float GO[64];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int m = 0; m < kXP; ++m) {
+                float lo, hi;
+                unpack2(GO2[c][m], lo, hi);
+                GO[3 * (2 * m) + c] = lo;
+                if (2 * m + 1 < kVO) GO[3 * (2 * m + 1) + c] = hi;
+            }
+        GO[63] = 0.f;
         // BatchNorm sums of the first conv: gy1 = Y1 . gO1 per channel (its inputs are still staged in shared memory)
         stage1_inputs<DIRECT>(S, A.x, A.N, e, [&](int o, float p0, float p1, float p2, float d0, float d1, float d2) {
             const ChanFwd f = chan_fwd(p0, p1, p2, d0, d1, d2, bn_coef(ws, 0, BN_A, o), bn_coef(ws, 0, BN_B, o));
@@ -758,7 +798,10 @@ __global__ void __launch_bounds__(kMaxTileThreads, 2) edgeconv_bwd2_kernel(const
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < kDwEntries; i += blockDim.x) atomicAdd(A.dW2 + i, dw_s[(i / (2 * kVO)) * kDwRow + i % (2 * kVO)]);
+    for (int i = threadIdx.x; i < kDwEntries; i += blockDim.x) {                // (o, h, in) <- row o, entry h * 22 + in
+        const int o = i / (2 * kVO), r = i - o * 2 * kVO, h = r / kVO;
+        atomicAdd(A.dW2 + i, dw_s[o * kDwRow + h * 2 * kXP + (r - h * kVO)]);
+    }
     for (int i = threadIdx.x; i < 2 * kVO; i += blockDim.x) atomicAdd(A.stats1 + i, (double)st_s[i]);
 }
 
