@@ -199,12 +199,13 @@ __device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
 // ---- per-point linear maps ------------------------------------------------------------------------------------------
 // x[B,C,3,N], W4[4][21][C] = {Uf, Ud, Vf, Vd} -> UU[B*N][128], VV[B*N][128]
 constexpr int kPlPts = 32;
+constexpr int kPlStride = kRowF + 1;                    // (a 128-float stride put a warp's 12 stores per item in one bank: 60 -> 30 us)
 __global__ void __launch_bounds__(256) vn_point_linear_kernel(const float* __restrict__ x, const float* __restrict__ W4, int C, int N,
                                                               float* __restrict__ UU, float* __restrict__ VV) {
     extern __shared__ float sm[];
     float* xs = sm;                                     // [3C][kPlPts]
     float* ws = xs + 3 * C * kPlPts;                    // [4][21][C]
-    float* outs = ws + 4 * kVO * C;                     // [2][kPlPts][128]
+    float* outs = ws + 4 * kVO * C;                     // [2][kPlPts][kPlStride]: odd stride, a warp's 32 points hit 32 banks
     const int b = blockIdx.y, n0 = blockIdx.x * kPlPts;
     const int np = min(kPlPts, N - n0);
     for (int i = threadIdx.x; i < 3 * C * kPlPts; i += blockDim.x) {
@@ -212,7 +213,7 @@ __global__ void __launch_bounds__(256) vn_point_linear_kernel(const float* __res
         xs[i] = p < np ? x[((size_t)b * 3 * C + row) * N + n0 + p] : 0.f;
     }
     for (int i = threadIdx.x; i < 4 * kVO * C; i += blockDim.x) ws[i] = W4[i];
-    for (int i = threadIdx.x; i < 2 * kPlPts * kRowF; i += blockDim.x) outs[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * kPlPts * kPlStride; i += blockDim.x) outs[i] = 0.f;
     __syncthreads();
     // thread -> (point p, channel o): 12 outputs
     for (int t = threadIdx.x; t < kPlPts * kVO; t += blockDim.x) {
@@ -228,17 +229,18 @@ __global__ void __launch_bounds__(256) vn_point_linear_kernel(const float* __res
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            outs[(0 * kPlPts + p) * kRowF + o * 3 + c] = acc[0][c];
-            outs[(0 * kPlPts + p) * kRowF + 64 + o * 3 + c] = acc[1][c];
-            outs[(1 * kPlPts + p) * kRowF + o * 3 + c] = acc[2][c];
-            outs[(1 * kPlPts + p) * kRowF + 64 + o * 3 + c] = acc[3][c];
+            outs[(0 * kPlPts + p) * kPlStride + o * 3 + c] = acc[0][c];
+            outs[(0 * kPlPts + p) * kPlStride + 64 + o * 3 + c] = acc[1][c];
+            outs[(1 * kPlPts + p) * kPlStride + o * 3 + c] = acc[2][c];
+            outs[(1 * kPlPts + p) * kPlStride + 64 + o * 3 + c] = acc[3][c];
         }
     }
     __syncthreads();
     const size_t row0 = ((size_t)b * N + n0) * kRowF;
-    for (int i = threadIdx.x; i < np * kRowF / 4; i += blockDim.x) {
-        reinterpret_cast<float4*>(UU + row0)[i] = reinterpret_cast<const float4*>(outs)[i];
-        reinterpret_cast<float4*>(VV + row0)[i] = reinterpret_cast<const float4*>(outs + kPlPts * kRowF)[i];
+    for (int i = threadIdx.x; i < np * kRowF; i += blockDim.x) {        // a warp writes 128 contiguous bytes of one row
+        const int r = i / kRowF, col = i % kRowF;
+        UU[row0 + i] = outs[r * kPlStride + col];
+        VV[row0 + i] = outs[(kPlPts + r) * kPlStride + col];
     }
 }
 
@@ -314,53 +316,107 @@ __global__ void edgeconv_bn_sums_finish_kernel(const double* __restrict__ sums, 
 // gUU / gVV [B*N][128] (gradients wrt the U and V rows) -> gx[B,C,3,N] = sum_m W4[m]^T g_m  and  dW4[4][21][C] += sum over
 // points and components of g_m (x) x.  64 points per block; the block's weight-gradient partials leave as one atomic each.
 constexpr int kPbPts = 64;
+constexpr int kCiGrp = 7;                               // input channels per thread
 constexpr int kPbStride = 129;                          // odd stride: a warp's 32 points read a column without bank conflicts
+constexpr int kPbXs = kPbPts + 1;                       // x rows: lanes = input channels, 3 * 65 floats apart = 21 different banks (3 * 64 floats:
+                                                        // one bank, a 21-way conflict on every load of the loop -- 181 -> 86 us)
 __global__ void __launch_bounds__(256) vn_point_linear_bwd_kernel(const float* __restrict__ gUU, const float* __restrict__ gVV,
                                                                   const float* __restrict__ x, const float* __restrict__ W4, int C, int N,
-                                                                  float* __restrict__ gx, float* __restrict__ dW4) {
-    extern __shared__ float sm[];
-    float* gs = sm;                                     // [2][kPbPts][129]: rows of gUU, then of gVV
-    float* xs = gs + 2 * kPbPts * kPbStride;            // [3C][kPbPts]
-    float* ws = xs + 3 * C * kPbPts;                    // [4][21][C]
-    const int b = blockIdx.y, n0 = blockIdx.x * kPbPts;
+                                                                  int nblk, float* __restrict__ gx, float* __restrict__ dW4) {
+    extern __shared__ __align__(16) float sm[];
+    float* dws = sm;                                    // [4][21][C] weight-gradient sums of this CTA over all its point blocks (16-byte aligned)
+    float* ws = dws + 4 * kVO * C;                      // [4][21][C]
+    float* gs = ws + 4 * kVO * C;                       // [2][kPbPts][129]: rows of gUU, then of gVV
+    float* xs = gs + 2 * kPbPts * kPbStride;            // [3C][kPbXs]: the weight-gradient loop reads a column of it per lane (lane = channel)
+    for (int i = threadIdx.x; i < 4 * kVO * C; i += blockDim.x) { ws[i] = W4[i]; dws[i] = 0.f; }
+    const int bpc = (N + kPbPts - 1) / kPbPts;          // point blocks per cloud
+    for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x) {
+    const int b = blk / bpc, n0 = (blk - b * bpc) * kPbPts;
     const int np = min(kPbPts, N - n0);
     const size_t row0 = ((size_t)b * N + n0) * kRowF;
+    __syncthreads();                                    // the previous block's readers are done with gs / xs
     for (int i = threadIdx.x; i < 2 * kPbPts * kRowF; i += blockDim.x) {
         const int half = i / (kPbPts * kRowF), r = (i / kRowF) % kPbPts, col = i % kRowF;
         gs[(half * kPbPts + r) * kPbStride + col] = r < np ? __ldg((half ? gVV : gUU) + row0 + (size_t)r * kRowF + col) : 0.f;
     }
     for (int i = threadIdx.x; i < 3 * C * kPbPts; i += blockDim.x) {
         const int row = i / kPbPts, p = i % kPbPts;
-        xs[i] = p < np ? __ldg(x + ((size_t)b * 3 * C + row) * N + n0 + p) : 0.f;
+        xs[row * kPbXs + p] = p < np ? __ldg(x + ((size_t)b * 3 * C + row) * N + n0 + p) : 0.f;
     }
-    for (int i = threadIdx.x; i < 4 * kVO * C; i += blockDim.x) ws[i] = W4[i];
     __syncthreads();
-    // gx: thread -> (point p, input channel ci), all three components; m = 0,1 read the gUU row (feat | dir), m = 2,3 the gVV row
-    for (int t = threadIdx.x; t < kPbPts * C; t += blockDim.x) {
-        const int p = t % kPbPts, ci = t / kPbPts;
+    // gx: thread -> (point p, kCiGrp input channels), all three components: the point's 4 x 21 gradient vectors are read once per
+    // group of channels (m = 0,1: the gUU row (feat | dir), m = 2,3: the gVV row); weights are warp-wide broadcasts
+    const int ngrp = (C + kCiGrp - 1) / kCiGrp;
+    for (int t = threadIdx.x; t < kPbPts * ngrp; t += blockDim.x) {
+        const int p = t % kPbPts, c0 = (t / kPbPts) * kCiGrp;
         if (p >= np) continue;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+        float a[kCiGrp][3];
+#pragma unroll
+        for (int u = 0; u < kCiGrp; ++u) a[u][0] = a[u][1] = a[u][2] = 0.f;
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
             const float* g = gs + ((m >> 1) * kPbPts + p) * kPbStride + (m & 1) * 64;
             for (int o = 0; o < kVO; ++o) {
-                const float w = ws[(m * kVO + o) * C + ci];
-                a0 = fmaf(w, g[3 * o], a0); a1 = fmaf(w, g[3 * o + 1], a1); a2 = fmaf(w, g[3 * o + 2], a2);
+                const float g0 = g[3 * o], g1 = g[3 * o + 1], g2 = g[3 * o + 2];
+                const float* w = ws + (m * kVO + o) * C + c0;
+#pragma unroll
+                for (int u = 0; u < kCiGrp; ++u) {
+                    if (c0 + u < C) {
+                        const float wv = w[u];
+                        a[u][0] = fmaf(wv, g0, a[u][0]); a[u][1] = fmaf(wv, g1, a[u][1]); a[u][2] = fmaf(wv, g2, a[u][2]);
+                    }
+                }
             }
         }
-        float* dst = gx + ((size_t)b * 3 * C + ci * 3) * N + n0 + p;
-        dst[0] = a0; dst[N] = a1; dst[2 * (size_t)N] = a2;
+#pragma unroll
+        for (int u = 0; u < kCiGrp; ++u) {
+            if (c0 + u < C) {
+                float* dst = gx + ((size_t)b * 3 * C + (c0 + u) * 3) * N + n0 + p;
+                dst[0] = a[u][0]; dst[N] = a[u][1]; dst[2 * (size_t)N] = a[u][2];
+            }
+        }
     }
-    // dW4[m][o][ci]: thread -> one entry, summed over the block's points and the three components
-    for (int t = threadIdx.x; t < 4 * kVO * C; t += blockDim.x) {
-        const int ci = t % C, mo = t / C, m = mo / kVO, o = mo % kVO;
-        const float* g = gs + (m >> 1) * kPbPts * kPbStride + (m & 1) * 64 + 3 * o;
-        const float* xr = xs + ci * 3 * kPbPts;
-        float acc = 0.f;
-        for (int p = 0; p < np; ++p)
-            acc = fmaf(g[p * kPbStride], xr[p], fmaf(g[p * kPbStride + 1], xr[kPbPts + p], fmaf(g[p * kPbStride + 2], xr[2 * kPbPts + p], acc)));
-        atomicAdd(dW4 + t, acc);
+    // dW4[m][o][ci]: thread -> (3 consecutive (m, o) rows, kCiGrp input channels, a third of the block's points): 9 + 21 loads feed
+    // 63 FMAs per point (one entry per thread needed 6 loads per 3 FMAs and left the kernel bound by the shared-memory pipe);
+    // the partial sums are collected in shared memory over all point blocks of the CTA
+    constexpr int kMoGrp = 3, kPSplit = 3;                  // 84 rows = 28 groups of 3 (a group never straddles m: 21 = 7 x 3)
+    const int pper = (kPbPts + kPSplit - 1) / kPSplit;
+    for (int t = threadIdx.x; t < (4 * kVO / kMoGrp) * ngrp * kPSplit; t += blockDim.x) {
+        const int ps = t % kPSplit, cg = (t / kPSplit) % ngrp, mog = t / (kPSplit * ngrp);
+        const int mo0 = mog * kMoGrp, m = mo0 / kVO, o0 = mo0 - m * kVO, c0 = cg * kCiGrp;
+        const float* g = gs + (m >> 1) * kPbPts * kPbStride + (m & 1) * 64 + 3 * o0;
+        float acc[kMoGrp][kCiGrp];
+#pragma unroll
+        for (int r = 0; r < kMoGrp; ++r)
+#pragma unroll
+            for (int u = 0; u < kCiGrp; ++u) acc[r][u] = 0.f;
+        const int p_end = min(np, (ps + 1) * pper);
+        for (int pp = ps * pper; pp < p_end; ++pp) {
+            float gv[kMoGrp][3];
+#pragma unroll
+            for (int r = 0; r < kMoGrp; ++r) { gv[r][0] = g[pp * kPbStride + 3 * r]; gv[r][1] = g[pp * kPbStride + 3 * r + 1]; gv[r][2] = g[pp * kPbStride + 3 * r + 2]; }
+#pragma unroll
+            for (int u = 0; u < kCiGrp; ++u) {
+                if (c0 + u < C) {
+                    const float* xr = xs + (c0 + u) * 3 * kPbXs + pp;
+                    const float x0 = xr[0], x1 = xr[kPbXs], x2 = xr[2 * kPbXs];
+#pragma unroll
+                    for (int r = 0; r < kMoGrp; ++r) acc[r][u] = fmaf(gv[r][0], x0, fmaf(gv[r][1], x1, fmaf(gv[r][2], x2, acc[r][u])));
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < kMoGrp; ++r)
+#pragma unroll
+            for (int u = 0; u < kCiGrp; ++u)
+                if (c0 + u < C) atomicAdd(dws + (mo0 + r) * C + c0 + u, acc[r][u]);
     }
+    }
+    // one 128-bit reduction per four entries and CTA (84 C is a multiple of 4; global atomics on these 7 KB were the limit of the
+    // kernel: one scalar atomic per entry and 64-point block, 0.9 M per call, cost about half of its 86 us; 71 us now)
+    __syncthreads();
+    for (int i = threadIdx.x; i < kVO * C; i += blockDim.x)
+        atomicAdd(reinterpret_cast<float4*>(dW4) + i, reinterpret_cast<const float4*>(dws)[i]);
 }
 
 // ---- per-edge machinery ---------------------------------------------------------------------------------------------
@@ -916,7 +972,7 @@ using namespace hpcs;
 extern "C" int hpcs_vn_point_linear_f32(const float* x, const float* W4, int B, int C, int N, float* UU, float* VV, void* stream) {
     if (!x || !W4 || !UU || !VV) return fail(HPCS_ERR_ARG, "vn_point_linear: null pointer");
     if (B <= 0 || B > 65535 || C < 1 || C > 64 || N <= 0) return fail(HPCS_ERR_ARG, "vn_point_linear: bad shape B=%d C=%d N=%d", B, C, N);
-    const size_t smem = sizeof(float) * ((size_t)3 * C * kPlPts + 4 * kVO * C + 2 * kPlPts * kRowF);
+    const size_t smem = sizeof(float) * ((size_t)3 * C * kPlPts + 4 * kVO * C + 2 * kPlPts * kPlStride);
     static thread_local size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
         cudaFuncSetAttribute(vn_point_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -930,13 +986,16 @@ extern "C" int hpcs_vn_point_linear_bwd_f32(const float* gUU, const float* gVV, 
                                             float* gx, float* dW4, void* stream) {
     if (!gUU || !gVV || !x || !W4 || !gx || !dW4) return fail(HPCS_ERR_ARG, "vn_point_linear_bwd: null pointer");
     if (B <= 0 || B > 65535 || C < 1 || C > 64 || N <= 0) return fail(HPCS_ERR_ARG, "vn_point_linear_bwd: bad shape B=%d C=%d N=%d", B, C, N);
-    const size_t smem = sizeof(float) * ((size_t)2 * kPbPts * kPbStride + (size_t)3 * C * kPbPts + 4 * kVO * C);
+    const size_t smem = sizeof(float) * ((size_t)2 * kPbPts * kPbStride + (size_t)3 * C * kPbXs + 2 * 4 * kVO * C);
+    if ((reinterpret_cast<uintptr_t>(dW4) & 15) != 0) return fail(HPCS_ERR_ARG, "vn_point_linear_bwd: dW4 must be 16-byte aligned");
     static thread_local size_t attr = 0;
     if (smem > 48 * 1024 && smem > attr) {
         cudaFuncSetAttribute(vn_point_linear_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = smem;
     }
-    vn_point_linear_bwd_kernel<<<dim3((N + kPbPts - 1) / kPbPts, B), 256, smem, as_stream(stream)>>>(gUU, gVV, x, W4, C, N, gx, dW4);
+    const int nblk = B * ((N + kPbPts - 1) / kPbPts);
+    const int grid = nblk < 2 * sm_count() ? nblk : 2 * sm_count();
+    vn_point_linear_bwd_kernel<<<grid, 256, smem, as_stream(stream)>>>(gUU, gVV, x, W4, C, N, nblk, gx, dW4);
     return check_launch("vn_point_linear_bwd_kernel");
 }
 
