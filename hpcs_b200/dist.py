@@ -24,14 +24,18 @@ def init_from_env(backend: str = None) -> Tuple[int, int, int]:
         if backend is None:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
         # The one collective of this path is a 5 MB gradient bucket overlapped with persistent one-CTA-per-SM kernels: every
-        # channel NCCL opens is a CTA on an SM those kernels are waiting for (144 gather CTAs on 148 SMs: more than four
-        # channels and a whole extra round of the gather is serialised behind them).  Two channels are enough for a
-        # latency-bound message.  Measured per batch, in-graph, B200: 2 GPUs (ring) 0.825 ms with NCCL's default, 0.806 with
-        # NCCL_MAX_NCHANNELS=2, 0.841 with 8; 8 GPUs (NVLS, which has its own channel count) 0.858 ms with the default 24 NVLS
-        # channels, 0.839 with NCCL_NVLS_NCHANNELS=2 (ring without NVLS: 1.08-1.38 ms).  The all-reduce alone takes 56 us at
-        # 8 GPUs whatever the setting (tools/allreduce_probe.py).  An explicit setting in the environment wins.
-        os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")
-        os.environ.setdefault("NCCL_NVLS_NCHANNELS", "2")
+        # channel NCCL opens is a CTA on an SM those kernels are waiting for (144 gather CTAs on 148 SMs), but too few channels
+        # make the all-reduce longer than the window it hides in.  Measured per batch, in-graph, B200 (profiles/r02_bench_*gpu*):
+        #   2 GPUs (ring):  0.825 ms with NCCL's defaults, 0.806 with NCCL_MAX_NCHANNELS=2, 0.841 with 8;
+        #   4 GPUs:         0.821 ms with the defaults, 0.891 with NCCL_MAX_NCHANNELS=2, 0.994 with 4, 0.832 with NVLS_NCHANNELS=2;
+        #   8 GPUs (NVLS):  0.858 ms with the defaults (24 NVLS channels; NCCL_MAX_NCHANNELS makes no difference), 0.839 with
+        #                   NCCL_NVLS_NCHANNELS=2; ring without NVLS 1.08-1.38 ms.
+        # The all-reduce alone takes 56 us at 8 GPUs whatever the setting (tools/allreduce_probe.py).  So: two ring channels
+        # at 2 GPUs, NCCL's own choice at 4, two NVLS channels at 8 and beyond; an explicit setting in the environment wins.
+        if world == 2:
+            os.environ.setdefault("NCCL_MAX_NCHANNELS", "2")
+        elif world >= 8:
+            os.environ.setdefault("NCCL_NVLS_NCHANNELS", "2")
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
         if backend == "nccl":

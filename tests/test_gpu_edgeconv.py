@@ -103,7 +103,8 @@ def test_fused_layer_vs_reference_layers_golden(hb, golden, tag, mode):
 
 
 @pytest.mark.parametrize("B,C,N,k,two,train", [(3, 21, 200, 20, True, True), (2, 21, 333, 10, True, False), (2, 1, 256, 20, True, True),
-                                                (2, 21, 150, 40, False, True), (1, 21, 77, 7, True, True), (4, 21, 128, 20, False, False)])
+                                                (2, 21, 150, 40, False, True), (1, 21, 77, 7, True, True), (4, 21, 128, 20, False, False),
+                                                (2, 5, 130, 12, True, True), (1, 2, 64, 8, False, True)])
 def test_fused_layer_vs_oracle_fp64(hb, B, C, N, k, two, train):
     from hpcs_b200.edgeconv import edgeconv
     gen = torch.Generator().manual_seed(B * 1000 + N + k)
