@@ -19,7 +19,7 @@ _LOCK = threading.Lock()
 _LIB: Optional[ctypes.CDLL] = None
 _DEVICE_OK = set()
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # name -> (restype, argtypes); mirrors include/hpcs_b200.h one to one
 _P, _I, _L, _F, _Z = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_float, _c.c_size_t
@@ -59,6 +59,7 @@ SIGNATURES = {
     "hpcs_cut_scores_f64": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "hpcs_rotate_points_f32": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
     "hpcs_one_hot_f32": (_I, [_P, _L, _I, _P, _P]),
+    "hpcs_cosface_logits_f32": (_I, [_P, _P, _P, _L, _I, _I, _F, _F, _P, _P]),
     "hpcs_edgeconv_bn_fold_f32": (_I, [_P, _L, _P, _P, _P, _P, _P, _F, _F, _I, _P, _I, _P]),
     "hpcs_edgeconv_bn_sums_f32": (_I, [_P, _P, _P, _I, _I, _I, _I, _P, _P, _I, _P, _P, _P]),
     "hpcs_edgeconv_bn_sums_finish_f32": (_I, [_P, _L, _I, _P, _I, _P, _P, _P]),

@@ -75,7 +75,70 @@ one_hot_kernel(const int64_t* __restrict__ y, int64_t rows, int classes, float* 
     }
 }
 
+// logits[i][c] = scale * (e_i . w_c / (max(|e_i|, eps) max(|w_c|, eps)) - margin * [labels[i] == c]): the metrics-side CosFace logits.
+// A block stages the normalised class directions once (shared memory, odd row stride) and walks 64-row groups of embeddings;
+// thread -> (row, class) pairs with the class index fastest, so the logits leave in coalesced rows.
+constexpr int kLgRows = 64;
+__global__ void __launch_bounds__(256)
+cosface_logits_kernel(const float* __restrict__ emb, const float* __restrict__ W, const int64_t* __restrict__ labels, int64_t n, int D,
+                      int classes, float margin, float scale, float* __restrict__ logits) {
+    extern __shared__ float lg_sm[];
+    const int S = D + 1;
+    float* wn = lg_sm;                                   // [classes][S] normalised columns of W
+    float* es = wn + (size_t)classes * S;                // [kLgRows][S] normalised embedding rows
+    for (int c = threadIdx.x; c < classes; c += blockDim.x) {
+        float s2 = 0.f;
+        for (int d = 0; d < D; ++d) { const float w = W[(size_t)d * classes + c]; s2 = fmaf(w, w, s2); }
+        const float inv = 1.f / fmaxf(sqrtf(s2), 1e-12f);           // F.normalize(p=2, eps=1e-12)
+        for (int d = 0; d < D; ++d) wn[c * S + d] = W[(size_t)d * classes + c] * inv;
+    }
+    const int64_t groups = (n + kLgRows - 1) / kLgRows;
+    for (int64_t g = blockIdx.x; g < groups; g += gridDim.x) {
+        const int64_t r0 = g * kLgRows;
+        const int nr = (int)((n - r0) < kLgRows ? (n - r0) : kLgRows);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nr * D; i += blockDim.x) es[(i / D) * S + i % D] = emb[r0 * D + i];
+        __syncthreads();
+        for (int r = threadIdx.x >> 5; r < nr; r += blockDim.x >> 5) {      // one warp per row: its norm
+            float s2 = 0.f;
+            for (int d = threadIdx.x & 31; d < D; d += 32) s2 = fmaf(es[r * S + d], es[r * S + d], s2);
+            s2 = warp_sum(s2);
+            const float inv = 1.f / fmaxf(sqrtf(s2), 1e-12f);
+            for (int d = threadIdx.x & 31; d < D; d += 32) es[r * S + d] *= inv;
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < nr * classes; t += blockDim.x) {
+            const int r = t / classes, c = t - r * classes;
+            const float* e = es + r * S;
+            const float* w = wn + c * S;
+            float acc = 0.f;
+            for (int d = 0; d < D; ++d) acc = fmaf(e[d], w[d], acc);
+            const float m = labels[r0 + r] == c ? margin : 0.f;
+            logits[(r0 + r) * classes + c] = (acc - m) * scale;
+        }
+    }
+}
+
 }  // namespace hpcs
+
+extern "C" int hpcs_cosface_logits_f32(const float* emb, const float* W, const int64_t* labels, int64_t n, int D, int classes, float margin,
+                                       float scale, float* logits, void* stream) {
+    using namespace hpcs;
+    if (n == 0) return HPCS_OK;
+    if (!emb || !W || !labels || !logits || n < 0 || D <= 0 || classes <= 0) return fail(HPCS_ERR_ARG, "cosface_logits: bad arguments");
+    const size_t smem = ((size_t)classes + kLgRows) * (D + 1) * sizeof(float);
+    if (smem > 200 * 1024) return fail(HPCS_ERR_ARG, "cosface_logits: classes=%d x D=%d does not fit shared memory", classes, D);
+    static thread_local size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        cudaFuncSetAttribute(cosface_logits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = smem;
+    }
+    int64_t groups = (n + kLgRows - 1) / kLgRows;
+    const int64_t cap = 4 * (int64_t)sm_count();
+    cosface_logits_kernel<<<(int)(groups < cap ? groups : cap), 256, smem, as_stream(stream)>>>(emb, W, labels, n, D, classes, margin, scale,
+                                                                                             logits);
+    return check_launch("cosface_logits_kernel");
+}
 
 extern "C" int hpcs_rotate_points_f32(const float* pts, const float* params, int mode, int B, int N, float* out,
                                       float* rot_out, void* stream) {

@@ -15,6 +15,8 @@ from __future__ import annotations
 
 from typing import Optional, Tuple, Union
 
+import weakref
+
 import torch
 import torch.nn.functional as F
 
@@ -457,6 +459,46 @@ class HierarchicalMetricHyperbolicLoss(MetricHyperbolicLoss):
 # ------------------------------------------------------------------------------------------------
 # methods bound onto the REFERENCE's own classes by hpcs_b200.patch (attribute names are the reference's)
 # ------------------------------------------------------------------------------------------------
+def cosface_logits(embeddings: torch.Tensor, W: torch.Tensor, labels: torch.Tensor, margin: float, scale: float) -> torch.Tensor:
+    """``scale * (cos(emb_i, W_c) - margin * [labels_i == c])`` in one kernel, forward only (no autograd graph): the logits the
+    reference's metrics are computed from (hpcs/loss/ultrametric_loss.py:95-112)."""
+    dev = _lib.require_cuda(embeddings, W, labels)
+    lib = _lib.load()
+    e = embeddings.detach().contiguous().float()
+    w = W.detach().contiguous().float()
+    if e.dim() != 2 or w.dim() != 2 or w.shape[0] != e.shape[1]:
+        raise ValueError(f"cosface_logits: embeddings {tuple(e.shape)} vs W {tuple(w.shape)}")
+    y = labels.detach().reshape(-1).contiguous().long()
+    if y.numel() != e.shape[0]:
+        raise ValueError("cosface_logits: one label per embedding row")
+    out = torch.empty(e.shape[0], w.shape[1], device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        _lib.check(lib.hpcs_cosface_logits_f32(e.data_ptr(), w.data_ptr(), y.data_ptr(), e.shape[0], e.shape[1], w.shape[1],
+                                               float(margin), float(scale), out.data_ptr(), _lib.stream_ptr(dev)),
+                   "hpcs_cosface_logits_f32")
+    return out
+
+
+def native_get_logits(self, embeddings, labels):
+    """Bound onto ``MetricHyperbolicLoss.get_logits`` (hpcs/loss/ultrametric_loss.py:95-112).  The reference calls it twice per
+    step with the same tensors (accuracy and IoU, hpcs/models/base_hyp_hc.py:88-99) and each call runs a matmul, a one-hot mask
+    and a boolean-mask gather that synchronises the host; here: one kernel, no synchronisation, and the second call of a step
+    returns the first one's result (same tensor objects, same versions, same weight).  Forward only: the callers are metrics."""
+    if not hasattr(self, "loss_cosface"):
+        raise ValueError("Cannot get logits since this class doesn't use any CosFaceLoss")
+    lc = self.loss_cosface
+    if hasattr(lc, "cast_types"):
+        lc.cast_types(embeddings.dtype, embeddings.device)
+    W = lc.W
+    key = (embeddings._version, labels._version, W._version, W.data_ptr())
+    cached = getattr(self, "_hpcs_logits_cache", None)
+    if cached is not None and cached[0]() is embeddings and cached[1]() is labels and cached[2] == key:
+        return cached[3]
+    logits = cosface_logits(embeddings, W, labels, lc.margin, lc.scale)
+    object.__setattr__(self, "_hpcs_logits_cache", (weakref.ref(embeddings), weakref.ref(labels), key, logits))
+    return logits
+
+
 def native_mine(self, embeddings, labels, ref_emb=None, ref_labels=None):
     """``RandomTripletMarginMiner.mine`` (hpcs/miner/triplet_margin_miner.py:13-38) without the [n,n] matrix: the
     reference's sampler order and RNG draws, the margin test by ``hpcs_triplet_filter_f32``."""

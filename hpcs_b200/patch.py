@@ -101,6 +101,7 @@ def _triplet_margin_compute_loss(self, embeddings, labels, indices_tuple, ref_em
 # (defining module, class name, method name) -> replacement
 METHODS: Dict[Tuple[str, str, str], object] = {
     ("hpcs.loss.ultrametric_loss", "MetricHyperbolicLoss", "compute_hyp"): loss.native_compute_hyp,
+    ("hpcs.loss.ultrametric_loss", "MetricHyperbolicLoss", "get_logits"): loss.native_get_logits,
     ("hpcs.miner.triplet_margin_miner", "RandomTripletMarginMiner", "mine"): loss.native_mine,
     ("hpcs.miner.triplet_margin_loss", "TripletMarginLoss", "compute_loss"): _triplet_margin_compute_loss,
     ("hpcs.nn.hyperbolic.hyp_embed", "ExpMap", "forward"): _expmap_forward,

@@ -28,7 +28,7 @@ extern "C" {
  * 3: + hpcs_triplet_sample_state_i32, hpcs_rotate_points_f32, hpcs_one_hot_f32, hpcs_peak_probe,
  *    hpcs_vn_point_linear_f32, hpcs_edgeconv_* (round 2; additions only)
  */
-#define HPCS_ABI_VERSION 3
+#define HPCS_ABI_VERSION 4
 
 enum {
     HPCS_OK = 0,
@@ -201,6 +201,14 @@ int hpcs_rotate_points_f32(const float* pts, const float* params, int mode, int 
 /* to_categorical(y, num_classes)   hpcs/utils/data.py:24-29: y[rows] int64 -> out[rows, num_classes] fp32 one-hot
  * (a row of zeros for a label outside [0, num_classes), where torch.eye indexing would raise). */
 int hpcs_one_hot_f32(const int64_t* y, int64_t rows, int num_classes, float* out, void* stream);
+/* MetricHyperbolicLoss.get_logits(embeddings, labels)   hpcs/loss/ultrametric_loss.py:95-112, called twice per step for the
+ * accuracy / IoU metrics (hpcs/models/base_hyp_hc.py:88-99) next to the loss's own evaluation.  The reference assembles it from
+ * pytorch-metric-learning CosFaceLoss pieces (get_cosine, get_target_mask, a boolean-mask gather that synchronises the host,
+ * modify_cosine_of_target_classes, scale_logits); here one forward-only kernel:
+ *   emb[n,D] fp32, W[D,classes] fp32 (the loss's weight), labels[n] int64 ->
+ *   logits[n,classes] = scale * (cos(emb_i, W_c) - margin * [labels_i == c]),  rows and columns normalised like F.normalize. */
+int hpcs_cosface_logits_f32(const float* emb, const float* W, const int64_t* labels, int64_t n, int D, int classes, float margin,
+                            float scale, float* logits, void* stream);
 
 /* ---- fused EdgeConv layer    -------------------------------------------------------------------------
  * x = get_graph_feature(x, k); x = convA(x); [x = convB(x);] x = mean_pool(x)

@@ -270,6 +270,20 @@ def compute_hyp(x, a, p, n, scale, temperature: float):
     return per_triplet.mean() + sim.mean()                              # :91
 
 
+def cosface_logits(embeddings: torch.Tensor, W: torch.Tensor, labels: torch.Tensor, margin: float, scale: float) -> torch.Tensor:
+    """``MetricHyperbolicLoss.get_logits`` (hpcs/loss/ultrametric_loss.py:95-112), statement by statement, with the members of
+    pytorch-metric-learning 1.6.3 ``CosFaceLoss`` it calls written out (third-party, not under /root/reference: ``get_cosine``
+    = cosine of the L2-normalised rows and columns, ``get_target_mask`` = one-hot, ``modify_cosine_of_target_classes`` =
+    ``c - margin``, ``scale_logits`` = ``logits * scale``)."""
+    mask = F.one_hot(labels.long(), W.shape[1]).to(embeddings.dtype)                     # :99
+    cosine = F.normalize(embeddings, p=2, dim=1) @ F.normalize(W, p=2, dim=0)           # :100
+    cosine_of_target_classes = cosine[mask == 1]                                        # :101
+    modified = cosine_of_target_classes - margin                                        # :102-104
+    diff = (modified - cosine_of_target_classes).unsqueeze(1)                           # :105-107
+    logits = cosine + (mask * diff)                                                     # :108
+    return logits * scale                                                               # :109
+
+
 # --------------------------------------------------------------------------------------------
 # part 3: linkage decode
 # --------------------------------------------------------------------------------------------

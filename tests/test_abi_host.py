@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in names:
         assert hasattr(lib, name), f"{name} declared in include/hpcs_b200.h but not exported"
     assert sorted(_lib.SIGNATURES) == names            # the ctypes table mirrors the header one to one
-    assert lib.hpcs_abi_version() == _lib.ABI_VERSION == 3
+    assert lib.hpcs_abi_version() == _lib.ABI_VERSION == 4
     assert _lib.launch_count() == 0 or torch.cuda.is_available()
 
 

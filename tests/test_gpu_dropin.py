@@ -378,3 +378,41 @@ def test_sampler_state_advances_under_graph_replay():
     g.replay()
     torch.cuda.synchronize()
     assert all(torch.equal(x, y) for x, y in zip(out, draws[1]))
+
+
+@pytest.mark.parametrize("n,D,classes", [(1000, 32, 50), (8192, 4, 39), (65, 16, 1), (3, 7, 130)])
+def test_cosface_logits_kernel_vs_oracle(n, D, classes):
+    """``hpcs_cosface_logits_f32`` against the restated ``get_logits`` (ultrametric_loss.py:95-112): ragged row counts,
+    a zero embedding row (F.normalize's eps), PartNet's 4-d embeddings."""
+    from hpcs_b200.loss import cosface_logits
+    gen = torch.Generator().manual_seed(n + classes)
+    emb = torch.randn(n, D, generator=gen) * 0.3
+    emb[0] = 0.0
+    W = torch.randn(D, classes, generator=gen)
+    y = torch.randint(0, classes, (n,), generator=gen)
+    got = cosface_logits(emb.cuda(), W.cuda(), y.cuda(), 0.35, 64.0).cpu()
+    want = O.cosface_logits(emb.double(), W.double(), y, 0.35, 64.0)
+    assert got.shape == (n, classes)
+    assert (got.double() - want).abs().max().item() < 1e-4 * 64.0
+
+
+def test_get_logits_through_patched_names_is_memoised(tree):
+    """``MetricHyperbolicLoss.get_logits`` (bound method of the reference-side class): equal to the reference formula, the
+    second call of a step with the same tensors returns the first result, an in-place weight update invalidates it."""
+    hpcs = tree
+    from hpcs.loss.ultrametric_loss import MetricHyperbolicLoss
+    torch.manual_seed(3)
+    loss = MetricHyperbolicLoss(num_class=50, embedding_size=32, cosface=True, miner=True).cuda()
+    x = (torch.randn(4096, 32) * 0.2).cuda()
+    y = torch.randint(0, 50, (4096,)).cuda()
+    a = loss.get_logits(x, y)
+    lc = loss.loss_cosface
+    want = O.cosface_logits(x.cpu().double(), lc.W.detach().cpu().double(), y.cpu(), lc.margin, lc.scale)
+    assert (a.cpu().double() - want).abs().max().item() < 1e-4 * lc.scale
+    assert loss.get_logits(x, y) is a
+    with torch.no_grad():
+        lc.W.mul_(-1.0)
+    b = loss.get_logits(x, y)
+    assert b is not a and not torch.equal(a, b)
+    x2 = x.clone()
+    assert loss.get_logits(x2, y) is not b

@@ -68,6 +68,8 @@ def test_cosface_and_logits_match_reference(refmods):
     x = (torch.randn(64, 5) * 0.2).requires_grad_(True)
     y = torch.randint(0, 7, (64,))
     assert torch.allclose(ours.get_logits(x, y), theirs.get_logits(x, y), atol=1e-6)
+    lc = theirs.loss_cosface                            # the oracle's restatement (what the GPU kernel is tested against)
+    assert torch.allclose(O.cosface_logits(x, lc.W, y, lc.margin, lc.scale), theirs.get_logits(x, y), atol=1e-6)
     lo, lt = ours.loss_cosface(x, y), theirs.loss_cosface(x, y)
     assert torch.allclose(lo, lt, atol=1e-6)
     go, gt = torch.autograd.grad(lo, x)[0], torch.autograd.grad(lt, x)[0]
