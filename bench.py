@@ -472,6 +472,7 @@ def run_native(args):
     probes = peak_probes.measure(dev)
     decode_rec = decode_subrecord(hb, dev, rank) if not args.no_decode else None
     edgeconv_rec = edgeconv_subrecord(hb, dev, B, rank) if not args.no_decode else None
+    model_rec = model_step_subrecord(dev, B, rank) if not args.no_decode else None
     barrier()
     sampler.region = "e2e"
     e2e_dev = run_e2e("device")
@@ -558,6 +559,7 @@ def run_native(args):
         "ops": ops,
         "decode": decode_rec,
         "edgeconv": edgeconv_rec,
+        "model_step": model_rec,
         "loss": loss_val,
         "e2e_loss": e2e_pts["loss"],
         "e2e_loss_host_sampled": e2e_host["loss"],
@@ -684,6 +686,94 @@ def edgeconv_subrecord(hb, dev, B, rank, reps=5):
         del convs, params, x, gout, idx
         torch.cuda.empty_cache()
     rec["three_layers_fwd_bwd_ms"] = {"fused": round(tot_f, 4), "unfused": round(tot_u, 4), "speedup": round(tot_u / tot_f, 2)}
+    return rec
+
+
+def model_step_subrecord(dev, B, rank, reps=10, warm=3):
+    """SURVEY 8d's "end-to-end clouds/s": one whole training step of the model -- VN_DGCNN_partseg + ExpMap + compute_loss,
+    forward, backward and the optimizer step (RAdam, like configure_optimizers) -- through the reference-facing names with the
+    binding installed, batch taken from HOST tensors as the data loader yields them.  The reference tree cannot travel to the GPU
+    box, so the model is the stand-in tree of tests/fake_reference built at the reference's layer shapes (tail_width 1024 // 3:
+    conv8 takes 2299 channels, 1 303 850 backbone parameters, the reference's count); its hot-path entry points raise if they
+    are reached unbound.  Graph layers, kNN, loss, sampler-side filter and input pipeline are this library; the dense tail
+    (conv6, the std-feature layers, conv7-11), the CosFace term and the optimizer are PyTorch library ops, outside the path.
+    Eager launches, host overhead included; CUDA events around `reps` steps after `warm`."""
+    if rank != 0:
+        return None
+    fake = os.path.join(ROOT, "tests", "fake_reference")
+    saved = {m: sys.modules.pop(m) for m in list(sys.modules) if m == "hpcs" or m.startswith("hpcs.") or m == "train"}
+    sys.path.insert(0, fake)
+    from hpcs_b200 import _lib, patch
+    rec = None
+    try:
+        import hpcs.models, hpcs.nn.dgcnn, hpcs.nn.pointnet, hpcs.nn.hyperbolic   # noqa: F401,E401  (import BEFORE install, like train.py)
+        patch.uninstall()
+        patch.install(strict=True)
+        from hpcs.models import ShapeNetHypHC
+        from hpcs.nn.dgcnn import VN_DGCNN_partseg
+        from hpcs.nn.hyperbolic import ExpMap
+        VN_DGCNN_partseg.tail_width = 1024 // 3
+        torch.manual_seed(0)
+        model = ShapeNetHypHC(nn_feat=VN_DGCNN_partseg(3, D_EMB, K_NN, 0.5, "mean", 16), nn_emb=ExpMap(), euclidean_size=D_EMB,
+                              hyp_size=D_EMB, num_class=50, t_per_anchor=T_PER_ANCHOR, fraction=0.0, temperature=TEMPERATURE,
+                              miner=True).to(dev).train()
+        params = sum(p.numel() for p in model.nn_feat.parameters())
+        opt = torch.optim.RAdam(model.parameters(), lr=1e-3)
+        host = synth_inputs(B, 1234)
+        pts = host["pts"].view(B, 3, N_PTS).transpose(1, 2).contiguous()          # [B,N,3], what the data loader yields
+        targets = host["labels"].view(B, N_PTS)
+        label = torch.randint(0, 16, (B, 1), generator=torch.Generator().manual_seed(5))
+        out = {}
+
+        def step(backward=True):
+            losses, _ = model.forward((pts, label, targets), testing=False)
+            total = losses["loss_metric"] + losses["loss_hyp"]
+            if backward:
+                opt.zero_grad(set_to_none=True)
+                total.backward()
+                opt.step()
+            out["loss"] = total.detach()
+
+        def timed(fn):
+            for _ in range(warm):
+                fn()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = _lib.launch_count()
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            return e0.elapsed_time(e1) / reps, (_lib.launch_count() - l0) // reps
+
+        torch.cuda.reset_peak_memory_stats(dev)
+        ms_ref_sampler, _ = timed(step)                      # default binding: the reference's host sampler (RNG-exact)
+        patch.install(strict=True, sampler="device")         # row f-3: triplets drawn on the GPU, no host sampling / index upload
+        ms_step, launches = timed(step)
+        with torch.no_grad():
+            ms_fwd, _ = timed(lambda: step(False))
+        rec = {"ms_per_step": round(ms_step, 3), "clouds_per_s": round(B / (ms_step * 1e-3), 1), "forward_only_ms": round(ms_fwd, 3),
+               "ms_per_step_host_sampler": round(ms_ref_sampler, 3), "clouds_per_s_host_sampler": round(B / (ms_ref_sampler * 1e-3), 1),
+               "sampler": "device (install(sampler='device')); *_host_sampler = the default binding, the reference's CPU sampler with identical RNG draws",
+               "batch": B, "native_launches_per_step": int(launches), "backbone_params": int(params),
+               "peak_mem_gb": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 2), "loss": float(out["loss"]),
+               "what": "VN_DGCNN_partseg + ExpMap + compute_loss, fwd + bwd + RAdam step, host batch in, binding installed "
+                       "(hpcs_b200.patch.install(strict=True)); stand-in tree at the reference's layer shapes; eager, host overhead included",
+               "optimizer": "RAdam", "timing": f"{reps} steps between CUDA events after {warm} warm-up steps"}
+    except Exception as exc:                                  # the sub-record must never take the bench line down
+        rec = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+    finally:
+        try:
+            patch.uninstall()
+            sys.modules["hpcs.nn.dgcnn"].VN_DGCNN_partseg.tail_width = 32
+        except Exception:
+            pass
+        if fake in sys.path:
+            sys.path.remove(fake)
+        for m in [m for m in sys.modules if m == "hpcs" or m.startswith("hpcs.")]:
+            del sys.modules[m]
+        sys.modules.update(saved)
     return rec
 
 

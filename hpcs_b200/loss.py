@@ -499,12 +499,29 @@ def native_get_logits(self, embeddings, labels):
     return logits
 
 
+# Which sampler the BOUND methods use (hpcs_b200.patch.install(sampler=...)): "reference" = the reference's sampler on the host,
+# torch RNG stream and draws identical to an unpatched run (one device->host copy of the labels, three index uploads per step);
+# "device" = the Philox sampler on the GPU (row f-3): same anchors in the same order, positives / negatives from the same
+# distributions but a different stream, no host work, key derived from torch.initial_seed().
+BOUND_SAMPLER = "reference"
+
+
+def _bound_sample(owner, labels, t_per_anchor, fraction):
+    if BOUND_SAMPLER == "device" and labels.is_cuda:
+        st = getattr(owner, "_hpcs_sampler_state", None)
+        if st is None or st.device != labels.device:
+            st = sampler_state(torch.initial_seed(), labels.device)
+            object.__setattr__(owner, "_hpcs_sampler_state", st)
+        return sample_triplets_device(labels, t_per_anchor, fraction, state=st)
+    return get_balanced_random_triplet_indices(labels, t_per_anchor=t_per_anchor, fraction=fraction)
+
+
 def native_mine(self, embeddings, labels, ref_emb=None, ref_labels=None):
     """``RandomTripletMarginMiner.mine`` (hpcs/miner/triplet_margin_miner.py:13-38) without the [n,n] matrix: the
-    reference's sampler order and RNG draws, the margin test by ``hpcs_triplet_filter_f32``."""
-    a, p, n = get_balanced_random_triplet_indices(labels, t_per_anchor=self.t_per_anchor, fraction=self.fraction)
+    reference's sampler order (and, with the default sampler, its RNG draws), the margin test by ``hpcs_triplet_filter_f32``."""
+    a, p, n = _bound_sample(self, labels, self.t_per_anchor, self.fraction)
     keep = filter_triplets(embeddings, a, p, n, self.margin, self.type_of_triplets)
-    return a[keep], p[keep], n[keep]
+    return a[keep].long(), p[keep].long(), n[keep].long()
 
 
 def native_compute_hyp(self, x_poincare, labels):
@@ -513,7 +530,7 @@ def native_compute_hyp(self, x_poincare, labels):
     ``hyp_miner``, ``scale``, ``temperature``) and never calls ``self.hyp_miner`` / ``self.distance_sim``."""
     if self.miner:
         m = self.hyp_miner
-        triplets = get_balanced_random_triplet_indices(labels, t_per_anchor=m.t_per_anchor, fraction=m.fraction)
+        triplets = _bound_sample(self, labels, m.t_per_anchor, m.fraction)
         kind, margin = m.type_of_triplets, m.margin
     else:
         triplets, kind, margin = self.get_triplets(x_poincare.shape[0]), "none", 0.0

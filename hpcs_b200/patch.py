@@ -23,6 +23,7 @@ on the reference path); ``verify()`` re-checks the binding at any later time.
 from __future__ import annotations
 
 import importlib
+import os
 import sys
 import warnings
 from typing import Dict, List, Tuple
@@ -141,9 +142,17 @@ def _rebind_aliases(original, replacement) -> List[str]:
     return done
 
 
-def install(strict: bool = True) -> List[str]:
+def install(strict: bool = True, sampler: str = None) -> List[str]:
     """Bind every target; returns the fully qualified names now on the native path.  A target that cannot be bound
-    raises :class:`PatchError` (``strict``) or is reported by one warning."""
+    raises :class:`PatchError` (``strict``) or is reported by one warning.
+    ``sampler``: which triplet sampler the bound loss / miner methods use -- "reference" (default: the reference's host sampler,
+    identical torch RNG draws) or "device" (Philox on the GPU, no host work per step, distributionally equal); None reads the
+    environment variable HPCS_B200_SAMPLER, else "reference"."""
+    if sampler is None:
+        sampler = os.environ.get("HPCS_B200_SAMPLER", "reference")
+    if sampler not in ("reference", "device"):
+        raise ValueError("sampler must be 'reference' or 'device'")
+    loss.BOUND_SAMPLER = sampler
     done, failed = [], []
     for (mod_name, attr), repl in FUNCTIONS.items():
         try:

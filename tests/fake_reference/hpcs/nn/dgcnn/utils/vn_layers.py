@@ -10,10 +10,14 @@ class VNBatchNorm(torch.nn.Module):
         self.bn = torch.nn.BatchNorm2d(num_features) if dim == 5 else torch.nn.BatchNorm1d(num_features)
 
 
+EPS = 1e-6
+
+
 class VNLinearLeakyReLU(torch.nn.Module):
     """Parameters where the reference keeps them (map_to_feat, map_to_dir, batchnorm.bn).  The 5-D (edge tensor) form is a
     hot-path consumer: calling it means the fused layer was not bound.  The 4-D form (conv6 / std-feature, outside the
-    path) is a plain channel mix so the dense tail of the backbone can run."""
+    path) does the layer's arithmetic with library ops -- Linear over channels, BatchNorm on the vector norms, leaky
+    projection onto the learnt direction -- so the dense tail of the backbone runs at its real cost."""
 
     def __init__(self, in_channels, out_channels, dim=5, share_nonlinearity=False, negative_slope=0.2):
         super().__init__()
@@ -26,17 +30,26 @@ class VNLinearLeakyReLU(torch.nn.Module):
         if x.dim() == 5:
             raise ReferencePathReached("VNLinearLeakyReLU on the [B,2C,3,N,k] edge tensor")
         p = self.map_to_feat(x.transpose(1, -1)).transpose(1, -1)
+        norm = p.norm(dim=2) + EPS
+        p = p / norm.unsqueeze(2) * self.batchnorm.bn(norm).unsqueeze(2)
         d = self.map_to_dir(x.transpose(1, -1)).transpose(1, -1)
-        return p + 0.1 * d.expand_as(p)
+        dot = (p * d).sum(2, keepdim=True)
+        keep = (dot >= 0).to(p.dtype)
+        proj = p - (dot / ((d * d).sum(2, keepdim=True) + EPS)) * d
+        s = self.negative_slope
+        return s * p + (1 - s) * (keep * p + (1 - keep) * proj)
 
 
 class VNStdFeature(torch.nn.Module):
-    def __init__(self, in_channels, dim=4, normalize_frame=False):
+    def __init__(self, in_channels, dim=4, normalize_frame=False, share_nonlinearity=False, negative_slope=0.2):
         super().__init__()
-        self.vn_lin = torch.nn.Linear(in_channels, 3, bias=False)
+        self.vn1 = VNLinearLeakyReLU(in_channels, in_channels // 2, dim=dim, share_nonlinearity=share_nonlinearity, negative_slope=negative_slope)
+        self.vn2 = VNLinearLeakyReLU(in_channels // 2, in_channels // 4, dim=dim, share_nonlinearity=share_nonlinearity, negative_slope=negative_slope)
+        self.vn_lin = torch.nn.Linear(in_channels // 4, 3, bias=False)
 
     def forward(self, x):
-        z0 = self.vn_lin(x.transpose(1, -1)).transpose(1, -1).transpose(1, 2)       # [B,3,3,N]
+        z0 = self.vn2(self.vn1(x))
+        z0 = self.vn_lin(z0.transpose(1, -1)).transpose(1, -1).transpose(1, 2)       # [B,3,3,N]
         return torch.einsum('bijm,bjkm->bikm', x, z0), z0
 
 

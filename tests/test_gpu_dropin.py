@@ -416,3 +416,39 @@ def test_get_logits_through_patched_names_is_memoised(tree):
     assert b is not a and not torch.equal(a, b)
     x2 = x.clone()
     assert loss.get_logits(x2, y) is not b
+
+
+def test_device_sampler_binding(tree):
+    """``install(sampler='device')``: the bound ``compute_hyp`` draws its triplets on the GPU (row f-3) -- same anchors in the
+    same order as the reference sampler, fresh draws per call, loss close to the host-sampled one (both are Monte-Carlo
+    estimates over 50 triplets per anchor of the same quantity); the default binding is put back afterwards."""
+    hpcs = tree
+    import hpcs_b200.patch as patch
+    from hpcs_b200 import loss as L
+    from hpcs.loss.ultrametric_loss import MetricHyperbolicLoss
+    torch.manual_seed(11)
+    gen = torch.Generator().manual_seed(11)
+    obj = MetricHyperbolicLoss(num_class=50, embedding_size=32, cosface=True, miner=True, t_per_anchor=50, fraction=0.0,
+                               scale=torch.nn.Parameter(torch.tensor([1e-3]))).cuda()
+    labels = shapenet_labels(gen, 4, 512).reshape(-1).cuda()
+    u = torch.randn(4 * 512, 32, generator=gen)
+    x = (torch.tanh(u.norm(dim=-1, keepdim=True)) * u / u.norm(dim=-1, keepdim=True)).cuda().requires_grad_(True)
+    try:
+        patch.install(strict=True, sampler="device")
+        assert L.BOUND_SAMPLER == "device"
+        before = launches()
+        l1 = obj.compute_hyp(x, labels)
+        l2 = obj.compute_hyp(x, labels)
+        assert launches() - before >= 2 * 2
+        g = torch.autograd.grad(l1, x)[0]
+        assert torch.isfinite(g).all() and g.abs().max().item() > 0
+        assert l1.item() != l2.item()                                   # the key advances on the device: fresh triplets
+        a_dev = L._bound_sample(obj, labels, 50, 0.0)[0].long().cpu()
+        patch.install(strict=True, sampler="reference")
+        a_ref = L._bound_sample(obj, labels, 50, 0.0)[0].cpu()
+        assert torch.equal(a_dev, a_ref)                                # anchors: identical order
+        l_ref = obj.compute_hyp(x, labels)
+        assert abs(l1.item() - l_ref.item()) < 0.05 * abs(l_ref.item())
+    finally:
+        patch.install(strict=True, sampler="reference")
+    assert L.BOUND_SAMPLER == "reference"
