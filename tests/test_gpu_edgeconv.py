@@ -106,6 +106,16 @@ def test_fused_layer_vs_reference_layers_golden(hb, golden, tag, mode):
                                                 (2, 21, 150, 40, False, True), (1, 21, 77, 7, True, True), (4, 21, 128, 20, False, False),
                                                 (2, 5, 130, 12, True, True), (1, 2, 64, 8, False, True)])
 def test_fused_layer_vs_oracle_fp64(hb, B, C, N, k, two, train):
+    layer_case(hb, B, C, N, k, two, train)
+
+
+def layer_case(hb, B, C, N, k, two, train, conditioning_aware=False):
+    """One fused layer against the fp64 oracle.  ``conditioning_aware`` (tools/stress_edgeconv.py): the layer is not
+    continuous -- the direction test ``dot >= 0`` switches a term of the gradient on and off, and ``|p| -> 0`` has a
+    ``1/|p|`` gradient -- so over random shapes a few per cent of the layers hold an (edge, channel) pair within fp32
+    rounding of a discontinuity, and ANY fp32 evaluation is then 1e-4..1e-3 off fp64 in some gradient.  The bar of a gradient
+    becomes max(1e-4, 3 x the largest change of the fp64 ORACLE's own gradient when its inputs and weights are perturbed by
+    1e-6 relative, three draws): it stays 1e-4 wherever the reference function is smooth at fp32 resolution."""
     from hpcs_b200.edgeconv import edgeconv
     gen = torch.Generator().manual_seed(B * 1000 + N + k)
     torch.manual_seed(N + k)
@@ -135,6 +145,18 @@ def test_fused_layer_vs_oracle_fp64(hb, B, C, N, k, two, train):
         y32 = O.edgeconv_layer(x32, idx.cpu(), o32, training=train)
         g32 = torch.autograd.grad((y32 * gout).sum(), [x32] + [c[n] for c in o32 for n in ("wf", "wd", "gamma", "beta")])
         bars = [max(REL, 5 * nrm_err(a, b)) for a, b in zip(g32, wgrads)]
+    if conditioning_aware:
+        pg = torch.Generator().manual_seed(99)
+        worst = [0.0] * len(wgrads)
+        for _ in range(3):
+            jit = lambda t: (t.detach() * (1 + 1e-6 * torch.randn(t.shape, generator=pg, dtype=t.dtype))).requires_grad_(True)   # noqa: E731
+            op = [dict(c, wf=jit(c["wf"]), wd=jit(c["wd"]), gamma=jit(c["gamma"]), beta=jit(c["beta"]),
+                       running_mean=c["running_mean"].clone(), running_var=c["running_var"].clone()) for c in [cv.as_oracle() for cv in convs]]
+            xp = jit(x.double())
+            yp = O.edgeconv_layer(xp, idx.cpu(), op, training=train)
+            gp = torch.autograd.grad((yp * gout.double()).sum(), [xp] + [c[n] for c in op for n in ("wf", "wd", "gamma", "beta")])
+            worst = [max(w, nrm_err(a, b)) for w, a, b in zip(worst, gp, wgrads)]
+        bars = [max(b, 3 * w) for b, w in zip(bars, worst)]
     for i, (gg, wg) in enumerate(zip(grads, wgrads)):
         assert nrm_err(gg, wg) < bars[i], (i, nrm_err(gg, wg), bars[i])
     if train:
