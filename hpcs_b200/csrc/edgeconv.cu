@@ -181,21 +181,6 @@ __device__ __forceinline__ void chan_bwd(const ChanFwd& f, float p0, float p1, f
     gp0 = fmaf(gq0, f.s, w * p0); gp1 = fmaf(gq1, f.s, w * p1); gp2 = fmaf(gq2, f.s, w * p2);
 }
 
-// 32 values per lane -> lane l receives the warp-wide sum of v[l]  (31 shuffles instead of 32 x 5)
-__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) {
-        const bool up = (lane & s) != 0;
-#pragma unroll
-        for (int j = 0; j < s; ++j) {
-            const float keep = up ? v[j + s] : v[j];
-            const float send = up ? v[j] : v[j + s];
-            v[j] = keep + __shfl_xor_sync(kFull, send, s);
-        }
-    }
-    return v[0];
-}
-
 // ---- per-point linear maps ------------------------------------------------------------------------------------------
 // x[B,C,3,N], W4[4][21][C] = {Uf, Ud, Vf, Vd} -> UU[B*N][128], VV[B*N][128]
 constexpr int kPlPts = 32;
